@@ -1,0 +1,175 @@
+/* include/mdpy_b200.h — C ABI of libmdpyb200.so, the B200-native (sm_100a) nonbonded
+ * hot path behind mdpy's Constraint / Integrator API.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / numpy /
+ * C++ types), returns an int status (MDK_OK == 0, negative == error, text from
+ * mdk_last_error) and never throws or aborts across the boundary.  Host pointers are
+ * borrowed for the duration of the call only.  One mdk_ctx == one CUDA device == one host
+ * thread at a time (not re-entrant).  File:line citations are relative to the reference
+ * tree (mdpy v0.2.x); INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Units are mdpy's internal ones: angstrom, femtosecond, dalton, e; energy Da*A^2/fs^2
+ * (mdpy/unit/__init__.py:31-41).
+ */
+#ifndef MDPY_B200_H
+#define MDPY_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MDK_API __attribute__((visibility("default")))
+#else
+#define MDK_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdk_ctx mdk_ctx;
+
+/* ---- status codes (mapped by the Python wrapper onto mdpy/error.py classes) ---- */
+enum {
+    MDK_OK = 0,
+    MDK_ERR_BAD_ARG = -1,          /* ValueError / ArrayDimError (mdpy/error.py:37) */
+    MDK_ERR_CUDA = -2,             /* RuntimeError */
+    MDK_ERR_NOT_BOUND = -3,        /* NonBoundedError (mdpy/error.py:87, constraint.py:39-43) */
+    MDK_ERR_CUTOFF_TOO_LARGE = -4, /* CellListPoorDefinedError (mdpy/error.py:123, cell_list.py:58-69) */
+    MDK_ERR_PARTICLE_LOST = -5,    /* ParticleLossError (mdpy/error.py:203, utils/pbc.py:30-34) */
+    MDK_ERR_OOM = -6,
+    MDK_ERR_NCCL = -7,
+    MDK_ERR_NLIST_STALE = -8       /* an atom moved more than skin/2 between rebuilds */
+};
+
+/* ---- force / energy terms (bit flags for mdk_compute, indices into energies[]) ---- */
+enum {
+    MDK_TERM_LJ = 1u << 0,          /* CharmmNonbondedConstraint.update, charmm_nonbonded_constraint.py:183-226 */
+    MDK_TERM_COUL_DIRECT = 1u << 1, /* erfc(alpha r)/r inside rc over the tile list [not in the reference tree] */
+    MDK_TERM_PME_RECIP = 1u << 2,   /* spread -> FFT -> influence function -> IFFT -> gather (+self, background, excluded-pair terms) */
+    MDK_TERM_COUL_BARE = 1u << 3,   /* ElectrostaticConstraint.update, electrostatic_constraint.py:137-174 (all pairs, minimum image) */
+    MDK_TERM_BOND = 1u << 4,        /* charmm_bond_constraint.py:53-73 */
+    MDK_TERM_ANGLE = 1u << 5,       /* charmm_angle_constraint.py:55-96 (incl. Urey-Bradley) */
+    MDK_TERM_DIHEDRAL = 1u << 6,    /* charmm_dihedral_constraint.py:59-95 */
+    MDK_TERM_IMPROPER = 1u << 7     /* charmm_improper_constraint.py:57-94 */
+};
+enum {
+    MDK_E_LJ = 0,
+    MDK_E_COUL_DIRECT = 1,
+    MDK_E_PME_RECIP = 2,
+    MDK_E_PME_SELF = 3,  /* self + neutralising background */
+    MDK_E_PME_EXCL = 4,  /* excluded-pair erf correction */
+    MDK_E_COUL_BARE = 5,
+    MDK_E_BOND = 6,
+    MDK_E_ANGLE = 7,
+    MDK_E_DIHEDRAL = 8,
+    MDK_E_IMPROPER = 9,
+    MDK_E_KINETIC = 10,
+    MDK_NUM_ENERGIES = 16
+};
+
+/* ---- lifetime ---- */
+/* Replaces the per-call cuda.to_device allocations of the reference
+ * (charmm_nonbonded_constraint.py:197-209): the context owns every device buffer,
+ * stream, cuFFT plan.  device = CUDA ordinal.  Fails (MDK_ERR_CUDA) when no sm_100 GPU
+ * is present — there is no CPU fallback. */
+MDK_API int mdk_create(int device, mdk_ctx **out);
+MDK_API void mdk_destroy(mdk_ctx *ctx);
+/* Last error text of this ctx (or of a failed mdk_create when ctx == NULL). */
+MDK_API const char *mdk_last_error(const mdk_ctx *ctx);
+/* Run all work of this ctx on an existing CUDA stream (cudaStream_t handle, e.g.
+ * torch.cuda.current_stream().cuda_stream) instead of the private one. */
+MDK_API int mdk_set_stream(mdk_ctx *ctx, void *cuda_stream);
+
+/* ---- system definition (bind time; reference: Constraint.bind_ensemble) ---- */
+/* Orthorhombic box edge lengths = diag(State.pbc_matrix) (state.py:47-54; SURVEY Q3: the
+ * reference's CUDA kernels and cell list read only the diagonal). */
+MDK_API int mdk_set_box(mdk_ctx *ctx, const double box[3]);
+/* topology.charges / topology.masses, float32 [n] (topology.py:59-68). */
+MDK_API int mdk_set_atoms(mdk_ctx *ctx, int n, const float *charges, const float *masses);
+/* Per-atom [eps, sigma, eps14, sigma14] table float32 [n,4] exactly as
+ * CharmmNonbondedConstraint.bind_ensemble builds it (charmm_nonbonded_constraint.py:48-62).
+ * rc = cutoff (inclusive, :90).  r_switch >= rc: the reference's plain truncation;
+ * r_switch < rc: CHARMM energy switch on (r_switch, rc] [not in the reference tree]. */
+MDK_API int mdk_set_lj(mdk_ctx *ctx, const float *eps_sigma, float rc, float r_switch);
+/* topology.bonded_particles (1-2 and 1-3 partners: excluded, charmm_nonbonded_constraint.py:83)
+ * and topology.scaling_particles (1-4 partners: eps14/sigma14, :92-97), int32, -1 padded,
+ * row widths wb / ws (topology.py:69-79).  Either pointer may be NULL with width 0. */
+MDK_API int mdk_set_exclusions(mdk_ctx *ctx, const int32_t *bonded, int wb, const int32_t *scaling, int ws);
+/* k_e = 1/(4 pi eps0) in internal units, taken from mdpy's own EPSILON0 at run time
+ * (electrostatic_constraint.py:21,60).  alpha / rc only matter for
+ * MDK_TERM_COUL_DIRECT and MDK_TERM_PME_RECIP. */
+MDK_API int mdk_set_coulomb(mdk_ctx *ctx, double k_e, double alpha, float rc);
+/* PME mesh and B-spline order (4, 5, 6 or 8). */
+MDK_API int mdk_set_pme(mdk_ctx *ctx, int nx, int ny, int nz, int order);
+/* Verlet buffer of the tile list (the reference rebuilds its cell list on every
+ * set_positions, state.py:61; here the list is reused until an atom has moved skin/2). */
+MDK_API int mdk_set_nlist(mdk_ctx *ctx, float skin);
+/* Bonded terms, parameters in internal units, one row per term:
+ *   bonds     idx [n,2], par [n,2] = (k, r0)                E = k (r - r0)^2
+ *   angles    idx [n,3], par [n,4] = (k, theta0, k_ub, r_ub) E = k (th - th0)^2 + k_ub (r13 - r_ub)^2
+ *   dihedrals idx [n,4], par [n,3] = (k, n, delta)          E = k (1 + cos(n phi - delta))
+ *   impropers idx [n,4], par [n,2] = (k, psi0)              E = k (psi - psi0)^2 */
+MDK_API int mdk_set_bonded(mdk_ctx *ctx, int kind /* 0 bond 1 angle 2 dihedral 3 improper */, int n,
+                   const int32_t *idx, const float *par);
+
+/* ---- state ---- */
+/* State.set_positions (state.py:56-61): wraps into [-L/2, L/2] (utils/pbc.py:28-36; an
+ * atom >= 2 images away -> MDK_ERR_PARTICLE_LOST) and marks the tile list for a
+ * displacement check.  xyz float32 [n,3] in topology (matrix_id) order. */
+MDK_API int mdk_upload_positions(mdk_ctx *ctx, const float *xyz);
+MDK_API int mdk_upload_positions_f64(mdk_ctx *ctx, const double *xyz);
+MDK_API int mdk_upload_velocities(mdk_ctx *ctx, const float *v);
+MDK_API int mdk_download_positions(mdk_ctx *ctx, float *xyz_wrapped);
+MDK_API int mdk_download_positions_f64(mdk_ctx *ctx, double *xyz_unwrapped);
+MDK_API int mdk_download_velocities(mdk_ctx *ctx, float *v);
+
+/* ---- hot path ---- */
+/* Force a neighbour (tile) list rebuild now.  Writes list statistics if non-NULL:
+ * stats[0]=i-blocks, [1]=work units, [2]=j-chunks, [3]=masked chunks, [4]=pair slots. */
+MDK_API int mdk_build_nlist(mdk_ctx *ctx, int64_t *stats);
+/* Constraint.update for the selected terms (bit-or of MDK_TERM_*): zeroes the force
+ * accumulator, rebuilds the tile list if an atom has moved more than skin/2, evaluates
+ * the terms and writes their energies (float64, internal units) into
+ * energies[MDK_NUM_ENERGIES] (may be NULL).  Synchronous. */
+MDK_API int mdk_compute(mdk_ctx *ctx, unsigned terms, double *energies);
+/* Constraint.forces: sum of the terms of the last mdk_compute, float32 [n,3] in
+ * matrix_id order. */
+MDK_API int mdk_download_forces(mdk_ctx *ctx, float *out);
+MDK_API int mdk_download_forces_f64(mdk_ctx *ctx, double *out);
+
+/* ---- integrators (the per-step position/velocity update) ---- */
+/* VerletIntegrator.integrate (verlet_integrator.py:20-50), device resident.
+ * reference_quirks != 0 reproduces the reference bit of behaviour the survey flags
+ * (first step a dt^2, reported velocity (x_n+1 - x_n)/(2 dt)); 0 gives the
+ * textbook initialisation (a dt^2/2) and central-difference velocities. */
+MDK_API int mdk_step_verlet(mdk_ctx *ctx, double dt, int nsteps, unsigned terms, int reference_quirks);
+MDK_API void mdk_verlet_reset(mdk_ctx *ctx); /* Integrator.erase_cache, integrator.py:20-22 */
+/* G-JF Langevin with the reference's coefficients a, b, sigma
+ * (langevin_integrator.py:23-31; textbook update), Philox4x32-10 noise. */
+MDK_API int mdk_step_langevin(mdk_ctx *ctx, double dt, double kT, double gamma, uint64_t seed,
+                      int nsteps, unsigned terms);
+/* Energies of the most recent force evaluation inside a step call (no extra work). */
+MDK_API int mdk_last_energies(mdk_ctx *ctx, double *energies);
+
+/* ---- test / measurement hooks ---- */
+/* The in-cutoff (rc of mdk_set_lj), non-excluded pair set the tile list yields, as
+ * matrix_id pairs i<j (unsorted).  *n_out = count; at most cap are written. */
+MDK_API int mdk_get_pairs(mdk_ctx *ctx, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out);
+/* Device time (ms, CUDA events on the ctx stream) of the last mdk_compute / step call,
+ * per phase: [0]=nlist rebuild [1]=pair kernel [2]=pme spread [3]=fft+convolve
+ * [4]=pme gather [5]=bonded+special pairs [6]=integrate [7]=bare coulomb
+ * [8]=total; plus counters [9]=kernel launches [10]=nlist rebuilds [11]=pair-kernel launches. */
+MDK_API int mdk_get_timing(mdk_ctx *ctx, double *out16);
+/* Enable (1) / disable (0) per-phase event timing (adds stream syncs; off by default). */
+MDK_API int mdk_set_profiling(mdk_ctx *ctx, int on);
+/* Raw device pointer + element count of the int64 fixed-point force accumulator in
+ * tile order (multi-GPU reduction by the host layer; scale = 2^40). */
+MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64);
+/* Restrict the pair-kernel work units this ctx evaluates to those with
+ * (unit_index % nranks) == rank (replicated-data force decomposition). */
+MDK_API int mdk_set_shard(mdk_ctx *ctx, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDPY_B200_H */

@@ -1,0 +1,480 @@
+// mdk_api.cu — the extern "C" boundary of libmdpyb200.so (see include/mdpy_b200.h).
+#include <stdarg.h>
+
+#include <cmath>
+
+#include "mdk_common.cuh"
+
+namespace mdk {
+
+static thread_local std::string g_create_err;
+
+int fail(mdk_ctx *c, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+static void invalidate(mdk_ctx *c) { c->nlist_valid = false; }
+
+__global__ void k_f32_to_f64(size_t n, const float *__restrict__ in, double *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+// forces back to matrix_id order
+template <typename T>
+__global__ void k_unpermute_forces(int n, const int *__restrict__ order, const long long *__restrict__ f_acc,
+                                   T *__restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a = order[k];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) out[3 * (size_t)a + d] = (T)((double)f_acc[3 * (size_t)k + d] * (1.0 / FIX_SCALE));
+}
+
+__global__ void k_wrapped_positions(int n, const double *__restrict__ x_cur, double Lx, double Ly, double Lz,
+                                    float *__restrict__ out) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    double L[3] = {Lx, Ly, Lz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double x = x_cur[3 * (size_t)a + d];
+        out[3 * (size_t)a + d] = (float)(x - L[d] * rint(x / L[d]));
+    }
+}
+
+__global__ void k_f64_to_f32(size_t n, const double *__restrict__ in, float *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+}  // namespace mdk
+
+using namespace mdk;
+
+#define NEED_CTX(c) \
+    if (!(c)) return MDK_ERR_BAD_ARG
+
+template <typename T>
+static int download_forces(mdk_ctx *c, T *out) {
+    if (!c->nlist_valid || !out) return fail(c, MDK_ERR_NOT_BOUND, "mdk_download_forces before mdk_compute");
+    T *tmp = nullptr;
+    size_t m = (size_t)3 * c->n;
+    MDK_CUDA(c, cudaMalloc(&tmp, m * sizeof(T)));
+    k_unpermute_forces<T><<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->order.p, c->f_acc.p, tmp);
+    ++c->n_launches;
+    cudaError_t e = cudaMemcpyAsync(out, tmp, m * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    MDK_CUDA(c, e);
+    return MDK_OK;
+}
+
+extern "C" {
+
+int mdk_create(int device, mdk_ctx **out) {
+    if (!out) return MDK_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, MDK_ERR_CUDA, "no CUDA device available (%s); mdpy_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, MDK_ERR_BAD_ARG, "device %d out of range [0, %d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, MDK_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MDK_ERR_CUDA, "device %d is sm_%d%d; libmdpyb200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return fail(nullptr, MDK_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    mdk_ctx *c = new mdk_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, MDK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    for (auto &ev : c->ev) cudaEventCreate(&ev);
+    if (c->counters.reserve(8) != cudaSuccess || c->flags.reserve(4) != cudaSuccess ||
+        c->e_acc.reserve(MDK_NUM_ENERGIES) != cudaSuccess) {
+        mdk_destroy(c);
+        return fail(nullptr, MDK_ERR_OOM, "cudaMalloc failed in mdk_create");
+    }
+    cudaMemset(c->counters.p, 0, 8 * sizeof(int));
+    cudaMemset(c->flags.p, 0, 4 * sizeof(int));
+    cudaMemset(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long));
+    *out = c;
+    return MDK_OK;
+}
+
+void mdk_destroy(mdk_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
+    c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release();
+    for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
+    c->x_cur.release(); c->x_prev.release(); c->vel.release(); c->f_prev.release();
+    c->order.release(); c->inv_order.release(); c->xs.release(); c->xs_ref.release(); c->ljs.release();
+    c->excl_s.release(); c->p14_s.release(); c->f_acc.release(); c->e_acc.release(); c->flags.release();
+    c->cell_key.release(); c->cell_key_sorted.release(); c->idx_tmp.release(); c->cell_start.release();
+    c->sort_tmp.release(); c->bb_center.release(); c->bb_half.release();
+    c->units.release(); c->chunk_j.release(); c->chunk_mask.release(); c->mask_excl.release(); c->mask_14.release();
+    c->counters.release();
+    c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release();
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *mdk_last_error(const mdk_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int mdk_set_stream(mdk_ctx *c, void *cuda_stream) {
+    NEED_CTX(c);
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return MDK_OK;
+}
+
+int mdk_set_box(mdk_ctx *c, const double box[3]) {
+    NEED_CTX(c);
+    if (!box) return fail(c, MDK_ERR_BAD_ARG, "box is NULL");
+    for (int a = 0; a < 3; ++a) {
+        if (!(box[a] > 0) || !std::isfinite(box[a])) return fail(c, MDK_ERR_BAD_ARG, "box edge %d = %g is not positive", a, box[a]);
+        c->box.Ld[a] = box[a];
+        c->box.L[a] = (float)box[a];
+        c->box.invL[a] = 1.0f / c->box.L[a];
+    }
+    c->have_box = true;
+    c->pme_dirty = true;
+    invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_atoms(mdk_ctx *c, int n, const float *charges, const float *masses) {
+    NEED_CTX(c);
+    if (n <= 0 || !charges || !masses) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_atoms: n=%d / NULL arrays", n);
+    cudaSetDevice(c->device);
+    if (n != c->n) {
+        c->have_pos = false; c->have_lj = false; c->wb = c->ws = 0;
+        c->verlet_cached = c->langevin_cached = false;
+        for (auto &b : c->bonded) b.n = 0;
+    }
+    c->n = n;
+    MDK_CUDA(c, c->q.reserve(n)); MDK_CUDA(c, c->mass.reserve(n));
+    MDK_CUDA(c, c->x_cur.reserve((size_t)3 * n)); MDK_CUDA(c, c->vel.reserve((size_t)3 * n));
+    MDK_CUDA(c, cudaMemcpyAsync(c->q.p, charges, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    MDK_CUDA(c, cudaMemcpyAsync(c->mass.p, masses, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    MDK_CUDA(c, cudaMemsetAsync(c->vel.p, 0, (size_t)3 * n * sizeof(double), c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    double sq = 0, sq2 = 0;
+    for (int i = 0; i < n; ++i) { sq += charges[i]; sq2 += (double)charges[i] * charges[i]; }
+    c->host_tmp.assign({sq, sq2});
+    invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_lj(mdk_ctx *c, const float *eps_sigma, float rc, float r_switch) {
+    NEED_CTX(c);
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_set_lj before mdk_set_atoms");
+    if (!eps_sigma) return fail(c, MDK_ERR_BAD_ARG, "eps_sigma is NULL");
+    if (!(rc > 0)) return fail(c, MDK_ERR_CUTOFF_TOO_LARGE, "Cutoff radius is poor defined, current value %.3f", rc);
+    MDK_CUDA(c, c->lj4.reserve(c->n));
+    MDK_CUDA(c, cudaMemcpyAsync(c->lj4.p, eps_sigma, (size_t)c->n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->rc_lj = rc;
+    c->r_switch = (r_switch > 0 && r_switch < rc) ? r_switch : rc;
+    c->have_lj = true;
+    invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_exclusions(mdk_ctx *c, const int32_t *bonded, int wb, const int32_t *scaling, int ws) {
+    NEED_CTX(c);
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_set_exclusions before mdk_set_atoms");
+    if (wb < 0 || ws < 0 || (wb > 0 && !bonded) || (ws > 0 && !scaling))
+        return fail(c, MDK_ERR_BAD_ARG, "mdk_set_exclusions: bad widths / NULL tables");
+    for (size_t i = 0; i < (size_t)c->n * wb; ++i)
+        if (bonded[i] < -1 || bonded[i] >= c->n) return fail(c, MDK_ERR_BAD_ARG, "bonded_particles entry %d out of range", bonded[i]);
+    for (size_t i = 0; i < (size_t)c->n * ws; ++i)
+        if (scaling[i] < -1 || scaling[i] >= c->n) return fail(c, MDK_ERR_BAD_ARG, "scaling_particles entry %d out of range", scaling[i]);
+    c->wb = wb; c->ws = ws;
+    if (wb > 0) {
+        MDK_CUDA(c, c->excl.reserve((size_t)c->n * wb));
+        MDK_CUDA(c, cudaMemcpyAsync(c->excl.p, bonded, (size_t)c->n * wb * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (ws > 0) {
+        MDK_CUDA(c, c->p14.reserve((size_t)c->n * ws));
+        MDK_CUDA(c, cudaMemcpyAsync(c->p14.p, scaling, (size_t)c->n * ws * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_coulomb(mdk_ctx *c, double k_e, double alpha, float rc) {
+    NEED_CTX(c);
+    if (!(k_e > 0) || alpha < 0 || rc < 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_coulomb: k_e=%g alpha=%g rc=%g", k_e, alpha, rc);
+    c->k_e = k_e; c->alpha = alpha; c->rc_coul = rc;
+    c->have_coul = true;
+    c->pme_dirty = true;
+    invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_pme(mdk_ctx *c, int nx, int ny, int nz, int order) {
+    NEED_CTX(c);
+    if (nx < 4 || ny < 4 || nz < 4) return fail(c, MDK_ERR_BAD_ARG, "PME mesh %dx%dx%d too small", nx, ny, nz);
+    if (order != 4 && order != 5 && order != 6 && order != 8) return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", order);
+    if (nx < order || ny < order || nz < order) return fail(c, MDK_ERR_BAD_ARG, "PME mesh smaller than the spline order");
+    c->pme_n[0] = nx; c->pme_n[1] = ny; c->pme_n[2] = nz; c->pme_order = order;
+    c->have_pme = true; c->pme_dirty = true;
+    return MDK_OK;
+}
+
+int mdk_set_nlist(mdk_ctx *c, float skin) {
+    NEED_CTX(c);
+    if (skin < 0) return fail(c, MDK_ERR_BAD_ARG, "negative skin");
+    c->skin = skin;
+    invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_bonded(mdk_ctx *c, int kind, int n, const int32_t *idx, const float *par) {
+    NEED_CTX(c);
+    static const int ni[4] = {2, 3, 4, 4}, np[4] = {2, 4, 3, 2};
+    if (kind < 0 || kind > 3 || n < 0 || (n > 0 && (!idx || !par))) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_bonded: bad arguments");
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_set_bonded before mdk_set_atoms");
+    for (size_t i = 0; i < (size_t)n * ni[kind]; ++i)
+        if (idx[i] < 0 || idx[i] >= c->n) return fail(c, MDK_ERR_BAD_ARG, "bonded term index %d out of range", idx[i]);
+    auto &b = c->bonded[kind];
+    b.n = n;
+    if (n > 0) {
+        MDK_CUDA(c, b.idx.reserve((size_t)n * ni[kind])); MDK_CUDA(c, b.par.reserve((size_t)n * np[kind]));
+        MDK_CUDA(c, cudaMemcpyAsync(b.idx.p, idx, (size_t)n * ni[kind] * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        MDK_CUDA(c, cudaMemcpyAsync(b.par.p, par, (size_t)n * np[kind] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return MDK_OK;
+}
+
+// ---- state ----
+static int check_lost(mdk_ctx *c, const double *x, const float *xf) {
+    // utils/pbc.py:29-34: |round(x / L)| >= 2 on any axis
+    for (int i = 0; i < c->n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            double v = xf ? (double)xf[3 * (size_t)i + d] : x[3 * (size_t)i + d];
+            if (!(std::fabs(std::nearbyint(v / c->box.Ld[d])) < 2))
+                return fail(c, MDK_ERR_PARTICLE_LOST, "Atom(s) with matrix id: [%d] moved beyond 2 PBC image.", i);
+        }
+    return MDK_OK;
+}
+
+int mdk_upload_positions(mdk_ctx *c, const float *xyz) {
+    NEED_CTX(c);
+    if (c->n <= 0 || !c->have_box) return fail(c, MDK_ERR_NOT_BOUND, "mdk_upload_positions before box/atoms");
+    if (!xyz) return fail(c, MDK_ERR_BAD_ARG, "xyz is NULL");
+    MDK_TRY(check_lost(c, nullptr, xyz));
+    size_t m = (size_t)3 * c->n;
+    MDK_CUDA(c, c->x_prev.reserve(m));  // staging (also the Verlet history buffer; cache is reset below)
+    float *stage = reinterpret_cast<float *>(c->x_prev.p);
+    MDK_CUDA(c, cudaMemcpyAsync(stage, xyz, m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    k_f32_to_f64<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, stage, c->x_cur.p);
+    ++c->n_launches;
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_pos = true;
+    c->verlet_cached = false; c->langevin_cached = false;
+    return MDK_OK;
+}
+
+int mdk_upload_positions_f64(mdk_ctx *c, const double *xyz) {
+    NEED_CTX(c);
+    if (c->n <= 0 || !c->have_box) return fail(c, MDK_ERR_NOT_BOUND, "mdk_upload_positions before box/atoms");
+    if (!xyz) return fail(c, MDK_ERR_BAD_ARG, "xyz is NULL");
+    MDK_TRY(check_lost(c, xyz, nullptr));
+    MDK_CUDA(c, cudaMemcpyAsync(c->x_cur.p, xyz, (size_t)3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_pos = true;
+    c->verlet_cached = false; c->langevin_cached = false;
+    return MDK_OK;
+}
+
+int mdk_upload_velocities(mdk_ctx *c, const float *v) {
+    NEED_CTX(c);
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_upload_velocities before mdk_set_atoms");
+    if (!v) return fail(c, MDK_ERR_BAD_ARG, "v is NULL");
+    size_t m = (size_t)3 * c->n;
+    MDK_CUDA(c, c->f_prev.reserve(m));
+    float *stage = reinterpret_cast<float *>(c->f_prev.p);
+    MDK_CUDA(c, cudaMemcpyAsync(stage, v, m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    k_f32_to_f64<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, stage, c->vel.p);
+    ++c->n_launches;
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->verlet_cached = false; c->langevin_cached = false;
+    return MDK_OK;
+}
+
+int mdk_download_positions(mdk_ctx *c, float *out) {
+    NEED_CTX(c);
+    if (!c->have_pos || !out) return fail(c, MDK_ERR_NOT_BOUND, "no positions on the device");
+    float *tmp = nullptr;
+    size_t m = (size_t)3 * c->n;
+    MDK_CUDA(c, cudaMalloc(&tmp, m * sizeof(float)));
+    k_wrapped_positions<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->x_cur.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], tmp);
+    ++c->n_launches;
+    cudaError_t e = cudaMemcpyAsync(out, tmp, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    MDK_CUDA(c, e);
+    return MDK_OK;
+}
+
+int mdk_download_positions_f64(mdk_ctx *c, double *out) {
+    NEED_CTX(c);
+    if (!c->have_pos || !out) return fail(c, MDK_ERR_NOT_BOUND, "no positions on the device");
+    MDK_CUDA(c, cudaMemcpyAsync(out, c->x_cur.p, (size_t)3 * c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MDK_OK;
+}
+
+int mdk_download_velocities(mdk_ctx *c, float *out) {
+    NEED_CTX(c);
+    if (c->n <= 0 || !out) return fail(c, MDK_ERR_NOT_BOUND, "no velocities on the device");
+    float *tmp = nullptr;
+    size_t m = (size_t)3 * c->n;
+    MDK_CUDA(c, cudaMalloc(&tmp, m * sizeof(float)));
+    k_f64_to_f32<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, c->vel.p, tmp);
+    ++c->n_launches;
+    cudaError_t e = cudaMemcpyAsync(out, tmp, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    MDK_CUDA(c, e);
+    return MDK_OK;
+}
+
+// ---- hot path ----
+static void prepare_pme_constants(mdk_ctx *c) {
+    if (c->have_coul && c->alpha > 0 && c->host_tmp.size() >= 2) {
+        double V = c->box.Ld[0] * c->box.Ld[1] * c->box.Ld[2];
+        c->e_self_bg = -c->k_e * c->alpha / sqrt(M_PI) * c->host_tmp[1] -
+                       c->k_e * M_PI * c->host_tmp[0] * c->host_tmp[0] / (2.0 * V * c->alpha * c->alpha);
+    }
+}
+
+int mdk_build_nlist(mdk_ctx *c, int64_t *stats) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    MDK_TRY(nlist_rebuild(c));
+    if (stats) {
+        stats[0] = c->n_blocks; stats[1] = c->stat_units; stats[2] = c->stat_chunks; stats[3] = c->stat_masks;
+        stats[4] = c->stat_chunks * 1024;
+    }
+    return MDK_OK;
+}
+
+int mdk_compute(mdk_ctx *c, unsigned terms, double *energies) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    prepare_pme_constants(c);
+    if (c->profiling) { for (auto &p : c->phase_ms) p = 0; cudaEventRecord(c->ev[2 * PH_TOTAL], c->stream); }
+    MDK_TRY(compute_terms(c, terms, true));
+    if (c->profiling) {
+        cudaEventRecord(c->ev[2 * PH_TOTAL + 1], c->stream);
+        cudaEventSynchronize(c->ev[2 * PH_TOTAL + 1]);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[2 * PH_TOTAL], c->ev[2 * PH_TOTAL + 1]);
+        c->phase_ms[PH_TOTAL] = ms;
+    }
+    if (energies) memcpy(energies, c->last_e, sizeof(c->last_e));
+    return MDK_OK;
+}
+
+int mdk_download_forces(mdk_ctx *c, float *out) { NEED_CTX(c); cudaSetDevice(c->device); return download_forces<float>(c, out); }
+int mdk_download_forces_f64(mdk_ctx *c, double *out) { NEED_CTX(c); cudaSetDevice(c->device); return download_forces<double>(c, out); }
+
+int mdk_step_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int reference_quirks) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!(dt > 0)) return fail(c, MDK_ERR_BAD_ARG, "dt must be positive");
+    prepare_pme_constants(c);
+    if (c->profiling) { for (auto &p : c->phase_ms) p = 0; cudaEventRecord(c->ev[2 * PH_TOTAL], c->stream); }
+    MDK_TRY(integrate_verlet(c, dt, nsteps, terms, reference_quirks));
+    if (c->profiling) {
+        cudaEventRecord(c->ev[2 * PH_TOTAL + 1], c->stream);
+        cudaEventSynchronize(c->ev[2 * PH_TOTAL + 1]);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[2 * PH_TOTAL], c->ev[2 * PH_TOTAL + 1]);
+        c->phase_ms[PH_TOTAL] = ms;
+    }
+    return MDK_OK;
+}
+
+void mdk_verlet_reset(mdk_ctx *c) { if (c) { c->verlet_cached = false; c->langevin_cached = false; } }
+
+int mdk_step_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!(dt > 0) || kT < 0 || gamma < 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_step_langevin: dt=%g kT=%g gamma=%g", dt, kT, gamma);
+    prepare_pme_constants(c);
+    if (c->profiling) { for (auto &p : c->phase_ms) p = 0; cudaEventRecord(c->ev[2 * PH_TOTAL], c->stream); }
+    MDK_TRY(integrate_langevin(c, dt, kT, gamma, seed, nsteps, terms));
+    if (c->profiling) {
+        cudaEventRecord(c->ev[2 * PH_TOTAL + 1], c->stream);
+        cudaEventSynchronize(c->ev[2 * PH_TOTAL + 1]);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[2 * PH_TOTAL], c->ev[2 * PH_TOTAL + 1]);
+        c->phase_ms[PH_TOTAL] = ms;
+    }
+    return MDK_OK;
+}
+
+int mdk_last_energies(mdk_ctx *c, double *energies) {
+    NEED_CTX(c);
+    if (!energies) return fail(c, MDK_ERR_BAD_ARG, "energies is NULL");
+    memcpy(energies, c->last_e, sizeof(c->last_e));
+    return MDK_OK;
+}
+
+int mdk_get_pairs(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!n_out || cap < 0 || (cap > 0 && (!out_i || !out_j))) return fail(c, MDK_ERR_BAD_ARG, "mdk_get_pairs: bad arguments");
+    if (!c->have_box || c->n <= 0 || !c->have_pos) return fail(c, MDK_ERR_NOT_BOUND, "mdk_get_pairs before box/atoms/positions");
+    return pair_enumerate(c, out_i, out_j, cap, n_out);
+}
+
+int mdk_get_timing(mdk_ctx *c, double *out16) {
+    NEED_CTX(c);
+    if (!out16) return fail(c, MDK_ERR_BAD_ARG, "out is NULL");
+    for (int k = 0; k < 16; ++k) out16[k] = 0;
+    for (int k = 0; k < PH_COUNT; ++k) out16[k] = c->phase_ms[k];
+    out16[9] = (double)c->n_launches; out16[10] = (double)c->n_rebuilds; out16[11] = (double)c->n_pair_launches;
+    out16[12] = (double)c->stat_units; out16[13] = (double)c->stat_chunks; out16[14] = (double)c->stat_masks;
+    out16[15] = (double)c->seg_chunks;
+    return MDK_OK;
+}
+
+int mdk_set_profiling(mdk_ctx *c, int on) { NEED_CTX(c); c->profiling = on != 0; return MDK_OK; }
+
+int mdk_force_accumulator(mdk_ctx *c, void **dev_ptr, int64_t *n_int64) {
+    NEED_CTX(c);
+    if (!dev_ptr || !n_int64) return fail(c, MDK_ERR_BAD_ARG, "NULL output");
+    *dev_ptr = c->f_acc.p;
+    *n_int64 = (int64_t)c->n_pad * 3;
+    return MDK_OK;
+}
+
+int mdk_set_shard(mdk_ctx *c, int rank, int nranks) {
+    NEED_CTX(c);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_shard(%d, %d)", rank, nranks);
+    c->shard_rank = rank; c->shard_n = nranks;
+    return MDK_OK;
+}
+
+}  // extern "C"

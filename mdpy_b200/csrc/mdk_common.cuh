@@ -1,0 +1,220 @@
+// mdk_common.cuh — context, buffers and device helpers shared by all translation units
+// of libmdpyb200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mdpy_b200.h"
+
+namespace mdk {
+
+constexpr int WARP = 32;
+constexpr int TILE = 32;                  // atoms per i-block and per j-chunk
+constexpr double FIX_SCALE = 1099511627776.0;   // 2^40: fixed-point forces (int64)
+constexpr float FIX_SCALE_F = 1099511627776.0f;
+constexpr float RINT_MAGIC = 12582912.0f;  // 1.5 * 2^23: (x + M) - M == rintf(x) for |x| < 2^22
+
+// ---------------------------------------------------------------------------
+// growable device buffer
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Box {
+    float L[3], invL[3];
+    double Ld[3];
+};
+
+// kernel-side view of the tile list
+struct NlistView {
+    const int4 *units;      // {i-block, first chunk, n chunks, unused}
+    const int *n_units;     // device counter
+    const int *chunk_j;     // [chunk][32] tile-order atom indices (padding -> 0 + mask bit)
+    const int *chunk_mask;  // [chunk] mask slot or -1
+    const unsigned *mask_excl;  // [slot][32] rotated exclusion bits per i-lane
+    const unsigned *mask_14;    // [slot][32] rotated 1-4 bits per i-lane
+};
+
+struct BondedSet {
+    int n = 0;
+    DevBuf<int> idx;
+    DevBuf<float> par;
+};
+
+enum Phase { PH_NLIST = 0, PH_PAIR, PH_SPREAD, PH_FFT, PH_GATHER, PH_BONDED, PH_INTEGRATE, PH_BARE, PH_TOTAL, PH_COUNT };
+
+}  // namespace mdk
+
+struct mdk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+
+    // ---- system (matrix_id order) ----
+    int n = 0;
+    mdk::Box box{};
+    bool have_box = false;
+    mdk::DevBuf<float> q, mass;          // [n]
+    mdk::DevBuf<float4> lj4;             // [n] eps, sigma, eps14, sigma14
+    bool have_lj = false;
+    float rc_lj = 0.f, r_switch = 0.f;
+    mdk::DevBuf<int> excl, p14;          // [n, wb] / [n, ws], -1 padded, matrix ids
+    int wb = 0, ws = 0;
+    double k_e = 0.0, alpha = 0.0;
+    float rc_coul = 0.f;
+    bool have_coul = false;
+    float skin = 2.0f;
+    mdk::BondedSet bonded[4];
+
+    // ---- state (matrix_id order) ----
+    mdk::DevBuf<double> x_cur, x_prev, vel;   // [n,3] unwrapped fp64 positions / velocities
+    mdk::DevBuf<double> f_prev;               // [n,3] Langevin: forces of the previous step
+    bool have_pos = false;
+    bool verlet_cached = false, langevin_cached = false;
+    uint64_t langevin_step = 0;
+
+    // ---- tile order ----
+    int n_blocks = 0;
+    int n_pad = 0;                            // n rounded up to 32
+    mdk::DevBuf<int> order, inv_order;        // tile slot -> matrix id, matrix id -> slot
+    mdk::DevBuf<float4> xs;                   // wrapped xyz + q*sqrt(k_e)
+    mdk::DevBuf<float4> xs_ref;               // xs at the last rebuild
+    mdk::DevBuf<float4> ljs;                  // 2 sqrt(eps), sigma/2, 2 sqrt(eps14), sigma14/2
+    mdk::DevBuf<int> excl_s, p14_s;           // exclusion tables in tile slots
+    mdk::DevBuf<long long> f_acc;             // [n_pad,3] fixed-point forces
+    mdk::DevBuf<long long> e_acc;             // [MDK_NUM_ENERGIES] fixed point
+    mdk::DevBuf<int> flags;                   // [0]=lost atoms [1]=needs rebuild [2]=pool overflow [3]=scratch
+    // cell grid
+    int ncell[3] = {0, 0, 0};
+    float cellw[3] = {0, 0, 0};
+    mdk::DevBuf<unsigned> cell_key, cell_key_sorted;
+    mdk::DevBuf<int> idx_tmp;
+    mdk::DevBuf<int> cell_start;              // [ncells + 1]
+    mdk::DevBuf<unsigned char> sort_tmp;
+    mdk::DevBuf<float4> bb_center, bb_half;   // [n_blocks]
+    // tile list pools
+    mdk::DevBuf<int4> units;
+    mdk::DevBuf<int> chunk_j, chunk_mask;
+    mdk::DevBuf<unsigned> mask_excl, mask_14;
+    mdk::DevBuf<int> counters;                // [0]=units [1]=chunks [2]=mask slots [3]=work cursor
+    size_t cap_units = 0, cap_chunks = 0, cap_masks = 0;
+    bool nlist_valid = false;
+    int seg_chunks = 8;
+    int64_t stat_units = 0, stat_chunks = 0, stat_masks = 0;
+    int shard_rank = 0, shard_n = 1;
+
+    // ---- PME ----
+    int pme_n[3] = {0, 0, 0};
+    int pme_order = 4;
+    bool have_pme = false, pme_dirty = true;
+    mdk::DevBuf<long long> grid_fix;          // fixed-point charge mesh
+    mdk::DevBuf<float> grid_r;                // real mesh
+    mdk::DevBuf<float2> grid_c;               // half spectrum
+    mdk::DevBuf<float> influence;             // G(m) on the half spectrum
+    cufftHandle plan_r2c = 0, plan_c2r = 0;
+    bool have_plans = false;
+    double e_self_bg = 0.0;
+
+    // ---- bookkeeping ----
+    double last_e[MDK_NUM_ENERGIES] = {0};
+    bool profiling = false;
+    cudaEvent_t ev[2 * mdk::PH_COUNT] = {nullptr};
+    double phase_ms[mdk::PH_COUNT] = {0};
+    int64_t n_launches = 0, n_rebuilds = 0, n_pair_launches = 0;
+    std::vector<double> host_tmp;
+};
+
+namespace mdk {
+
+int fail(mdk_ctx *c, int code, const char *fmt, ...);
+#define MDK_CUDA(c, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return mdk::fail((c), e__ == cudaErrorMemoryAllocation ? MDK_ERR_OOM : MDK_ERR_CUDA, \
+                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define MDK_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != MDK_OK) return rc__; \
+    } while (0)
+
+struct PhaseTimer {
+    mdk_ctx *c; int ph;
+    PhaseTimer(mdk_ctx *c_, int ph_) : c(c_), ph(ph_) {
+        if (c->profiling) cudaEventRecord(c->ev[2 * ph], c->stream);
+    }
+    ~PhaseTimer() {
+        if (c->profiling) {
+            cudaEventRecord(c->ev[2 * ph + 1], c->stream);
+            cudaEventSynchronize(c->ev[2 * ph + 1]);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[2 * ph], c->ev[2 * ph + 1]);
+            c->phase_ms[ph] += ms;
+        }
+    }
+};
+
+// translation-unit entry points
+int nlist_refresh_sorted(mdk_ctx *c);          // xs <- wrap(x_cur) in tile order + displacement check
+int nlist_rebuild(mdk_ctx *c);
+int nlist_ensure(mdk_ctx *c);                  // rebuild if flagged / invalid
+NlistView nlist_view(mdk_ctx *c);
+int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul);
+int pair_special(mdk_ctx *c, bool pme_excl);   // excluded-pair erf correction
+int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out);
+int coulomb_bare(mdk_ctx *c);
+int pme_prepare(mdk_ctx *c);
+int pme_compute(mdk_ctx *c);
+int bonded_compute(mdk_ctx *c, unsigned terms);
+int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
+int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms);
+int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);
+
+// ---------------------------------------------------------------------------
+// device helpers
+#ifdef __CUDACC__
+// Minimum image along one axis with exactly the rounding sequence of the canonical pair
+// criterion (oracle/mdpy_oracle.c:ora_pair_set_f32).
+__device__ __forceinline__ float min_image(float d, float L, float invL) {
+    float t = __fadd_rn(__fmaf_rn(d, invL, RINT_MAGIC), -RINT_MAGIC);
+    return __fmaf_rn(-L, t, d);
+}
+__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+__device__ __forceinline__ long long to_fix(float f) { return __float2ll_rn(f * FIX_SCALE_F); }
+__device__ __forceinline__ long long to_fix(double f) { return __double2ll_rn(f * FIX_SCALE); }
+__device__ __forceinline__ void atomic_add_fix(long long *p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+}  // namespace mdk

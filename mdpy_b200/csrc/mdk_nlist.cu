@@ -1,0 +1,508 @@
+// mdk_nlist.cu — tile (neighbour) list: cell sort, i-block bounding boxes, per-block
+// filtered j-atom chunks with rotated exclusion / 1-4 masks.
+//
+// Replaces mdpy/core/cell_list.py:83-116 (dense -1-padded [nx,ny,nz,P] cell table rebuilt
+// on every State.set_positions, state.py:61) and the 27-cell stencil walk of
+// charmm_nonbonded_constraint.py:78-83.  Pair-set definition: every pair
+// with minimum-image r <= rc that is not in bonded_particles — the list holds a superset
+// (rc + skin against the i-block bounding box) and the pair kernel applies the canonical
+// fp32 test.
+//
+// Layout.  Atoms are sorted by cell (x fastest), 32 consecutive sorted atoms form an
+// i-block.  For each i-block the builder emits chunks of 32 j-atoms (tile-order indices)
+// whose tile index is larger than the block's (half shell by index) and that lie within
+// rc+skin of the block's periodic bounding box; chunk 0 is the block itself.  Chunks are
+// grouped into work units of at most seg_chunks chunks taken from a global pool.
+// A chunk that contains an excluded or 1-4 pair, padding, or belongs to a ragged last
+// block carries 2 x 32 words of masks, already rotated so that lane l at rotation step k
+// tests bit k (pair i = l, j-slot = (l + k) & 31).
+#include <cub/cub.cuh>
+
+#include "mdk_common.cuh"
+
+namespace mdk {
+
+struct GridParams {
+    int n, n_blocks;
+    float L[3], invL[3];
+    int ncell[3];
+    float inv_cw[3];
+    float R, R2;
+    float skin_half2;
+};
+
+// ---------------------------------------------------------------------------
+__global__ void k_cell_keys(int n, const double *__restrict__ x_cur, GridParams g,
+                            const double3 Ld, unsigned *__restrict__ keys, int *__restrict__ idx) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    double L[3] = {Ld.x, Ld.y, Ld.z};
+    int cidx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double x = x_cur[3 * a + d];
+        float w = (float)(x - L[d] * rint(x / L[d]));
+        int ci = (int)floorf((w + 0.5f * g.L[d]) * g.inv_cw[d]);
+        cidx[d] = min(max(ci, 0), g.ncell[d] - 1);
+    }
+    keys[a] = (unsigned)((cidx[2] * g.ncell[1] + cidx[1]) * g.ncell[0] + cidx[0]);
+    idx[a] = a;
+}
+
+__global__ void k_cell_start(int n, int ncells, const unsigned *__restrict__ keys_sorted,
+                             int *__restrict__ cell_start) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncells) return;
+    // lower_bound(keys_sorted, c)
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (keys_sorted[mid] < (unsigned)c) lo = mid + 1; else hi = mid;
+    }
+    cell_start[c] = lo;
+}
+
+// tile-order gather of positions / charges / LJ parameters; also resets the displacement
+// reference.  Slots >= n (ragged last block) are parked at the origin with zero charge/eps.
+__global__ void k_gather_sorted(int n, int n_pad, const int *__restrict__ order,
+                                const double *__restrict__ x_cur, const float *__restrict__ q,
+                                const float4 *__restrict__ lj4, bool have_lj, float sqrt_ke,
+                                const double3 Ld, float4 *__restrict__ xs, float4 *__restrict__ xs_ref,
+                                float4 *__restrict__ ljs, int *__restrict__ inv_order) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pad) return;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), l = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < n) {
+        int a = order[k];
+        inv_order[a] = k;
+        double L[3] = {Ld.x, Ld.y, Ld.z};
+        float w[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double x = x_cur[3 * a + d];
+            w[d] = (float)(x - L[d] * rint(x / L[d]));
+        }
+        p = make_float4(w[0], w[1], w[2], q[a] * sqrt_ke);
+        if (have_lj) {
+            float4 v = lj4[a];
+            l = make_float4(2.f * sqrtf(v.x), 0.5f * v.y, 2.f * sqrtf(v.z), 0.5f * v.w);
+        }
+    }
+    xs[k] = p; xs_ref[k] = p; ljs[k] = l;
+}
+
+// exclusion / 1-4 tables translated to tile slots
+__global__ void k_tables_sorted(int n, const int *__restrict__ order, const int *__restrict__ inv_order,
+                                const int *__restrict__ tab, int w, int *__restrict__ tab_s) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * w) return;
+    int k = t / w, e = t - k * w;
+    int p = tab[(size_t)order[k] * w + e];
+    tab_s[t] = p < 0 ? -1 : inv_order[p];
+}
+
+// xs <- wrap(x_cur) in the existing tile order + skin/2 displacement check (flags[1])
+__global__ void k_refresh_sorted(int n, const int *__restrict__ order, const double *__restrict__ x_cur,
+                                 const double3 Ld, GridParams g, float4 *__restrict__ xs,
+                                 const float4 *__restrict__ xs_ref, int *__restrict__ flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a = order[k];
+    double L[3] = {Ld.x, Ld.y, Ld.z};
+    float w[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double x = x_cur[3 * a + d];
+        w[d] = (float)(x - L[d] * rint(x / L[d]));
+    }
+    float4 r = xs_ref[k];
+    float dx = min_image(w[0] - r.x, g.L[0], g.invL[0]);
+    float dy = min_image(w[1] - r.y, g.L[1], g.invL[1]);
+    float dz = min_image(w[2] - r.z, g.L[2], g.invL[2]);
+    if (dist2(dx, dy, dz) > g.skin_half2) flags[1] = 1;
+    float4 p = xs[k];
+    xs[k] = make_float4(w[0], w[1], w[2], p.w);
+}
+
+// one warp per i-block: periodic bounding box relative to the block's first atom
+__global__ void k_block_bbox(GridParams g, const float4 *__restrict__ xs, float4 *__restrict__ bbc,
+                             float4 *__restrict__ bbh) {
+    int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (b >= g.n_blocks) return;
+    int k = b * TILE + lane;
+    bool valid = k < g.n;
+    float4 p = xs[valid ? k : b * TILE];
+    float rx = __shfl_sync(0xffffffffu, p.x, 0), ry = __shfl_sync(0xffffffffu, p.y, 0),
+          rz = __shfl_sync(0xffffffffu, p.z, 0);
+    float d[3] = {min_image(p.x - rx, g.L[0], g.invL[0]), min_image(p.y - ry, g.L[1], g.invL[1]),
+                  min_image(p.z - rz, g.L[2], g.invL[2])};
+    float mn[3], mx[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = mx[a] = d[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    }
+    if (lane == 0) {
+        bbc[b] = make_float4(rx + 0.5f * (mn[0] + mx[0]), ry + 0.5f * (mn[1] + mx[1]),
+                             rz + 0.5f * (mn[2] + mx[2]), 0.f);
+        bbh[b] = make_float4(0.5f * (mx[0] - mn[0]) + 1e-4f, 0.5f * (mx[1] - mn[1]) + 1e-4f,
+                             0.5f * (mx[2] - mn[2]) + 1e-4f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct BuildOut {
+    int4 *units;
+    int *chunk_j, *chunk_mask;
+    unsigned *mask_excl, *mask_14;
+    int *counters;  // [0]=units [1]=chunks [2]=mask slots
+    int *flags;     // [2]=overflow
+    int cap_units, cap_chunks, cap_masks;
+    int seg;
+};
+
+struct BlockEmitter {
+    int b, lane, n;
+    bool i_valid, ragged;
+    int seg_base, seg_fill;
+    const int *excl_s, *p14_s;
+    int wb, ws;
+    BuildOut o;
+
+    __device__ int alloc(int *ctr, int count) {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(ctr, count);
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+    __device__ void close_unit() {
+        if (seg_fill > 0) {
+            int u = alloc(&o.counters[0], 1);
+            if (u < o.cap_units) {
+                if (lane == 0) o.units[u] = make_int4(b, seg_base, seg_fill, 0);
+            } else if (lane == 0) o.flags[2] = 1;
+        }
+        seg_fill = 0;
+    }
+    __device__ void begin() { seg_base = alloc(&o.counters[1], o.seg); seg_fill = 0; }
+    // j: tile index of this lane's j atom, or -1 (padding)
+    __device__ void emit(int j, bool diagonal) {
+        if (seg_fill == o.seg) { close_unit(); seg_base = alloc(&o.counters[1], o.seg); }
+        int chunk = seg_base + seg_fill;
+        ++seg_fill;
+        unsigned jm = 0u, j14 = 0u;
+        if (j < 0) {
+            jm = 0xffffffffu;
+        } else {
+            for (int e = 0; e < wb; ++e) {
+                int p = excl_s[(size_t)j * wb + e];
+                if (p >= 0 && (p >> 5) == b) jm |= 1u << (p & 31);
+            }
+            for (int e = 0; e < ws; ++e) {
+                int p = p14_s[(size_t)j * ws + e];
+                if (p >= 0 && (p >> 5) == b) j14 |= 1u << (p & 31);
+            }
+            j14 &= ~jm;  // excluded wins over 1-4 (charmm_nonbonded_constraint.py:83 before :92)
+            if (diagonal) jm |= ~((1u << lane) - 1u);  // keep only i-slot < j-slot
+        }
+        bool flagged = __ballot_sync(0xffffffffu, (jm | j14) != 0u) != 0u || ragged;
+        bool ok = chunk + 1 <= o.cap_chunks;
+        if (!ok && lane == 0) o.flags[2] = 1;
+        int slot = -1;
+        if (flagged) {
+            unsigned mi = 0u, m14 = 0u;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                int src = (lane + k) & 31;
+                unsigned v = __shfl_sync(0xffffffffu, jm, src);
+                unsigned w = __shfl_sync(0xffffffffu, j14, src);
+                mi |= ((v >> lane) & 1u) << k;
+                m14 |= ((w >> lane) & 1u) << k;
+            }
+            if (!i_valid) mi = 0xffffffffu;
+            slot = alloc(&o.counters[2], 1);
+            if (slot < o.cap_masks) {
+                o.mask_excl[(size_t)slot * 32 + lane] = mi;
+                o.mask_14[(size_t)slot * 32 + lane] = m14;
+            } else {
+                if (lane == 0) o.flags[2] = 1;
+                slot = -1;
+            }
+        }
+        if (ok) {
+            o.chunk_j[(size_t)chunk * 32 + lane] = j < 0 ? 0 : j;
+            if (lane == 0) o.chunk_mask[chunk] = slot;
+        }
+    }
+};
+
+__device__ __forceinline__ int imod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+constexpr int BUILD_WARPS = 4;
+
+__global__ void __launch_bounds__(BUILD_WARPS * 32)
+k_build_lists(GridParams g, const float4 *__restrict__ xs, const float4 *__restrict__ bbc,
+              const float4 *__restrict__ bbh, const int *__restrict__ cell_start,
+              const int *__restrict__ excl_s, int wb, const int *__restrict__ p14_s, int ws,
+              BuildOut o) {
+    __shared__ int stage_all[BUILD_WARPS][64];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *stage = stage_all[wid];
+    int warp_global = blockIdx.x * BUILD_WARPS + wid, n_warps = gridDim.x * BUILD_WARPS;
+    for (int b = warp_global; b < g.n_blocks; b += n_warps) {
+        float4 c = bbc[b], h = bbh[b];
+        BlockEmitter em;
+        em.b = b; em.lane = lane; em.n = g.n;
+        em.i_valid = (b * TILE + lane) < g.n;
+        em.ragged = (b == g.n_blocks - 1) && (g.n & 31);
+        em.excl_s = excl_s; em.p14_s = p14_s; em.wb = wb; em.ws = ws; em.o = o;
+        em.begin();
+        {
+            int k = b * TILE + lane;
+            em.emit(k < g.n ? k : -1, true);
+        }
+        const int first_j = (b + 1) * TILE;
+        // candidate cell ranges: bbox +- R (plus a rounding margin), periodic
+        float cc[3] = {c.x, c.y, c.z}, hh[3] = {h.x, h.y, h.z};
+        int lo[3], len[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float ext = hh[a] + g.R + 1e-3f + 1e-5f * g.L[a];
+            int l0 = (int)floorf((cc[a] - ext + 0.5f * g.L[a]) * g.inv_cw[a]);
+            int h0 = (int)floorf((cc[a] + ext + 0.5f * g.L[a]) * g.inv_cw[a]);
+            int ln = h0 - l0 + 1;
+            if (ln >= g.ncell[a]) { l0 = 0; ln = g.ncell[a]; }
+            lo[a] = imod(l0, g.ncell[a]);
+            len[a] = ln;
+        }
+        int nstage = 0;
+        for (int iz = 0; iz < len[2]; ++iz) {
+            int zz = lo[2] + iz; if (zz >= g.ncell[2]) zz -= g.ncell[2];
+            for (int iy = 0; iy < len[1]; ++iy) {
+                int yy = lo[1] + iy; if (yy >= g.ncell[1]) yy -= g.ncell[1];
+                int row = (zz * g.ncell[1] + yy) * g.ncell[0];
+                // one or two contiguous x segments
+                int x0 = lo[0], cnt0 = min(len[0], g.ncell[0] - lo[0]);
+                int cnt1 = len[0] - cnt0;
+#pragma unroll 1
+                for (int sgm = 0; sgm < 2; ++sgm) {
+                    int xa = sgm == 0 ? x0 : 0, cn = sgm == 0 ? cnt0 : cnt1;
+                    if (cn <= 0) continue;
+                    int s = cell_start[row + xa], e = cell_start[row + xa + cn];
+                    s = max(s, first_j);
+                    for (int base = s; base < e; base += 32) {
+                        int j = base + lane;
+                        bool pass = false;
+                        if (j < e) {
+                            float4 p = xs[j];
+                            float dx = fmaxf(fabsf(min_image(p.x - cc[0], g.L[0], g.invL[0])) - hh[0], 0.f);
+                            float dy = fmaxf(fabsf(min_image(p.y - cc[1], g.L[1], g.invL[1])) - hh[1], 0.f);
+                            float dz = fmaxf(fabsf(min_image(p.z - cc[2], g.L[2], g.invL[2])) - hh[2], 0.f);
+                            pass = (dx * dx + dy * dy + dz * dz) <= g.R2;
+                        }
+                        unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) stage[nstage + __popc(bal & ((1u << lane) - 1u))] = j;
+                        nstage += __popc(bal);
+                        __syncwarp();
+                        if (nstage >= 32) {
+                            int jj = stage[lane];
+                            int rest = stage[32 + lane];
+                            __syncwarp();
+                            em.emit(jj, false);
+                            stage[lane] = rest;
+                            nstage -= 32;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+        if (nstage > 0) em.emit(lane < nstage ? stage[lane] : -1, false);
+        __syncwarp();
+        em.close_unit();
+    }
+}
+
+// ---------------------------------------------------------------------------
+static GridParams make_grid_params(mdk_ctx *c) {
+    GridParams g{};
+    g.n = c->n;
+    g.n_blocks = c->n_blocks;
+    for (int a = 0; a < 3; ++a) {
+        g.L[a] = c->box.L[a]; g.invL[a] = c->box.invL[a];
+        g.ncell[a] = c->ncell[a];
+        g.inv_cw[a] = 1.0f / c->cellw[a];
+    }
+    float rc = fmaxf(c->have_lj ? c->rc_lj : 0.f, c->have_coul ? c->rc_coul : 0.f);
+    g.R = rc + c->skin;
+    g.R2 = g.R * g.R;
+    g.skin_half2 = 0.25f * c->skin * c->skin;
+    return g;
+}
+
+static int check_cutoff(mdk_ctx *c) {
+    float rc = fmaxf(c->have_lj ? c->rc_lj : 0.f, c->have_coul ? c->rc_coul : 0.f);
+    // cell_list.py:56-69: cutoff 0 or floor(L / rc) < 2 is a poorly defined list
+    if (c->have_lj && c->rc_lj <= 0.f)
+        return fail(c, MDK_ERR_CUTOFF_TOO_LARGE, "Cutoff radius is poor defined, current value %.3f", c->rc_lj);
+    for (int a = 0; a < 3; ++a)
+        if (rc > 0.f && floor(c->box.Ld[a] / rc) < 2)
+            return fail(c, MDK_ERR_CUTOFF_TOO_LARGE, "The cutoff_radius is too large to create cell list");
+    return MDK_OK;
+}
+
+int nlist_refresh_sorted(mdk_ctx *c) {
+    if (!c->nlist_valid) return MDK_OK;
+    GridParams g = make_grid_params(c);
+    double3 Ld = make_double3(c->box.Ld[0], c->box.Ld[1], c->box.Ld[2]);
+    k_refresh_sorted<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->order.p, c->x_cur.p, Ld, g,
+                                                               c->xs.p, c->xs_ref.p, c->flags.p);
+    ++c->n_launches;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+NlistView nlist_view(mdk_ctx *c) {
+    NlistView v;
+    v.units = c->units.p; v.n_units = c->counters.p;
+    v.chunk_j = c->chunk_j.p; v.chunk_mask = c->chunk_mask.p;
+    v.mask_excl = c->mask_excl.p; v.mask_14 = c->mask_14.p;
+    return v;
+}
+
+int nlist_rebuild(mdk_ctx *c) {
+    if (!c->have_box || c->n <= 0 || !c->have_pos)
+        return fail(c, MDK_ERR_NOT_BOUND, "neighbour list needs box, atoms and positions");
+    MDK_TRY(check_cutoff(c));
+    PhaseTimer pt(c, PH_NLIST);
+    const int n = c->n;
+    c->n_blocks = (n + TILE - 1) / TILE;
+    c->n_pad = c->n_blocks * TILE;
+    // cell geometry: y/z width ~ cbrt(32 / rho) so that 32 consecutive sorted atoms are
+    // roughly cubic, x width half of that (finer range ends along the contiguous axis)
+    double V = c->box.Ld[0] * c->box.Ld[1] * c->box.Ld[2];
+    double rho = n / V;
+    float rc = fmaxf(c->have_lj ? c->rc_lj : 0.f, c->have_coul ? c->rc_coul : 0.f);
+    double R = rc + c->skin;
+    double cyz = cbrt(32.0 / rho);
+    if (cyz < 3.0) cyz = 3.0;
+    if (cyz > R && R > 0) cyz = R;
+    double target[3] = {0.5 * cyz, cyz, cyz};
+    long long ncells = 1;
+    for (int a = 0; a < 3; ++a) {
+        int nc = (int)floor(c->box.Ld[a] / target[a]);
+        if (nc < 1) nc = 1;
+        if (nc > 1024) nc = 1024;
+        c->ncell[a] = nc;
+        c->cellw[a] = (float)(c->box.Ld[a] / nc);
+        ncells *= nc;
+    }
+    GridParams g = make_grid_params(c);
+    double3 Ld = make_double3(c->box.Ld[0], c->box.Ld[1], c->box.Ld[2]);
+
+    MDK_CUDA(c, c->cell_key.reserve(n)); MDK_CUDA(c, c->cell_key_sorted.reserve(n));
+    MDK_CUDA(c, c->idx_tmp.reserve(n)); MDK_CUDA(c, c->order.reserve(n));
+    MDK_CUDA(c, c->inv_order.reserve(n)); MDK_CUDA(c, c->cell_start.reserve((size_t)ncells + 1));
+    MDK_CUDA(c, c->xs.reserve(c->n_pad)); MDK_CUDA(c, c->xs_ref.reserve(c->n_pad));
+    MDK_CUDA(c, c->ljs.reserve(c->n_pad)); MDK_CUDA(c, c->f_acc.reserve((size_t)c->n_pad * 3));
+    MDK_CUDA(c, c->bb_center.reserve(c->n_blocks)); MDK_CUDA(c, c->bb_half.reserve(c->n_blocks));
+    MDK_CUDA(c, c->excl_s.reserve((size_t)n * (c->wb > 0 ? c->wb : 1)));
+    MDK_CUDA(c, c->p14_s.reserve((size_t)n * (c->ws > 0 ? c->ws : 1)));
+
+    const int T = 256;
+    k_cell_keys<<<(n + T - 1) / T, T, 0, c->stream>>>(n, c->x_cur.p, g, Ld, c->cell_key.p, c->idx_tmp.p);
+    int end_bit = 1;
+    while ((1ll << end_bit) < ncells) ++end_bit;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->cell_key.p, c->cell_key_sorted.p, c->idx_tmp.p,
+                                    c->order.p, n, 0, end_bit, c->stream);
+    MDK_CUDA(c, c->sort_tmp.reserve(tmp_bytes));
+    MDK_CUDA(c, cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp_bytes, c->cell_key.p, c->cell_key_sorted.p,
+                                                c->idx_tmp.p, c->order.p, n, 0, end_bit, c->stream));
+    k_cell_start<<<(int)((ncells + 1 + T - 1) / T), T, 0, c->stream>>>(n, (int)ncells, c->cell_key_sorted.p,
+                                                                       c->cell_start.p);
+    float sqrt_ke = c->have_coul ? (float)sqrt(c->k_e) : 0.f;
+    k_gather_sorted<<<(c->n_pad + T - 1) / T, T, 0, c->stream>>>(n, c->n_pad, c->order.p, c->x_cur.p, c->q.p,
+                                                                 c->lj4.p, c->have_lj, sqrt_ke, Ld, c->xs.p,
+                                                                 c->xs_ref.p, c->ljs.p, c->inv_order.p);
+    if (c->wb > 0)
+        k_tables_sorted<<<(n * c->wb + T - 1) / T, T, 0, c->stream>>>(n, c->order.p, c->inv_order.p, c->excl.p,
+                                                                      c->wb, c->excl_s.p);
+    if (c->ws > 0)
+        k_tables_sorted<<<(n * c->ws + T - 1) / T, T, 0, c->stream>>>(n, c->order.p, c->inv_order.p, c->p14.p,
+                                                                      c->ws, c->p14_s.p);
+    k_block_bbox<<<(c->n_blocks * 32 + T - 1) / T, T, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p);
+    c->n_launches += 7;
+    MDK_CUDA(c, cudaGetLastError());
+
+    // work-unit granularity: enough units to fill the machine a few times over
+    {
+        double per_block = rho * (4.0 / 3.0) * M_PI * R * R * R * 0.5 * 2.2 / 32.0 + 1.0;  // chunks (estimate)
+        double total_chunks = per_block * c->n_blocks;
+        double want_units = 8.0 * c->sm_count * 8;  // ~8 resident warps per SM, 8 waves
+        int seg = (int)(total_chunks / want_units);
+        if (seg < 2) seg = 2;
+        if (seg > 16) seg = 16;
+        c->seg_chunks = seg;
+        size_t est_chunks = (size_t)(total_chunks * 1.3) + (size_t)c->n_blocks * (seg + 1) + 1024;
+        if (c->cap_chunks < est_chunks) c->cap_chunks = est_chunks;
+        size_t est_units = est_chunks / seg + (size_t)c->n_blocks * 2 + 1024;
+        if (c->cap_units < est_units) c->cap_units = est_units;
+        size_t est_masks = (size_t)c->n_blocks * 8 + 1024;
+        if (c->cap_masks < est_masks) c->cap_masks = est_masks;
+    }
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        MDK_CUDA(c, c->units.reserve(c->cap_units));
+        MDK_CUDA(c, c->chunk_j.reserve(c->cap_chunks * 32));
+        MDK_CUDA(c, c->chunk_mask.reserve(c->cap_chunks));
+        MDK_CUDA(c, c->mask_excl.reserve(c->cap_masks * 32));
+        MDK_CUDA(c, c->mask_14.reserve(c->cap_masks * 32));
+        MDK_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(int), c->stream));
+        MDK_CUDA(c, cudaMemsetAsync(c->flags.p + 1, 0, 2 * sizeof(int), c->stream));
+        BuildOut o;
+        o.units = c->units.p; o.chunk_j = c->chunk_j.p; o.chunk_mask = c->chunk_mask.p;
+        o.mask_excl = c->mask_excl.p; o.mask_14 = c->mask_14.p;
+        o.counters = c->counters.p; o.flags = c->flags.p;
+        o.cap_units = (int)c->cap_units; o.cap_chunks = (int)c->cap_chunks; o.cap_masks = (int)c->cap_masks;
+        o.seg = c->seg_chunks;
+        int blocks = (c->n_blocks + BUILD_WARPS - 1) / BUILD_WARPS;
+        int max_blocks = c->sm_count * 16;
+        if (blocks > max_blocks) blocks = max_blocks;
+        k_build_lists<<<blocks, BUILD_WARPS * 32, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p,
+                                                                 c->cell_start.p, c->excl_s.p, c->wb,
+                                                                 c->p14_s.p, c->ws, o);
+        ++c->n_launches;
+        MDK_CUDA(c, cudaGetLastError());
+        int h_cnt[8], h_flags[4];
+        MDK_CUDA(c, cudaMemcpyAsync(h_cnt, c->counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!h_flags[2]) {
+            c->stat_units = h_cnt[0]; c->stat_chunks = h_cnt[1]; c->stat_masks = h_cnt[2];
+            c->nlist_valid = true;
+            ++c->n_rebuilds;
+            return MDK_OK;
+        }
+        // pool overflow: grow to what the builder asked for (plus slack) and redo
+        c->cap_chunks = (size_t)(h_cnt[1] * 1.25) + 1024;
+        c->cap_units = (size_t)(h_cnt[0] * 1.25) + 1024;
+        c->cap_masks = (size_t)(h_cnt[2] * 1.25) + 1024;
+    }
+    return fail(c, MDK_ERR_OOM, "tile list pools kept overflowing");
+}
+
+int nlist_ensure(mdk_ctx *c) {
+    if (c->nlist_valid) {
+        int h_flags[4];
+        MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!h_flags[1]) return MDK_OK;
+    }
+    return nlist_rebuild(c);
+}
+
+}  // namespace mdk

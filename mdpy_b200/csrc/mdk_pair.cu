@@ -1,0 +1,332 @@
+// mdk_pair.cu — pair-force kernel over the tile list: CHARMM Lennard-Jones (plain cutoff
+// or energy switch) and erfc direct-space Coulomb, half shell, fixed-point accumulation.
+//
+// Replaces CharmmNonbondedConstraint.cuda_kernel (charmm_nonbonded_constraint.py:110-181:
+// one thread per (atom, cell slot), O(B) exclusion scans, 7 global float atomics per pair)
+// and supplies the erfc direct-space term the reference does not have.
+//
+// Mapping.  One warp per work unit (i-block, up to seg chunks of 32 j-atoms).  Lane l owns
+// i-atom l for the whole unit (force in registers).  Each chunk's 32 j-atoms are staged in
+// shared memory (coalesced float4 gathers); at rotation step k lane l evaluates the pair
+// (i = l, j-slot = (l + k) & 31), so the 32 lanes always touch 32 distinct j-slots: the
+// j-force accumulators travel with the j-slot through a 3-register shuffle ring and are
+// flushed with one int64 atomic per component per j-atom per chunk.  Every pair is
+// evaluated once (Newton's third law), against the reference's twice-at-half-weight.
+#include "mdk_common.cuh"
+
+namespace mdk {
+
+struct PairParams {
+    float L[3], invL[3];
+    float rc2_lj, ron2, inv_ab3, rc2_max;  // CHARMM switch: (rc^2 - ron^2)^-3
+    float rc2_c, alpha, two_alpha_over_sqrtpi;
+    int n;
+    int shard_rank, shard_n;
+};
+
+// erfc(x) * exp(x^2) ~= t * P(t), t = 1 / (1 + 0.4 x): degree-8 least-squares fit on
+// x in [0, 4.2], max relative error 8e-9 in exact arithmetic, <4e-7 evaluated in fp32
+// (fit script: oracle/fit_erfc.py).
+__device__ __forceinline__ float erfcx_poly(float x) {
+    float t = __fdividef(1.0f, __fmaf_rn(0.4f, x, 1.0f));
+    float p = 1.2938003984e-02f;
+    p = __fmaf_rn(p, t, 8.5587749120e-03f);
+    p = __fmaf_rn(p, t, -2.5232078617e-01f);
+    p = __fmaf_rn(p, t, 5.1394868547e-01f);
+    p = __fmaf_rn(p, t, -2.5095656442e-01f);
+    p = __fmaf_rn(p, t, 3.5446957253e-01f);
+    p = __fmaf_rn(p, t, 1.5382895656e-01f);
+    p = __fmaf_rn(p, t, 2.3447514612e-01f);
+    p = __fmaf_rn(p, t, 2.2505821879e-01f);
+    return p * t;
+}
+
+constexpr int PAIR_WARPS = 8;
+
+template <bool DO_LJ, bool DO_COUL, bool SWITCH>
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
+       long long *__restrict__ f_acc, long long *__restrict__ e_acc, int *__restrict__ cursor) {
+    __shared__ float4 s_x[PAIR_WARPS][32];
+    __shared__ float4 s_lj[PAIR_WARPS][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n_units = *nl.n_units;
+    double e_lj_tot = 0.0, e_c_tot = 0.0;
+
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(cursor, 1);
+        u = __shfl_sync(0xffffffffu, u, 0) * P.shard_n + P.shard_rank;
+        if (u >= n_units) break;
+        const int4 unit = nl.units[u];
+        const int ia = unit.x * TILE + lane;
+        const float4 xi = xs[ia];
+        const float4 li = ljs[ia];
+        float fix = 0.f, fiy = 0.f, fiz = 0.f;
+        float e_lj = 0.f, e_c = 0.f;
+
+        for (int cidx = 0; cidx < unit.z; ++cidx) {
+            const int chunk = unit.y + cidx;
+            const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
+            const int mslot = nl.chunk_mask[chunk];
+            unsigned excl = 0u, m14 = 0u;
+            if (mslot >= 0) {
+                excl = nl.mask_excl[(size_t)mslot * 32 + lane];
+                if (DO_LJ) m14 = nl.mask_14[(size_t)mslot * 32 + lane];
+            }
+            __syncwarp();
+            s_x[wid][lane] = xs[j];
+            if (DO_LJ) s_lj[wid][lane] = ljs[j];
+            __syncwarp();
+            float fjx = 0.f, fjy = 0.f, fjz = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const int slot = (lane + k) & 31;
+                const float4 xj = s_x[wid][slot];
+                const float dx = min_image(xj.x - xi.x, P.L[0], P.invL[0]);
+                const float dy = min_image(xj.y - xi.y, P.L[1], P.invL[1]);
+                const float dz = min_image(xj.z - xi.z, P.L[2], P.invL[2]);
+                const float r2 = dist2(dx, dy, dz);
+                if (r2 <= P.rc2_max && !((excl >> k) & 1u)) {
+                    const float rinv = rsqrtf(r2);
+                    const float r2inv = rinv * rinv;
+                    float g = 0.f;  // dE/dr / r : F_i = g d, F_j = -g d  (d = x_j - x_i)
+                    if (DO_LJ) {
+                        if (r2 <= P.rc2_lj) {
+                            const float4 lj = s_lj[wid][slot];
+                            const bool is14 = (m14 >> k) & 1u;
+                            const float a = is14 ? li.z * lj.z : li.x * lj.x;       // 4 eps_ij
+                            const float s = is14 ? li.w + lj.w : li.y + lj.y;       // sigma_ij
+                            const float s2 = s * s * r2inv;
+                            const float s6 = s2 * s2 * s2;
+                            const float t = a * s6, w = t * s6;                      // 4 eps s^6, 4 eps s^12
+                            float e = w - t;
+                            float gl = (6.f * t - 12.f * w) * r2inv;
+                            if (SWITCH) {
+                                if (r2 > P.ron2) {
+                                    const float da = P.rc2_lj - r2;
+                                    const float S = da * da * (P.rc2_lj + 2.f * r2 - 3.f * P.ron2) * P.inv_ab3;
+                                    const float dS = 12.f * da * (P.ron2 - r2) * P.inv_ab3;  // (dS/dr)/r
+                                    gl = gl * S + e * dS;
+                                    e *= S;
+                                }
+                            }
+                            e_lj += e;
+                            g += gl;
+                        }
+                    }
+                    if (DO_COUL) {
+                        if (r2 <= P.rc2_c) {
+                            const float qq = xi.w * xj.w;
+                            const float r = r2 * rinv;
+                            const float ar = P.alpha * r;
+                            const float ex = __expf(-ar * ar);
+                            const float erfc_ar = erfcx_poly(ar) * ex;
+                            const float qr = qq * rinv;
+                            e_c += qr * erfc_ar;
+                            g -= qq * (erfc_ar * rinv + P.two_alpha_over_sqrtpi * ex) * r2inv;
+                        }
+                    }
+                    const float fx = g * dx, fy = g * dy, fz = g * dz;
+                    fix += fx; fiy += fy; fiz += fz;
+                    fjx -= fx; fjy -= fy; fjz -= fz;
+                }
+                // the accumulators follow the j-slot: lane l next serves slot (l + k + 1) & 31,
+                // whose running sum sits in lane l + 1
+                fjx = __shfl_sync(0xffffffffu, fjx, (lane + 1) & 31);
+                fjy = __shfl_sync(0xffffffffu, fjy, (lane + 1) & 31);
+                fjz = __shfl_sync(0xffffffffu, fjz, (lane + 1) & 31);
+            }
+            // after 32 rotations lane l holds the sum for slot l again
+            if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {
+                atomic_add_fix(&f_acc[3 * (size_t)j + 0], to_fix(fjx));
+                atomic_add_fix(&f_acc[3 * (size_t)j + 1], to_fix(fjy));
+                atomic_add_fix(&f_acc[3 * (size_t)j + 2], to_fix(fjz));
+            }
+        }
+        if (fix != 0.f || fiy != 0.f || fiz != 0.f) {
+            atomic_add_fix(&f_acc[3 * (size_t)ia + 0], to_fix(fix));
+            atomic_add_fix(&f_acc[3 * (size_t)ia + 1], to_fix(fiy));
+            atomic_add_fix(&f_acc[3 * (size_t)ia + 2], to_fix(fiz));
+        }
+        e_lj_tot += (double)e_lj;
+        e_c_tot += (double)e_c;
+    }
+    if (DO_LJ) {
+        double v = warp_sum(e_lj_tot);
+        if (lane == 0 && v != 0.0) atomic_add_fix(&e_acc[MDK_E_LJ], to_fix(v));
+    }
+    if (DO_COUL) {
+        double v = warp_sum(e_c_tot);
+        if (lane == 0 && v != 0.0) atomic_add_fix(&e_acc[MDK_E_COUL_DIRECT], to_fix(v));
+    }
+}
+
+static PairParams make_pair_params(mdk_ctx *c, bool do_lj, bool do_coul) {
+    PairParams P{};
+    for (int a = 0; a < 3; ++a) { P.L[a] = c->box.L[a]; P.invL[a] = c->box.invL[a]; }
+    P.rc2_lj = do_lj ? c->rc_lj * c->rc_lj : -1.f;
+    float ron = c->r_switch;
+    P.ron2 = ron * ron;
+    if (do_lj && ron < c->rc_lj) {
+        double a2 = (double)c->rc_lj * c->rc_lj, b2 = (double)ron * ron;
+        P.inv_ab3 = (float)(1.0 / ((a2 - b2) * (a2 - b2) * (a2 - b2)));
+    }
+    P.rc2_c = do_coul ? c->rc_coul * c->rc_coul : -1.f;
+    P.rc2_max = fmaxf(P.rc2_lj, P.rc2_c);
+    P.alpha = (float)c->alpha;
+    P.two_alpha_over_sqrtpi = (float)(2.0 * c->alpha / sqrt(M_PI));
+    P.n = c->n;
+    P.shard_rank = c->shard_rank; P.shard_n = c->shard_n;
+    return P;
+}
+
+int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
+    if (!do_lj && !do_coul) return MDK_OK;
+    if (do_lj && !c->have_lj) return fail(c, MDK_ERR_NOT_BOUND, "LJ term requested before mdk_set_lj");
+    if (do_coul && !c->have_coul) return fail(c, MDK_ERR_NOT_BOUND, "Coulomb term requested before mdk_set_coulomb");
+    PhaseTimer pt(c, PH_PAIR);
+    PairParams P = make_pair_params(c, do_lj, do_coul);
+    NlistView nl = nlist_view(c);
+    MDK_CUDA(c, cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
+    const bool sw = do_lj && c->r_switch < c->rc_lj;
+    int grid = c->sm_count * 4;
+    long long max_blocks = (c->stat_units + PAIR_WARPS - 1) / PAIR_WARPS;
+    if (max_blocks < 1) max_blocks = 1;
+    if (grid > max_blocks) grid = (int)max_blocks;
+    dim3 g(grid), b(PAIR_WARPS * 32);
+    int *cursor = c->counters.p + 3;
+#define LAUNCH(LJ, CO, SW)                                                                             \
+    k_pair<LJ, CO, SW><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->f_acc.p,                  \
+                                                 reinterpret_cast<long long *>(c->e_acc.p), cursor)
+    if (do_lj && do_coul) { if (sw) LAUNCH(true, true, true); else LAUNCH(true, true, false); }
+    else if (do_lj)       { if (sw) LAUNCH(true, false, true); else LAUNCH(true, false, false); }
+    else                  LAUNCH(false, true, false);
+#undef LAUNCH
+    c->n_launches += 1;
+    c->n_pair_launches += 1;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Excluded-pair Ewald correction: the reciprocal sum contains every pair, also the
+// bonded ones the direct sum skips; remove -k_e q_i q_j erf(alpha r)/r for each of them.
+__global__ void k_excl_correction(int n, int wb, const int *__restrict__ excl_s,
+                                  const float4 *__restrict__ xs, double Lx, double Ly, double Lz,
+                                  double alpha, long long *__restrict__ f_acc,
+                                  long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < n * wb) {
+        int k = t / wb;
+        int p = excl_s[t];
+        if (p > k) {
+            float4 a = xs[k], b = xs[p];
+            double d[3] = {(double)b.x - a.x, (double)b.y - a.y, (double)b.z - a.z};
+            d[0] -= Lx * rint(d[0] / Lx); d[1] -= Ly * rint(d[1] / Ly); d[2] -= Lz * rint(d[2] / Lz);
+            double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            double r = sqrt(r2);
+            double qq = (double)a.w * (double)b.w;
+            double ar = alpha * r;
+            double erf_ar = erf(ar);
+            e = -qq * erf_ar / r;
+            // dE/dr = -qq (2 alpha/sqrt(pi) exp(-a^2 r^2)/r - erf/r^2);  F_i = dE/dr d/r
+            double g = -qq * (1.1283791670955126 * alpha * exp(-ar * ar) / r - erf_ar / r2) / r;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                atomic_add_fix(&f_acc[3 * (size_t)k + x], to_fix(g * d[x]));
+                atomic_add_fix(&f_acc[3 * (size_t)p + x], to_fix(-g * d[x]));
+            }
+        }
+    }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[MDK_E_PME_EXCL], to_fix(e));
+}
+
+int pair_special(mdk_ctx *c, bool pme_excl) {
+    if (!pme_excl || c->wb <= 0) return MDK_OK;
+    PhaseTimer pt(c, PH_BONDED);
+    int total = c->n * c->wb;
+    k_excl_correction<<<(total + 255) / 256, 256, 0, c->stream>>>(
+        c->n, c->wb, c->excl_s.p, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,
+        reinterpret_cast<long long *>(c->e_acc.p));
+    ++c->n_launches;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Test hook: walk the tile list exactly like k_pair and emit every pair that passes the
+// canonical cutoff test and is not masked.
+__global__ void k_enumerate(PairParams P, NlistView nl, const float4 *__restrict__ xs,
+                            const int *__restrict__ order, int *__restrict__ out_i, int *__restrict__ out_j,
+                            unsigned long long cap, unsigned long long *__restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_units = *nl.n_units;
+    for (int u = warp; u < n_units; u += n_warps) {
+        const int4 unit = nl.units[u];
+        const int ia = unit.x * TILE + lane;
+        const float4 xi = xs[ia];
+        for (int cidx = 0; cidx < unit.z; ++cidx) {
+            const int chunk = unit.y + cidx;
+            const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
+            const int mslot = nl.chunk_mask[chunk];
+            unsigned excl = mslot >= 0 ? nl.mask_excl[(size_t)mslot * 32 + lane] : 0u;
+            const float4 xj_own = xs[j];
+            for (int k = 0; k < 32; ++k) {
+                const int slot = (lane + k) & 31;
+                float4 xj;
+                xj.x = __shfl_sync(0xffffffffu, xj_own.x, slot);
+                xj.y = __shfl_sync(0xffffffffu, xj_own.y, slot);
+                xj.z = __shfl_sync(0xffffffffu, xj_own.z, slot);
+                const int jj = __shfl_sync(0xffffffffu, j, slot);
+                const float dx = min_image(xj.x - xi.x, P.L[0], P.invL[0]);
+                const float dy = min_image(xj.y - xi.y, P.L[1], P.invL[1]);
+                const float dz = min_image(xj.z - xi.z, P.L[2], P.invL[2]);
+                const float r2 = dist2(dx, dy, dz);
+                if (r2 <= P.rc2_lj && !((excl >> k) & 1u)) {
+                    unsigned long long pos = atomicAdd(count, 1ull);
+                    if (pos < cap) {
+                        int a = order[ia], b = order[jj];
+                        out_i[pos] = a < b ? a : b;
+                        out_j[pos] = a < b ? b : a;
+                    }
+                }
+            }
+        }
+    }
+}
+
+int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out) {
+    if (!c->have_lj) return fail(c, MDK_ERR_NOT_BOUND, "mdk_get_pairs needs mdk_set_lj");
+    MDK_TRY(nlist_refresh_sorted(c));
+    MDK_TRY(nlist_ensure(c));
+    PairParams P = make_pair_params(c, true, false);
+    int *d_i = nullptr, *d_j = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    size_t capn = cap > 0 ? (size_t)cap : 1;
+    MDK_CUDA(c, cudaMalloc(&d_i, capn * sizeof(int)));
+    MDK_CUDA(c, cudaMalloc(&d_j, capn * sizeof(int)));
+    MDK_CUDA(c, cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+    MDK_CUDA(c, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
+    k_enumerate<<<c->sm_count * 4, 256, 0, c->stream>>>(P, nlist_view(c), c->xs.p, c->order.p, d_i, d_j,
+                                                       (unsigned long long)cap, d_cnt);
+    ++c->n_launches;
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    size_t got = h < (unsigned long long)cap ? (size_t)h : (size_t)cap;
+    if (e == cudaSuccess && got) {
+        e = cudaMemcpy(out_i, d_i, got * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(out_j, d_j, got * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_i); cudaFree(d_j); cudaFree(d_cnt);
+    MDK_CUDA(c, e);
+    *n_out = (int64_t)h;
+    return MDK_OK;
+}
+
+}  // namespace mdk

@@ -1,0 +1,541 @@
+// mdk_step.cu — everything around the pair/PME kernels inside one MD step: the
+// reference-semantics all-pairs Coulomb, CHARMM bonded terms, Verlet / Langevin updates
+// and the term dispatcher behind mdk_compute.
+#include "mdk_common.cuh"
+
+namespace mdk {
+
+// ===========================================================================
+// Bare Coulomb, all pairs, minimum image, no cutoff — ElectrostaticConstraint.cpu_kernel
+// (electrostatic_constraint.py:52-79): E = sum_{i<j, j not bonded to i} q_i q_j/(4 pi eps0 r).
+// O(N^2) by definition of the reference; evaluated in float64 (full shell, force on i only,
+// j staged through shared memory), then the bonded pairs are taken out again.
+constexpr int BARE_T = 128;
+
+__global__ void __launch_bounds__(BARE_T)
+k_coulomb_bare(int n, const float4 *__restrict__ xs, const float *__restrict__ q, const int *__restrict__ order,
+               double k_e, double Lx, double Ly, double Lz, long long *__restrict__ f_acc,
+               long long *__restrict__ e_acc) {
+    __shared__ double4 sj[BARE_T];
+    const int i = blockIdx.x * BARE_T + threadIdx.x;
+    double xi = 0, yi = 0, zi = 0, qi = 0;
+    if (i < n) { float4 a = xs[i]; xi = a.x; yi = a.y; zi = a.z; qi = k_e * (double)q[order[i]]; }
+    double fx = 0, fy = 0, fz = 0, e = 0;
+    for (int base = 0; base < n; base += BARE_T) {
+        int j = base + threadIdx.x;
+        double4 v = make_double4(0, 0, 0, 0);
+        if (j < n) { float4 b = xs[j]; v = make_double4(b.x, b.y, b.z, (double)q[order[j]]); }
+        __syncthreads();
+        sj[threadIdx.x] = v;
+        __syncthreads();
+        int lim = min(BARE_T, n - base);
+        for (int t = 0; t < lim; ++t) {
+            if (base + t == i) continue;
+            double4 b = sj[t];
+            double dx = b.x - xi, dy = b.y - yi, dz = b.z - zi;
+            dx -= Lx * rint(dx / Lx); dy -= Ly * rint(dy / Ly); dz -= Lz * rint(dz / Lz);
+            double r2 = dx * dx + dy * dy + dz * dz;
+            double rinv = rsqrt(r2);
+            double qq = qi * b.w;
+            double er = qq * rinv;
+            e += er;
+            double g = -er * rinv * rinv;  // dE/dr / r
+            fx += g * dx; fy += g * dy; fz += g * dz;
+        }
+    }
+    if (i < n) {
+        atomic_add_fix(&f_acc[3 * (size_t)i + 0], to_fix(fx));
+        atomic_add_fix(&f_acc[3 * (size_t)i + 1], to_fix(fy));
+        atomic_add_fix(&f_acc[3 * (size_t)i + 2], to_fix(fz));
+    }
+    e = warp_sum(0.5 * e);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[MDK_E_COUL_BARE], to_fix(e));
+}
+
+__global__ void k_coulomb_bare_excl(int n, int wb, const int *__restrict__ excl_s, const float4 *__restrict__ xs,
+                                    const float *__restrict__ q, const int *__restrict__ order, double k_e,
+                                    double Lx, double Ly, double Lz, long long *__restrict__ f_acc,
+                                    long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < n * wb) {
+        int k = t / wb;
+        int p = excl_s[t];
+        if (p > k) {
+            float4 a = xs[k], b = xs[p];
+            double dx = (double)b.x - a.x, dy = (double)b.y - a.y, dz = (double)b.z - a.z;
+            dx -= Lx * rint(dx / Lx); dy -= Ly * rint(dy / Ly); dz -= Lz * rint(dz / Lz);
+            double r2 = dx * dx + dy * dy + dz * dz;
+            double rinv = rsqrt(r2);
+            double qq = k_e * (double)q[order[k]] * (double)q[order[p]];
+            e = -qq * rinv;
+            double g = qq * rinv * rinv * rinv;  // minus the pair's dE/dr / r
+            atomic_add_fix(&f_acc[3 * (size_t)k + 0], to_fix(g * dx));
+            atomic_add_fix(&f_acc[3 * (size_t)k + 1], to_fix(g * dy));
+            atomic_add_fix(&f_acc[3 * (size_t)k + 2], to_fix(g * dz));
+            atomic_add_fix(&f_acc[3 * (size_t)p + 0], to_fix(-g * dx));
+            atomic_add_fix(&f_acc[3 * (size_t)p + 1], to_fix(-g * dy));
+            atomic_add_fix(&f_acc[3 * (size_t)p + 2], to_fix(-g * dz));
+        }
+    }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[MDK_E_COUL_BARE], to_fix(e));
+}
+
+int coulomb_bare(mdk_ctx *c) {
+    if (!c->have_coul) return fail(c, MDK_ERR_NOT_BOUND, "Coulomb term requested before mdk_set_coulomb");
+    PhaseTimer pt(c, PH_BARE);
+    long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
+    k_coulomb_bare<<<(c->n + BARE_T - 1) / BARE_T, BARE_T, 0, c->stream>>>(
+        c->n, c->xs.p, c->q.p, c->order.p, c->k_e, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->f_acc.p, e_acc);
+    ++c->n_launches;
+    if (c->wb > 0) {
+        int total = c->n * c->wb;
+        k_coulomb_bare_excl<<<(total + 255) / 256, 256, 0, c->stream>>>(
+            c->n, c->wb, c->excl_s.p, c->xs.p, c->q.p, c->order.p, c->k_e, c->box.Ld[0], c->box.Ld[1],
+            c->box.Ld[2], c->f_acc.p, e_acc);
+        ++c->n_launches;
+    }
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// ===========================================================================
+// CHARMM bonded terms.  One thread per term, fp32 geometry on the wrapped
+// tile-order positions, minimum image per bond vector, fixed-point force atomics.
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+struct BoxF { float L[3], invL[3]; };
+__device__ __forceinline__ V3 mi_vec(float4 a, float4 b, const BoxF &bx) {  // b - a, minimum image
+    return {min_image(b.x - a.x, bx.L[0], bx.invL[0]), min_image(b.y - a.y, bx.L[1], bx.invL[1]),
+            min_image(b.z - a.z, bx.L[2], bx.invL[2])};
+}
+__device__ __forceinline__ void add_force(long long *f_acc, int slot, V3 f) {
+    atomic_add_fix(&f_acc[3 * (size_t)slot + 0], to_fix(f.x));
+    atomic_add_fix(&f_acc[3 * (size_t)slot + 1], to_fix(f.y));
+    atomic_add_fix(&f_acc[3 * (size_t)slot + 2], to_fix(f.z));
+}
+__device__ __forceinline__ void block_energy(double e, long long *e_acc, int which) {
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[which], to_fix(e));
+}
+
+// E = k (r - r0)^2   (charmm_bond_constraint.py:53-73)
+__global__ void k_bonds(int nb, const int *__restrict__ idx, const float *__restrict__ par,
+                        const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
+                        long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < nb) {
+        int s1 = inv_order[idx[2 * t]], s2 = inv_order[idx[2 * t + 1]];
+        float k = par[2 * t], r0 = par[2 * t + 1];
+        V3 d = mi_vec(xs[s1], xs[s2], bx);
+        float r = sqrtf(dot(d, d));
+        float dr = r - r0;
+        e = (double)(k * dr * dr);
+        V3 f = (2.f * k * dr / r) * d;  // force on atom 1 (toward 2 when stretched)
+        add_force(f_acc, s1, f);
+        add_force(f_acc, s2, -1.f * f);
+    }
+    block_energy(e, e_acc, MDK_E_BOND);
+}
+
+// E = k (theta - theta0)^2 + k_ub (r13 - r_ub)^2   (charmm_angle_constraint.py:55-96)
+__global__ void k_angles(int na, const int *__restrict__ idx, const float *__restrict__ par,
+                         const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
+                         long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < na) {
+        int s1 = inv_order[idx[3 * t]], s2 = inv_order[idx[3 * t + 1]], s3 = inv_order[idx[3 * t + 2]];
+        float k = par[4 * t], th0 = par[4 * t + 1], ku = par[4 * t + 2], u0 = par[4 * t + 3];
+        float4 p1 = xs[s1], p2 = xs[s2], p3 = xs[s3];
+        V3 r21 = mi_vec(p2, p1, bx), r23 = mi_vec(p2, p3, bx);
+        float l21 = sqrtf(dot(r21, r21)), l23 = sqrtf(dot(r23, r23));
+        float ct = dot(r21, r23) / (l21 * l23);
+        ct = fminf(1.f, fmaxf(-1.f, ct));
+        float th = acosf(ct);
+        float st = sqrtf(fmaxf(1.f - ct * ct, 1e-12f));
+        float dEdth = 2.f * k * (th - th0);
+        // d theta / d r1 = -(r23/l23 - ct r21/l21) / (l21 st)
+        V3 e21 = (1.f / l21) * r21, e23 = (1.f / l23) * r23;
+        V3 f1 = (dEdth / (l21 * st)) * (e23 - ct * e21);
+        V3 f3 = (dEdth / (l23 * st)) * (e21 - ct * e23);
+        e = (double)(k * (th - th0) * (th - th0));
+        add_force(f_acc, s2, -1.f * (f1 + f3));
+        if (ku != 0.f) {  // Urey-Bradley 1-3 spring acts on the end atoms only
+            V3 r13 = mi_vec(p1, p3, bx);
+            float l13 = sqrtf(dot(r13, r13));
+            float du = l13 - u0;
+            e += (double)(ku * du * du);
+            V3 fu = (2.f * ku * du / l13) * r13;
+            f1 = f1 + fu;
+            f3 = f3 - fu;
+        }
+        add_force(f_acc, s1, f1);
+        add_force(f_acc, s3, f3);
+    }
+    block_energy(e, e_acc, MDK_E_ANGLE);
+}
+
+// Torsion geometry shared by dihedrals and impropers: phi by the reference's atan2
+// convention (utils/geometry.py:84-96), analytic gradient (Blondel & Karplus form).
+__device__ __forceinline__ float torsion(float4 p1, float4 p2, float4 p3, float4 p4, const BoxF &bx, V3 &g1,
+                                         V3 &g2, V3 &g3, V3 &g4) {
+    V3 r1 = mi_vec(p1, p2, bx), r2 = mi_vec(p2, p3, bx), r3 = mi_vec(p3, p4, bx);
+    V3 n1 = cross(r1, r2), n2 = cross(r2, r3);
+    float l2 = sqrtf(dot(r2, r2));
+    float x = l2 * dot(r1, n2), y = dot(n1, n2);
+    float phi = atan2f(x, y);
+    float n1sq = fmaxf(dot(n1, n1), 1e-20f), n2sq = fmaxf(dot(n2, n2), 1e-20f);
+    // d phi / d r_a, d phi / d r_d
+    g1 = (-l2 / n1sq) * n1;
+    g4 = (l2 / n2sq) * n2;
+    const float a = -dot(r1, r2) / (l2 * l2), b = -dot(r3, r2) / (l2 * l2);
+    g2 = (a - 1.f) * g1 + (-b) * g4;
+    g3 = (b - 1.f) * g4 + (-a) * g1;
+    return phi;
+}
+
+// E = k (1 + cos(n phi - delta))   (charmm_dihedral_constraint.py:59-95; the force is the
+// analytic gradient of this energy — the reference's `-k (1 - n sin(..))` at :80 is not).
+__global__ void k_dihedrals(int nd, const int *__restrict__ idx, const float *__restrict__ par,
+                            const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
+                            long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < nd) {
+        int s[4];
+        for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
+        float k = par[3 * t], nn = par[3 * t + 1], delta = par[3 * t + 2];
+        V3 g1, g2, g3, g4;
+        float phi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
+        float arg = nn * phi - delta;
+        e = (double)(k * (1.f + cosf(arg)));
+        float dEdphi = -k * nn * sinf(arg);
+        add_force(f_acc, s[0], (-dEdphi) * g1);
+        add_force(f_acc, s[1], (-dEdphi) * g2);
+        add_force(f_acc, s[2], (-dEdphi) * g3);
+        add_force(f_acc, s[3], (-dEdphi) * g4);
+    }
+    block_energy(e, e_acc, MDK_E_DIHEDRAL);
+}
+
+// E = k (psi - psi0)^2   (charmm_improper_constraint.py:57-94)
+__global__ void k_impropers(int ni, const int *__restrict__ idx, const float *__restrict__ par,
+                            const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
+                            long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < ni) {
+        int s[4];
+        for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
+        float k = par[2 * t], psi0 = par[2 * t + 1];
+        V3 g1, g2, g3, g4;
+        float psi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
+        float d = psi - psi0;
+        e = (double)(k * d * d);
+        float dE = 2.f * k * d;
+        add_force(f_acc, s[0], (-dE) * g1);
+        add_force(f_acc, s[1], (-dE) * g2);
+        add_force(f_acc, s[2], (-dE) * g3);
+        add_force(f_acc, s[3], (-dE) * g4);
+    }
+    block_energy(e, e_acc, MDK_E_IMPROPER);
+}
+
+int bonded_compute(mdk_ctx *c, unsigned terms) {
+    BoxF bx;
+    for (int a = 0; a < 3; ++a) { bx.L[a] = c->box.L[a]; bx.invL[a] = c->box.invL[a]; }
+    long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
+    PhaseTimer pt(c, PH_BONDED);
+    const int T = 128;
+    if ((terms & MDK_TERM_BOND) && c->bonded[0].n > 0) {
+        k_bonds<<<(c->bonded[0].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[0].n, c->bonded[0].idx.p, c->bonded[0].par.p,
+                                                                  c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);
+        ++c->n_launches;
+    }
+    if ((terms & MDK_TERM_ANGLE) && c->bonded[1].n > 0) {
+        k_angles<<<(c->bonded[1].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[1].n, c->bonded[1].idx.p, c->bonded[1].par.p,
+                                                                   c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);
+        ++c->n_launches;
+    }
+    if ((terms & MDK_TERM_DIHEDRAL) && c->bonded[2].n > 0) {
+        k_dihedrals<<<(c->bonded[2].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[2].n, c->bonded[2].idx.p,
+                                                                      c->bonded[2].par.p, c->inv_order.p, c->xs.p, bx,
+                                                                      c->f_acc.p, e_acc);
+        ++c->n_launches;
+    }
+    if ((terms & MDK_TERM_IMPROPER) && c->bonded[3].n > 0) {
+        k_impropers<<<(c->bonded[3].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[3].n, c->bonded[3].idx.p,
+                                                                      c->bonded[3].par.p, c->inv_order.p, c->xs.p, bx,
+                                                                      c->f_acc.p, e_acc);
+        ++c->n_launches;
+    }
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// ===========================================================================
+// term dispatcher
+int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
+    if (!c->have_box || c->n <= 0 || !c->have_pos)
+        return fail(c, MDK_ERR_NOT_BOUND, "mdk_compute before box/atoms/positions were set");
+    MDK_TRY(nlist_refresh_sorted(c));
+    MDK_TRY(nlist_ensure(c));
+    MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
+    MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
+    MDK_TRY(pair_compute(c, terms & MDK_TERM_LJ, terms & MDK_TERM_COUL_DIRECT));
+    if (terms & MDK_TERM_PME_RECIP) {
+        MDK_TRY(pme_compute(c));
+        MDK_TRY(pair_special(c, true));
+    }
+    if (terms & MDK_TERM_COUL_BARE) MDK_TRY(coulomb_bare(c));
+    if (terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER))
+        MDK_TRY(bonded_compute(c, terms));
+    if (sync_energies) {
+        long long h[MDK_NUM_ENERGIES];
+        MDK_CUDA(c, cudaMemcpyAsync(h, c->e_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < MDK_NUM_ENERGIES; ++k) c->last_e[k] = (double)h[k] / FIX_SCALE;
+        if (terms & MDK_TERM_PME_RECIP) c->last_e[MDK_E_PME_SELF] = c->e_self_bg;
+    }
+    return MDK_OK;
+}
+
+// ===========================================================================
+// Integrators (tile order: thread k handles atom order[k]).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void normal3(uint64_t seed, uint32_t atom, uint64_t step, double xi[3]) {
+    uint32_t r[4];
+    philox4x32_10(atom, (uint32_t)step, (uint32_t)(step >> 32), 0x4d445059u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double two_m32 = 2.3283064365386963e-10;
+    double u0 = ((double)r[0] + 0.5) * two_m32, u1 = ((double)r[1] + 0.5) * two_m32;
+    double u2 = ((double)r[2] + 0.5) * two_m32, u3 = ((double)r[3] + 0.5) * two_m32;
+    double m0 = sqrt(-2.0 * log(u0)), m1 = sqrt(-2.0 * log(u2));
+    double s, cth;
+    sincospi(2.0 * u1, &s, &cth);
+    xi[0] = m0 * cth; xi[1] = m0 * s;
+    sincospi(2.0 * u3, &s, &cth);
+    xi[2] = m1 * cth;
+}
+
+struct StepGeom { double L[3]; float Lf[3], invLf[3]; float skin_half2; };
+
+__device__ __forceinline__ void publish_position(int k, const double x[3], const StepGeom &g, float4 *xs,
+                                                 const float4 *xs_ref, int *flags) {
+    float w[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w[d] = (float)(x[d] - g.L[d] * rint(x[d] / g.L[d]));
+    float4 r = xs_ref[k];
+    float dx = min_image(w[0] - r.x, g.Lf[0], g.invLf[0]);
+    float dy = min_image(w[1] - r.y, g.Lf[1], g.invLf[1]);
+    float dz = min_image(w[2] - r.z, g.Lf[2], g.invLf[2]);
+    if (dist2(dx, dy, dz) > g.skin_half2) flags[1] = 1;
+    xs[k] = make_float4(w[0], w[1], w[2], xs[k].w);
+}
+
+// Verlet.  mode 0: initialise x_prev from (x, v, a) then step; mode 1: step.
+// Reference recurrences (verlet_integrator.py:28-43): x_prev = x - v dt + a dt^2 [quirk; textbook
+// a dt^2/2], x_new = 2 x - x_prev + a dt^2.
+__global__ void k_verlet(int n, int mode, int quirks, double dt, const int *__restrict__ order,
+                         const float *__restrict__ mass, const long long *__restrict__ f_acc,
+                         double *__restrict__ x_cur, double *__restrict__ x_prev, const double *__restrict__ vel,
+                         StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
+                         int *__restrict__ flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a = order[k];
+    double inv_m = 1.0 / (double)mass[a];
+    double xn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double acc = (double)f_acc[3 * (size_t)k + d] * (1.0 / FIX_SCALE) * inv_m;
+        double xc = x_cur[3 * a + d];
+        double xp = mode == 0 ? xc - vel[3 * a + d] * dt + (quirks ? 1.0 : 0.5) * acc * dt * dt : x_prev[3 * a + d];
+        xn[d] = 2.0 * xc - xp + acc * dt * dt;
+        x_prev[3 * a + d] = xc;
+        x_cur[3 * a + d] = xn[d];
+    }
+    publish_position(k, xn, g, xs, xs_ref, flags);
+}
+
+// velocities at the end of VerletIntegrator.integrate (verlet_integrator.py:47-50).
+// quirks: minimg(x_cur - x_prev) / (2 dt) (sic).  textbook: (x_cur - x_prev)/dt + a(x_cur) dt / 2.
+__global__ void k_verlet_velocity(int n, int quirks, double dt, const int *__restrict__ order,
+                                  const float *__restrict__ mass, const long long *__restrict__ f_acc,
+                                  const double *__restrict__ x_cur, const double *__restrict__ x_prev,
+                                  double *__restrict__ vel, StepGeom g) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a = order[k];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double dx = x_cur[3 * a + d] - x_prev[3 * a + d];
+        if (quirks) {
+            dx -= g.L[d] * rint(dx / g.L[d]);
+            vel[3 * a + d] = dx / (2.0 * dt);
+        } else {
+            double acc = (double)f_acc[3 * (size_t)k + d] * (1.0 / FIX_SCALE) / (double)mass[a];
+            vel[3 * a + d] = dx / dt + 0.5 * acc * dt;
+        }
+    }
+}
+
+// G-JF Langevin (Gronbech-Jensen & Farago 2013) with the reference's a, b, sigma
+// (langevin_integrator.py:23-31):
+//   x' = x + b dt v + b dt^2/(2m) f + b dt/(2m) beta',   beta' = sqrt(2 gamma m kT dt) xi
+//   v' = a v + dt/(2m) (a f + f') + b/m beta'
+// Invariant between calls: x_cur = x_n, vel = v_n, f_prev = f(x_n).
+// mode bit 0 (FINISH): f_acc holds f(x_n+1); complete v_n+1 with noise index step-1, set f_prev.
+// mode bit 1 (ADVANCE): move x one step with noise index `step` using the newest force.
+// mode bit 2 (FROM_PREV): the newest force is f_prev (start of a call on a cached state).
+__global__ void k_langevin(int n, int mode, double dt, double ca, double cb, double two_g_kT_dt,
+                           uint64_t seed, uint64_t step, const int *__restrict__ order,
+                           const float *__restrict__ mass, const long long *__restrict__ f_acc,
+                           double *__restrict__ x_cur, double *__restrict__ vel, double *__restrict__ f_prev,
+                           StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
+                           int *__restrict__ flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a = order[k];
+    double m = (double)mass[a], inv_m = 1.0 / m;
+    double bs = sqrt(two_g_kT_dt * m);
+    double f_new[3], v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        f_new[d] = (mode & 4) ? f_prev[3 * a + d] : (double)f_acc[3 * (size_t)k + d] * (1.0 / FIX_SCALE);
+        v[d] = vel[3 * a + d];
+    }
+    if (mode & 1) {
+        double xi[3];
+        normal3(seed, (uint32_t)a, step - 1, xi);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            v[d] = ca * v[d] + 0.5 * dt * inv_m * (ca * f_prev[3 * a + d] + f_new[d]) + cb * inv_m * bs * xi[d];
+            vel[3 * a + d] = v[d];
+        }
+    }
+    if (!(mode & 4)) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f_prev[3 * a + d] = f_new[d];
+    }
+    if (mode & 2) {
+        double xi[3], xn[3];
+        normal3(seed, (uint32_t)a, step, xi);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            xn[d] = x_cur[3 * a + d] + cb * dt * v[d] + 0.5 * cb * dt * dt * inv_m * f_new[d] +
+                    0.5 * cb * dt * inv_m * bs * xi[d];
+            x_cur[3 * a + d] = xn[d];
+        }
+        publish_position(k, xn, g, xs, xs_ref, flags);
+    }
+}
+
+__global__ void k_kinetic(int n, const float *__restrict__ mass, const double *__restrict__ vel,
+                          long long *__restrict__ e_acc) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (a < n) {
+        double vx = vel[3 * a], vy = vel[3 * a + 1], vz = vel[3 * a + 2];
+        e = 0.5 * (double)mass[a] * (vx * vx + vy * vy + vz * vz);
+    }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[MDK_E_KINETIC], to_fix(e));
+}
+
+static StepGeom make_geom(mdk_ctx *c) {
+    StepGeom g;
+    for (int a = 0; a < 3; ++a) { g.L[a] = c->box.Ld[a]; g.Lf[a] = c->box.L[a]; g.invLf[a] = c->box.invL[a]; }
+    g.skin_half2 = 0.25f * c->skin * c->skin;
+    return g;
+}
+
+static int fetch_energies(mdk_ctx *c, unsigned terms) {
+    long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
+    k_kinetic<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->mass.p, c->vel.p, e_acc);
+    ++c->n_launches;
+    long long h[MDK_NUM_ENERGIES];
+    MDK_CUDA(c, cudaMemcpyAsync(h, c->e_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < MDK_NUM_ENERGIES; ++k) c->last_e[k] = (double)h[k] / FIX_SCALE;
+    if (terms & MDK_TERM_PME_RECIP) c->last_e[MDK_E_PME_SELF] = c->e_self_bg;
+    return MDK_OK;
+}
+
+int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks) {
+    if (nsteps <= 0) return MDK_OK;
+    const int n = c->n, T = 256, B = (n + T - 1) / T;
+    StepGeom g = make_geom(c);
+    MDK_CUDA(c, c->x_prev.reserve((size_t)3 * n));
+    for (int s = 0; s < nsteps; ++s) {
+        MDK_TRY(compute_terms(c, terms, false));
+        PhaseTimer pt(c, PH_INTEGRATE);
+        int mode = c->verlet_cached ? 1 : 0;
+        k_verlet<<<B, T, 0, c->stream>>>(n, mode, quirks, dt, c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p,
+                                         c->x_prev.p, c->vel.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
+        ++c->n_launches;
+        c->verlet_cached = true;
+    }
+    if (!quirks) MDK_TRY(compute_terms(c, terms, false));  // a(x_cur) for the velocity
+    k_verlet_velocity<<<B, T, 0, c->stream>>>(n, quirks, dt, c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p,
+                                              c->x_prev.p, c->vel.p, g);
+    ++c->n_launches;
+    MDK_CUDA(c, cudaGetLastError());
+    return fetch_energies(c, terms);
+}
+
+int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms) {
+    if (nsteps <= 0) return MDK_OK;
+    const int n = c->n, T = 256, B = (n + T - 1) / T;
+    StepGeom g = make_geom(c);
+    MDK_CUDA(c, c->f_prev.reserve((size_t)3 * n));
+    const double ca = (1.0 - 0.5 * gamma * dt) / (1.0 + 0.5 * gamma * dt), cb = 1.0 / (1.0 + 0.5 * gamma * dt);
+    const double tg = 2.0 * gamma * kT * dt;
+#define LANGEVIN(mode)                                                                                          \
+    do {                                                                                                        \
+        PhaseTimer pt(c, PH_INTEGRATE);                                                                         \
+        k_langevin<<<B, T, 0, c->stream>>>(n, (mode), dt, ca, cb, tg, seed, c->langevin_step, c->order.p,       \
+                                           c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, \
+                                           c->xs_ref.p, c->flags.p);                                            \
+        ++c->n_launches;                                                                                        \
+    } while (0)
+    if (!c->langevin_cached) {
+        MDK_TRY(compute_terms(c, terms, false));  // f(x_0)
+        LANGEVIN(2);
+        c->langevin_cached = true;
+    } else {
+        MDK_TRY(nlist_refresh_sorted(c));
+        MDK_TRY(nlist_ensure(c));
+        LANGEVIN(2 | 4);
+    }
+    ++c->langevin_step;
+    for (int s = 0; s < nsteps; ++s) {
+        MDK_TRY(compute_terms(c, terms, false));  // f(x_n+1)
+        const bool more = s + 1 < nsteps;
+        LANGEVIN(more ? 3 : 1);
+        if (more) ++c->langevin_step;
+    }
+#undef LANGEVIN
+    MDK_CUDA(c, cudaGetLastError());
+    return fetch_energies(c, terms);
+}
+
+}  // namespace mdk

@@ -1,0 +1,250 @@
+"""oracle/cpu_oracle.py — numpy/ctypes front end of the CPU oracle.
+
+TEST INFRASTRUCTURE ONLY (see oracle/mdpy_oracle.c).  Imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs;
+never by mdpy_b200/.
+
+The host-level logic the reference keeps in Python is restated here in numpy, each
+function citing the reference lines it follows; the per-pair loops live in
+liboracle.so (mdpy_oracle.c).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'liboracle.so')
+_lib = None
+
+CELL_LIST_SKIN = 2.0  # mdpy/core/cell_list.py:17
+NEIGHBOR_TEMPLATE = np.array(  # mdpy/constraint/__init__.py:13-19
+    [[i, j, k] for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)], dtype=np.int32)
+
+
+def build(force=False):
+    """Compile liboracle.so with gcc (oracle/Makefile)."""
+    src = [os.path.join(_HERE, f) for f in ('mdpy_oracle.c', 'mdpy_oracle_impl.h')]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(['make', '-C', _HERE, '-B', 'liboracle.so'],
+                          stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.ora_lj_cell_f32.restype = C.c_longlong
+        _lib.ora_lj_cell_f64.restype = C.c_longlong
+        _lib.ora_pair_set_f32.restype = C.c_longlong
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _real(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return np.float32, '_f32', C.c_float
+    return np.float64, '_f64', C.c_double
+
+
+def _pad_rows(a):
+    """-1-padded int32 [n,w] table with w >= 1 (reference: topology.py:69-79)."""
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    if a.ndim != 2 or a.shape[1] == 0:
+        a = -np.ones((a.shape[0], 1), dtype=np.int32)
+    return a
+
+
+# ----------------------------------------------------------------------------
+# Reference restatement
+# ----------------------------------------------------------------------------
+
+def wrap_positions(positions, pbc, pbc_inv):
+    """mdpy/utils/pbc.py:28-36.  Returns (wrapped, n_lost, first_lost)."""
+    dt, suf, _ = _real(positions.dtype)
+    pos = np.ascontiguousarray(positions, dtype=dt)
+    out = np.empty_like(pos)
+    first = C.c_int(-1)
+    lost = getattr(lib(), 'ora_wrap_positions' + suf)(
+        pos.shape[0], _p(pos), _p(np.ascontiguousarray(pbc, dtype=dt)),
+        _p(np.ascontiguousarray(pbc_inv, dtype=dt)), _p(out), C.byref(first))
+    return out, lost, first.value
+
+
+def cell_attributes(pbc_diag, cutoff_radius, dtype=np.float32):
+    """mdpy/core/cell_list.py:56-81 (set_cutoff_radius + _update_attributes).
+
+    Raises ValueError where the reference raises CellListPoorDefinedError (:58-69).
+    Returns (num_cells_vec int32[3], cell_matrix[3,3], cell_inv[3,3])."""
+    pbc_diag = np.asarray(pbc_diag)
+    if cutoff_radius == 0:
+        raise ValueError('Cutoff radius is poor defined')
+    if (np.floor(pbc_diag / (np.ones(3) * cutoff_radius)) < 2).any():
+        raise ValueError('The cutoff_radius is too large to create cell list')
+    ncell = np.floor((pbc_diag + CELL_LIST_SKIN) / (np.ones(3) * cutoff_radius)).astype(np.int32)
+    ncell[ncell < 3] = 3
+    cell_matrix = np.diag((pbc_diag + CELL_LIST_SKIN) / ncell).astype(dtype)
+    cell_inv = np.linalg.inv(cell_matrix)
+    return ncell, cell_matrix, cell_inv
+
+
+def cell_list_update(positions, cell_inv, ncell):
+    """mdpy/core/cell_list.py:83-116.  Returns (particle_cell_index [n,3], cell_list [nx,ny,nz,P])."""
+    dt, suf, _ = _real(positions.dtype)
+    pos = np.ascontiguousarray(positions, dtype=dt)
+    ncell = np.ascontiguousarray(ncell, dtype=np.int32)
+    pci = np.empty((pos.shape[0], 3), dtype=np.int32)
+    P = getattr(lib(), 'ora_cell_index' + suf)(
+        pos.shape[0], _p(pos), _p(np.ascontiguousarray(cell_inv, dtype=dt)), _p(ncell), _p(pci))
+    cl = np.empty((ncell[0], ncell[1], ncell[2], P), dtype=np.int32)
+    lib().ora_cell_fill(pos.shape[0], _p(pci), _p(ncell), P, _p(cl))
+    return pci, cl
+
+
+def lj_cell(positions, params, pbc, rc, bonded, scaling, cell_cutoff=None):
+    """CharmmNonbondedConstraint.update() on the CPU platform
+    (charmm_nonbonded_constraint.py:183-195 -> cpu_kernel :64-108) including the cell
+    list it reads from State (state.py:56-61; the list's cutoff is the largest constraint
+    cutoff, ensemble.py:49-50, passed here as cell_cutoff, default rc... the reference's
+    CellList default is 12, cell_list.py:20).  Returns (forces, energy, ordered_visits)."""
+    dt, suf, creal = _real(positions.dtype)
+    pos = np.ascontiguousarray(positions, dtype=dt)
+    pbc = np.ascontiguousarray(pbc, dtype=dt)
+    pbc_inv = np.ascontiguousarray(np.linalg.inv(pbc), dtype=dt)
+    ncell, _, cell_inv = cell_attributes(pbc.diagonal(), rc if cell_cutoff is None else cell_cutoff, dt)
+    pci, cl = cell_list_update(pos, cell_inv, ncell)
+    bonded, scaling = _pad_rows(bonded), _pad_rows(scaling)
+    forces = np.empty_like(pos)
+    e = C.c_double(0)
+    visits = getattr(lib(), 'ora_lj_cell' + suf)(
+        pos.shape[0], _p(pos), _p(np.ascontiguousarray(params, dtype=dt)), _p(pbc), _p(pbc_inv),
+        creal(rc), _p(bonded), bonded.shape[1], _p(scaling), scaling.shape[1], _p(pci), _p(cl),
+        _p(ncell), cl.shape[3], _p(forces), C.byref(e))
+    return forces, e.value, visits
+
+
+def coulomb_allpairs(positions, charges, pbc, bonded, k):
+    """ElectrostaticConstraint.update() on the CPU platform
+    (electrostatic_constraint.py:137-145 -> cpu_kernel :52-79); k = 4 pi eps0."""
+    dt, suf, _ = _real(positions.dtype)
+    pos = np.ascontiguousarray(positions, dtype=dt)
+    pbc = np.ascontiguousarray(pbc, dtype=dt)
+    pbc_inv = np.ascontiguousarray(np.linalg.inv(pbc), dtype=dt)
+    bonded = _pad_rows(bonded)
+    forces = np.empty_like(pos)
+    e = C.c_double(0)
+    getattr(lib(), 'ora_coulomb_allpairs' + suf)(
+        pos.shape[0], _p(pos), _p(np.ascontiguousarray(charges, dtype=dt).reshape(-1)), _p(bonded),
+        bonded.shape[1], _p(pbc), _p(pbc_inv), C.c_double(k), _p(forces), C.byref(e))
+    return forces, e.value
+
+
+def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn):
+    """VerletIntegrator.integrate (verlet_integrator.py:20-50) for a fresh integrator:
+    x_prev = x - v dt + a dt^2 (:31-34, sic), x_new = 2x - x_prev + a dt^2 (:40-43), positions
+    wrapped into State every step (:44 -> state.py:56-61), reported velocity
+    minimg(x_cur - x_prev)/(2 dt) (:47-50, sic — half the true value).
+    force_fn(wrapped_positions) -> forces [n,3].  float64 host arithmetic like the reference.
+    Returns (state_positions, state_velocities, cur_positions_unwrapped, pre_positions)."""
+    pbc = np.asarray(pbc, dtype=np.float64)
+    pbc_inv = np.linalg.inv(pbc)
+    masses = np.asarray(masses, dtype=np.float64).reshape(-1, 1)
+    state_pos, _, _ = wrap_positions(np.asarray(positions, dtype=np.float64), pbc, pbc_inv)
+    acc = force_fn(state_pos) / masses
+    cur = state_pos.copy()
+    pre = cur - np.asarray(velocities, dtype=np.float64) * dt_fs + acc * dt_fs ** 2
+    for step in range(num_steps):
+        if step != 0:
+            acc = force_fn(state_pos) / masses
+        cur, pre = 2 * cur - pre + acc * dt_fs ** 2, cur
+        state_pos, lost, _ = wrap_positions(cur, pbc, pbc_inv)
+        if lost:
+            raise RuntimeError('ParticleLossError')
+    d = cur - pre
+    s = d @ pbc_inv
+    s -= np.round(s)
+    vel = (s @ pbc) / 2 / dt_fs
+    return state_pos, vel, cur, pre
+
+
+# ----------------------------------------------------------------------------
+# Float64 truth
+# ----------------------------------------------------------------------------
+
+def nonbonded_bruteforce(positions, box, params, charges, bonded, scaling, rc_lj=12.0, r_on=None,
+                         coul_mode=0, k_e=0.0, alpha=0.0, rc_coul=None, i_range=None):
+    """All-pairs float64 LJ (+switch) and Coulomb (mode 1: erfc + excluded-pair erf
+    correction; mode 2: the reference's bare minimum-image sum).  See mdpy_oracle.c.
+    Returns dict(f_lj, f_coul, e_lj, e_coul, e_excl, n_lj, n_coul); forces are only
+    filled for atoms in i_range (default all)."""
+    pos = np.ascontiguousarray(positions, dtype=np.float64)
+    n = pos.shape[0]
+    box = np.ascontiguousarray(box, dtype=np.float64).reshape(3)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    q = np.ascontiguousarray(charges, dtype=np.float64).reshape(-1)
+    bonded, scaling = _pad_rows(bonded), _pad_rows(scaling)
+    i0, i1 = (0, n) if i_range is None else i_range
+    f_lj = np.zeros((n, 3)); f_c = np.zeros((n, 3))
+    en = np.zeros(3); cnt = np.zeros(2, dtype=np.int64)
+    lib().ora_nonbonded_bruteforce(
+        n, _p(pos), _p(box), _p(params), _p(q), _p(bonded), bonded.shape[1], _p(scaling),
+        scaling.shape[1], C.c_double(rc_lj), C.c_double(rc_lj if r_on is None else r_on),
+        int(coul_mode), C.c_double(k_e), C.c_double(alpha),
+        C.c_double(rc_lj if rc_coul is None else rc_coul), int(i0), int(i1), _p(f_lj), _p(f_c),
+        _p(en), _p(cnt))
+    return dict(f_lj=f_lj, f_coul=f_c, e_lj=en[0], e_coul=en[1], e_excl=en[2],
+                n_lj=int(cnt[0]), n_coul=int(cnt[1]))
+
+
+def pair_set_f32(positions, box, rc, bonded):
+    """The canonical fp32 in-cutoff pair set, i<j, lexicographic (mdpy_oracle.c:ora_pair_set_f32)."""
+    pos = np.ascontiguousarray(positions, dtype=np.float32)
+    n = pos.shape[0]
+    box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
+    bonded = _pad_rows(bonded)
+    cap = max(1024, int(n * 700))
+    while True:
+        oi = np.empty(cap, dtype=np.int32); oj = np.empty(cap, dtype=np.int32)
+        cnt = lib().ora_pair_set_f32(n, _p(pos), _p(box), C.c_float(rc), _p(bonded),
+                                     bonded.shape[1], _p(oi), _p(oj), C.c_longlong(cap))
+        if cnt <= cap:
+            return np.stack([oi[:cnt], oj[:cnt]], axis=1)
+        cap = int(cnt)
+
+
+def ewald_recip(positions, charges, box, alpha, kmax, k_e):
+    """Explicit k-space Ewald sum.  Returns (forces, e_rec, e_self, e_background)."""
+    pos = np.ascontiguousarray(positions, dtype=np.float64)
+    q = np.ascontiguousarray(charges, dtype=np.float64).reshape(-1)
+    box = np.ascontiguousarray(box, dtype=np.float64).reshape(3)
+    kmax = np.ascontiguousarray(np.broadcast_to(kmax, 3), dtype=np.int32)
+    f = np.zeros_like(pos); en = np.zeros(3)
+    lib().ora_ewald_recip(pos.shape[0], _p(pos), _p(q), _p(box), C.c_double(alpha), _p(kmax),
+                          C.c_double(k_e), _p(f), _p(en))
+    return f, en[0], en[1], en[2]
+
+
+def ewald_exact(positions, charges, box, bonded, k_e, tol_exp=36.0):
+    """Converged Ewald energy/forces (the PME truth; parity otherwise unpinned):
+    alpha chosen so the real-space sum converges inside the minimum image
+    (erfc(alpha L/2) ~ e^-tol_exp), k-space summed until exp(-pi^2 m^2/alpha^2) < e^-tol_exp.
+    Excluded (bonded) pairs are removed exactly.  Returns (forces, energy)."""
+    box = np.asarray(box, dtype=np.float64).reshape(3)
+    n = positions.shape[0]
+    alpha = 2.0 * np.sqrt(tol_exp) / box.min()
+    kmax = np.ceil(np.sqrt(tol_exp) * alpha * box / np.pi).astype(np.int32)
+    zero_params = np.zeros((n, 4))
+    d = nonbonded_bruteforce(positions, box, zero_params, charges, bonded,
+                             -np.ones((n, 1), dtype=np.int32), rc_lj=0.0, coul_mode=1, k_e=k_e,
+                             alpha=alpha, rc_coul=0.5 * box.min())
+    f_rec, e_rec, e_self, e_bg = ewald_recip(positions, charges, box, alpha, kmax, k_e)
+    return d['f_coul'] + f_rec, d['e_coul'] + d['e_excl'] + e_rec + e_self + e_bg

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the mdpy nonbonded hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME]
+
+A "step" is one MD step of the hot path on one synthetic box: neighbour-list upkeep, CHARMM LJ +
+erfc direct space over the tile list, PME reciprocal (spread, cuFFT, influence function, gather),
+bonded terms and the Langevin position/velocity update.  Default workload = BASELINE.json configs[1]:
+23 556-atom TIP3P box, 9 A cutoff, PME 64^3 order 4, Langevin 300 K, 2 fs.
+
+Prints ONE JSON line (rank 0).  value = ns/day with the state resident on the device (CUDA events
+around K steps); e2e = the same metric through the drop-in Constraint API with host buffers
+(positions H2D and forces D2H every step, numpy integrator on the host — the way the reference's
+own integrators drive Constraint.update).  roofline = the pair kernel against the FP32 CUDA-core
+peak (70 flop per in-cutoff pair), roofline_pme = spread/FFT/gather against measured
+HBM bandwidth.  cpu_baseline / --impl reference = the reference's per-step work (27-cell-list LJ +
+all-pairs Coulomb, no PME) restated in C (oracle/), on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (generator key, cutoff, switch, pme grid, dt fs)
+    'water_23k': dict(gen='water_23k', cutoff=9.0, switch=None, grid=(64, 64, 64), dt=2.0),
+    'protein_92k': dict(gen='protein_92k', cutoff=12.0, switch=10.0, grid=(108, 108, 80), dt=2.0),
+    'protein_1m': dict(gen='protein_1m', cutoff=12.0, switch=10.0, grid=(216, 216, 216), dt=2.0),
+}
+FLOP_PER_PAIR = 70.0
+TEMPERATURE, GAMMA = 300.0, 1e-3   # K, 1/fs (= 1/ps)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d['hbm_gbs']), sm_max_mhz=float(d.get('sm_max_mhz', 1965.0)), source='measured')
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device=0):
+        self.device, self.proc, self.lines = device, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(',')]
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(p) > 5 + k and p[5 + k].lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def ns_per_day(steps, seconds, dt_fs):
+    return steps / seconds * dt_fs * 86400.0 * 1e-6
+
+
+def build_system(cfg):
+    from mdpy_b200 import synthetic
+    return synthetic.CONFIGS[cfg['gen']]()
+
+
+# ---------------------------------------------------------------------------------------------
+def reference_step_seconds(system, cfg, threads, budget_s=12.0):
+    """One step of the reference's CPU path (LJ over its 27-cell list + all-pairs Coulomb, both
+    restated in C in oracle/), timed on a bounded slice of the outer atom loop and scaled to all N
+    atoms.  Returns (seconds per full step, sample description)."""
+    from oracle import cpu_oracle as ora
+    n = system.num_particles
+    topo = system.topology()
+    pos = system.positions.astype(np.float32)
+    pbc = np.diag(system.box).astype(np.float32)
+    table = system.lj_table()
+    k = 4 * np.pi * float(np.float32(0.5727653))
+    # calibrate on a small slice, then size the sample to the budget
+    probe = max(threads * 8, min(n, 256))
+    t0 = time.perf_counter()
+    ora.lj_cell(pos, table, pbc, cfg['cutoff'], topo.bonded_particles, topo.scaling_particles, cell_cutoff=12.0,
+                i_range=(0, probe), threads=threads)
+    ora.coulomb_allpairs(pos, topo.charges, pbc, topo.bonded_particles, k, i_range=(0, probe), threads=threads)
+    per_atom = (time.perf_counter() - t0) / probe
+    m = int(min(n, max(probe, budget_s / max(per_atom, 1e-9))))
+    t0 = time.perf_counter()
+    ora.lj_cell(pos, table, pbc, cfg['cutoff'], topo.bonded_particles, topo.scaling_particles, cell_cutoff=12.0,
+                i_range=(0, m), threads=threads)
+    t_lj = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ora.coulomb_allpairs(pos, topo.charges, pbc, topo.bonded_particles, k, i_range=(0, m), threads=threads)
+    t_c = time.perf_counter() - t0
+    # LJ is linear in the slice; the all-pairs loop is triangular: slice [0, m) covers
+    # m n - m(m+1)/2 of the n(n-1)/2 pairs
+    frac_c = (m * n - m * (m + 1) / 2.0) / (n * (n - 1) / 2.0)
+    full = t_lj * n / m + t_c / frac_c
+    sample = ('atoms [0,%d) of %d of the outer loops of LJ (27-cell list, rc %.0f A) and all-pairs Coulomb, fp32, '
+              'scaled to N (LJ linear, Coulomb by pair count); reference semantics: no PME' % (m, n, cfg['cutoff']))
+    return full, sample
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's own CPU algorithm for the path on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    system = build_system(cfg)
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    times = []
+    sample = ''
+    for it in range(args.warmup + args.steps):
+        t, sample = reference_step_seconds(system, cfg, threads, budget_s=per_step)
+        if it >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    value = ns_per_day(1, sec, cfg['dt'])
+    line = dict(metric='ns_per_day', value=value, unit='ns/day', impl='reference', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='strong', vs_baseline=None,
+                dtype='f32', data='synthetic', atom_steps_per_s=system.num_particles / sec,
+                config=dict(workload=args.config, atoms=system.num_particles, cutoff_A=cfg['cutoff'], dt_fs=cfg['dt'],
+                            note='reference path = plain-cutoff LJ + bare all-pairs Coulomb (no PME in the reference tree)'),
+                cpu_baseline=dict(value=value, unit='ns/day', cores=threads, kind='port', sample=sample),
+                e2e=dict(value=value, unit='ns/day', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args, cfg):
+    import mdpy_b200 as md
+    from mdpy_b200 import _native
+    from mdpy_b200.integrator import LangevinIntegrator
+    from mdpy_b200.unit import KB, Quantity, default_energy_unit, kelvin
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    os.environ['MDPY_B200_DEVICE'] = str(local)
+
+    system = build_system(cfg)
+    n = system.num_particles
+    ens = system.ensemble(cutoff=cfg['cutoff'], switch=cfg['switch'], pme=True, ewald_error=1e-6, grid=cfg['grid'],
+                          order=4, bonded=True)
+    ctx = _native.context_of(ens)
+    dev = ctx.dev
+    if world > 1:
+        from mdpy_b200 import multigpu
+        multigpu.attach(ctx, dist, rank, world)
+    kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
+
+    # relax the lattice start (untimed): short, strongly damped steps, then the production step
+    for dt, gamma, steps in ((0.1, 0.2, 200), (0.5, 0.05, 200), (1.0, 0.01, 300)):
+        LangevinIntegrator(dt, TEMPERATURE, gamma, seed=1).integrate(ens, steps)
+    integ = LangevinIntegrator(cfg['dt'], TEMPERATURE, GAMMA, seed=1)
+    integ.integrate(ens, max(args.warmup, 3))
+    terms = 0
+    for c in ens.constraints:
+        terms |= c.terms
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- timed region: K steps, state resident on the device, CUDA events on the ctx stream ----
+    dev.set_profiling(1)
+    t_before = dev.timing()
+    barrier()
+    with ClockSampler(local) as clocks:
+        w0 = time.perf_counter()
+        dev.step_langevin(cfg['dt'], kT, GAMMA, 1, args.steps, terms)
+        wall = time.perf_counter() - w0
+    barrier()
+    t_after = dev.timing()
+    dev_ms = t_after['total_ms']
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms = float(tt.item())
+    launches = int(t_after['launches'] - t_before['launches'])
+    rebuilds = int(t_after['rebuilds'] - t_before['rebuilds'])
+    value = ns_per_day(args.steps, dev_ms * 1e-3, cfg['dt'])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-phase profile (separate pass, per-phase events add syncs: not part of `value`) ----
+    prof_steps = min(200, max(20, args.steps))
+    dev.set_profiling(2)
+    dev.step_langevin(cfg['dt'], kT, GAMMA, 1, prof_steps, terms)
+    ph = dev.timing()
+    dev.set_profiling(0)
+    pair_ms = ph['pair_ms'] / prof_steps
+    pme_ms = (ph['spread_ms'] + ph['fft_ms'] + ph['gather_ms']) / prof_steps
+    # L2-flushed variant: one step at a time with a 256 MB memset in between (outside the events)
+    dev.set_profiling(1)
+    fl = []
+    for _ in range(min(50, args.steps)):
+        dev.flush_l2()
+        dev.step_langevin(cfg['dt'], kT, GAMMA, 1, 1, terms)
+        fl.append(dev.timing()['total_ms'])
+    dev.set_profiling(0)
+
+    # in-cutoff pair count of the current configuration (for the flop model)
+    lj = ens.constraints[0]
+    ctx._pos_rev = None
+    ens.state._positions = dev.download_positions()
+    n_pairs = len(lj.neighbor_pairs())
+
+    peaks = measured_peaks()
+    fp32_peak = 148 * 128 * 2 * peaks['sm_max_mhz'] * 1e6 / 1e12
+    achieved = FLOP_PER_PAIR * n_pairs / (pair_ms * 1e-3) / 1e12
+    K = int(np.prod(cfg['grid']))
+    pme_bytes = 44.0 * n + 34.0 * K
+    pme_gbs = pme_bytes / (pme_ms * 1e-3) / 1e9
+
+    # ---- e2e: the drop-in per-step path with host buffers ----
+    e2e_steps = min(args.steps, 300)
+    x = ens.state.positions.astype(np.float64)
+    v = ens.state.velocities.astype(np.float64)
+    m = np.asarray(ens.topology.masses, dtype=np.float64).reshape(-1, 1)
+    rng = np.random.default_rng(0)
+    dt = cfg['dt']
+    ca = (1 - GAMMA * dt / 2) / (1 + GAMMA * dt / 2); cb = 1 / (1 + GAMMA * dt / 2)
+    ens.state.set_positions(x.astype(np.float32)); ens.update()
+    f = ens.forces.copy()
+    for _ in range(3):   # warm-up of the host path
+        ens.state.set_positions(x.astype(np.float32)); ens.update()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        beta = np.sqrt(2 * GAMMA * kT * dt * m) * rng.standard_normal(x.shape)
+        x = x + cb * dt * v + cb * dt * dt / (2 * m) * f + cb * dt / (2 * m) * beta
+        xw = (x - system.box * np.round(x / system.box)).astype(np.float32)
+        ens.state.set_positions(xw)            # host -> State (wrap), H2D inside update()
+        ens.update()                           # one fused device evaluation, forces D2H
+        f_new = ens.forces
+        v = ca * v + dt / (2 * m) * (ca * f + f_new) + cb / m * beta
+        f = f_new.copy()
+    e2e_sec = time.perf_counter() - t0
+    e2e_value = ns_per_day(e2e_steps, e2e_sec, dt)
+
+    # ---- CPU baseline (bounded sample) ----
+    threads = os.cpu_count() or 1
+    cpu_sec, sample = reference_step_seconds(system, cfg, 1, budget_s=10.0)
+
+    stats = dev.timing()
+    line = dict(
+        metric='ns_per_day', value=value, unit='ns/day', n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
+        data='synthetic', atom_steps_per_s=n * args.steps / (dev_ms * 1e-3), wall_ms_per_step=wall * 1e3 / args.steps,
+        config=dict(workload=args.config, atoms=n, cutoff_A=cfg['cutoff'], switch_A=cfg['switch'], pme_grid=list(cfg['grid']),
+                    pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=2.0,
+                    terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_in_timed=rebuilds,
+                    l2='steady-state MD trajectory: every step consumes the previous step\'s output, nothing is re-timed '
+                       'on a repeated input; working set %.1f MB; l2_flushed_ms_per_step gives the same step with a '
+                       '256 MB L2 flush before it' % ((32.0 * n + 12.0 * K) / 1e6)),
+        l2_flushed_ms_per_step=float(np.median(fl)),
+        clocks=clocks.summary(), gpu_launches=launches,
+        e2e=dict(value=e2e_value, unit='ns/day', h2d_bytes_per_step=12 * n, d2h_bytes_per_step=24 * n,
+                 steps=e2e_steps, ms_per_step=e2e_sec * 1e3 / e2e_steps,
+                 path='State.set_positions + Ensemble.update (fused mdk_compute) per step, numpy G-JF update on the host'),
+        roofline=dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak, traffic=None,
+                      kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=pair_ms,
+                      peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source']),
+        roofline_pme=dict(bound='hbm', achieved=pme_gbs, peak=peaks['hbm_gbs'], unit='GB/s', frac=pme_gbs / peaks['hbm_gbs'],
+                          bytes_per_step=pme_bytes, kernels_ms=pme_ms, peak_source=peaks['source'],
+                          note='spread + convert + cuFFT R2C/C2R + convolve + gather; mesh is L2 resident'),
+        phases_ms_per_step={k: ph[k] / prof_steps for k in ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms',
+                                                            'bonded_ms', 'integrate_ms')},
+        nlist=dict(work_units=int(stats['work_units']), j_chunks=int(stats['j_chunks']), masked_chunks=int(stats['masked_chunks']),
+                   seg_chunks=int(stats['seg_chunks']), pair_slots=int(stats['j_chunks']) * 1024,
+                   slot_efficiency=n_pairs / max(1.0, stats['j_chunks'] * 1024.0)),
+        cpu_baseline=dict(value=ns_per_day(1, cpu_sec, dt), unit='ns/day', cores=1, kind='port', sample=sample,
+                          host_cores=threads, seconds_per_step=cpu_sec),
+    )
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='water_23k', choices=sorted(CONFIGS))
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == 'reference':
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == '__main__':
+    main()

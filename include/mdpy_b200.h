@@ -160,11 +160,13 @@ MDK_API int mdk_get_pairs(mdk_ctx *ctx, int32_t *out_i, int32_t *out_j, int64_t 
  * [4]=pme gather [5]=bonded+special pairs [6]=integrate [7]=bare coulomb
  * [8]=total; plus counters [9]=kernel launches [10]=nlist rebuilds [11]=pair-kernel launches. */
 MDK_API int mdk_get_timing(mdk_ctx *ctx, double *out16);
-/* Enable (1) / disable (0) per-phase event timing (adds stream syncs; off by default). */
-MDK_API int mdk_set_profiling(mdk_ctx *ctx, int on);
+/* Event timing level: 0 off (default), 1 whole-call CUDA events only, 2 per-phase events (adds stream syncs). */
+MDK_API int mdk_set_profiling(mdk_ctx *ctx, int level);
 /* Raw device pointer + element count of the int64 fixed-point force accumulator in
  * tile order (multi-GPU reduction by the host layer; scale = 2^40). */
 MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64);
+/* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
+MDK_API int mdk_flush_l2(mdk_ctx *ctx);
 /* Restrict the pair-kernel work units this ctx evaluates to those with
  * (unit_index % nranks) == rank (replicated-data force decomposition). */
 MDK_API int mdk_set_shard(mdk_ctx *ctx, int rank, int nranks);

@@ -460,13 +460,22 @@ int mdk_get_timing(mdk_ctx *c, double *out16) {
     return MDK_OK;
 }
 
-int mdk_set_profiling(mdk_ctx *c, int on) { NEED_CTX(c); c->profiling = on != 0; return MDK_OK; }
+int mdk_set_profiling(mdk_ctx *c, int level) { NEED_CTX(c); c->profiling = level < 0 ? 0 : level; return MDK_OK; }
 
 int mdk_force_accumulator(mdk_ctx *c, void **dev_ptr, int64_t *n_int64) {
     NEED_CTX(c);
     if (!dev_ptr || !n_int64) return fail(c, MDK_ERR_BAD_ARG, "NULL output");
     *dev_ptr = c->f_acc.p;
     *n_int64 = (int64_t)c->n_pad * 3;
+    return MDK_OK;
+}
+
+int mdk_flush_l2(mdk_ctx *c) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    const size_t bytes = (size_t)256 << 20;  // > 126 MB of L2
+    MDK_CUDA(c, c->sort_tmp.reserve(bytes));
+    MDK_CUDA(c, cudaMemsetAsync(c->sort_tmp.p, 0xA5, bytes, c->stream));
     return MDK_OK;
 }
 

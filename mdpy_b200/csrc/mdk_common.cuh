@@ -138,7 +138,7 @@ struct mdk_ctx {
 
     // ---- bookkeeping ----
     double last_e[MDK_NUM_ENERGIES] = {0};
-    bool profiling = false;
+    int profiling = 0;                        // 0 off, 1 whole-call events only, 2 per-phase events (adds syncs)
     cudaEvent_t ev[2 * mdk::PH_COUNT] = {nullptr};
     double phase_ms[mdk::PH_COUNT] = {0};
     int64_t n_launches = 0, n_rebuilds = 0, n_pair_launches = 0;
@@ -164,10 +164,10 @@ int fail(mdk_ctx *c, int code, const char *fmt, ...);
 struct PhaseTimer {
     mdk_ctx *c; int ph;
     PhaseTimer(mdk_ctx *c_, int ph_) : c(c_), ph(ph_) {
-        if (c->profiling) cudaEventRecord(c->ev[2 * ph], c->stream);
+        if (c->profiling >= 2) cudaEventRecord(c->ev[2 * ph], c->stream);
     }
     ~PhaseTimer() {
-        if (c->profiling) {
+        if (c->profiling >= 2) {
             cudaEventRecord(c->ev[2 * ph + 1], c->stream);
             cudaEventSynchronize(c->ev[2 * ph + 1]);
             float ms = 0;

@@ -1,0 +1,30 @@
+"""Langevin dynamics — same constructor and coefficients as
+mdpy/integrator/langevin_integrator.py:18-35 (a = (1 - g dt/2)/(1 + g dt/2), b = 1/(1 + g dt/2),
+sigma = sqrt(2 kT g)), textbook G-JF update with one force evaluation per step.  The reference's own
+update has the force sign and state carry-over wrong and draws numpy noise, so there is
+no trajectory parity to keep; this integrator is validated by equipartition instead.
+Noise: Philox4x32-10 keyed by `seed`, counter = (atom, step) — reproducible and order independent.
+"""
+import numpy as np
+
+from ..unit import KB, Quantity, check_quantity_value, default_energy_unit, default_temperature_unit, default_time_unit
+from .integrator import Integrator
+
+
+class LangevinIntegrator(Integrator):
+    def __init__(self, time_step, temperature, friction_rate, seed=0):
+        super().__init__(time_step)
+        self._temperature = check_quantity_value(temperature, default_temperature_unit)
+        self._gamma = check_quantity_value(friction_rate, 1 / default_time_unit)
+        self._kbt = (Quantity(self._temperature, default_temperature_unit) * KB).convert_to(default_energy_unit).value
+        self._sigma = np.sqrt(2 * self._kbt * self._gamma)
+        half = self._gamma * self._time_step / 2
+        self._a = (1 - half) / (1 + half)
+        self._b = 1 / (1 + half)
+        self._seed = int(seed)
+
+    def integrate(self, ensemble, num_steps: int = 1):
+        ctx, terms = self._prepare(ensemble)
+        ctx.dev.step_langevin(float(self._time_step), float(self._kbt), float(self._gamma), self._seed,
+                              int(num_steps), terms)
+        self._publish(ensemble, ctx, terms)

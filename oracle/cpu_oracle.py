@@ -64,6 +64,22 @@ def _pad_rows(a):
     return a
 
 
+def _run_slices(piece, i_range, threads):
+    """Evaluate piece((i0, i1)) over `threads` interleaved-size slices of i_range on host threads
+    (ctypes releases the GIL); the caller adds the partial results."""
+    i0, i1 = int(i_range[0]), int(i_range[1])
+    threads = max(1, min(int(threads), i1 - i0)) if i1 > i0 else 1
+    if threads == 1:
+        return [piece((i0, i1))]
+    # the all-pairs loop is triangular: equalise work with sqrt-spaced cut points
+    frac = 1.0 - np.sqrt(1.0 - np.arange(threads + 1) / threads)
+    cuts = np.unique(np.round(i0 + frac * (i1 - i0)).astype(int))
+    cuts[0], cuts[-1] = i0, i1
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(piece, list(zip(cuts[:-1], cuts[1:]))))
+
+
 # ----------------------------------------------------------------------------
 # Reference restatement
 # ----------------------------------------------------------------------------
@@ -110,7 +126,7 @@ def cell_list_update(positions, cell_inv, ncell):
     return pci, cl
 
 
-def lj_cell(positions, params, pbc, rc, bonded, scaling, cell_cutoff=None):
+def lj_cell(positions, params, pbc, rc, bonded, scaling, cell_cutoff=None, i_range=None, threads=1):
     """CharmmNonbondedConstraint.update() on the CPU platform
     (charmm_nonbonded_constraint.py:183-195 -> cpu_kernel :64-108) including the cell
     list it reads from State (state.py:56-61; the list's cutoff is the largest constraint
@@ -123,16 +139,21 @@ def lj_cell(positions, params, pbc, rc, bonded, scaling, cell_cutoff=None):
     ncell, _, cell_inv = cell_attributes(pbc.diagonal(), rc if cell_cutoff is None else cell_cutoff, dt)
     pci, cl = cell_list_update(pos, cell_inv, ncell)
     bonded, scaling = _pad_rows(bonded), _pad_rows(scaling)
-    forces = np.empty_like(pos)
-    e = C.c_double(0)
-    visits = getattr(lib(), 'ora_lj_cell' + suf)(
-        pos.shape[0], _p(pos), _p(np.ascontiguousarray(params, dtype=dt)), _p(pbc), _p(pbc_inv),
-        creal(rc), _p(bonded), bonded.shape[1], _p(scaling), scaling.shape[1], _p(pci), _p(cl),
-        _p(ncell), cl.shape[3], _p(forces), C.byref(e))
-    return forces, e.value, visits
+    params = np.ascontiguousarray(params, dtype=dt)
+    fn = getattr(lib(), 'ora_lj_cell' + suf)
+
+    def piece(rng):
+        forces = np.empty_like(pos)
+        e = C.c_double(0)
+        visits = fn(pos.shape[0], _p(pos), _p(params), _p(pbc), _p(pbc_inv), creal(rc), _p(bonded), bonded.shape[1],
+                    _p(scaling), scaling.shape[1], _p(pci), _p(cl), _p(ncell), cl.shape[3], int(rng[0]), int(rng[1]),
+                    _p(forces), C.byref(e))
+        return forces, e.value, visits
+    parts = _run_slices(piece, (0, pos.shape[0]) if i_range is None else i_range, threads)
+    return sum(p[0] for p in parts), sum(p[1] for p in parts), sum(p[2] for p in parts)
 
 
-def coulomb_allpairs(positions, charges, pbc, bonded, k):
+def coulomb_allpairs(positions, charges, pbc, bonded, k, i_range=None, threads=1):
     """ElectrostaticConstraint.update() on the CPU platform
     (electrostatic_constraint.py:137-145 -> cpu_kernel :52-79); k = 4 pi eps0."""
     dt, suf, _ = _real(positions.dtype)
@@ -140,12 +161,17 @@ def coulomb_allpairs(positions, charges, pbc, bonded, k):
     pbc = np.ascontiguousarray(pbc, dtype=dt)
     pbc_inv = np.ascontiguousarray(np.linalg.inv(pbc), dtype=dt)
     bonded = _pad_rows(bonded)
-    forces = np.empty_like(pos)
-    e = C.c_double(0)
-    getattr(lib(), 'ora_coulomb_allpairs' + suf)(
-        pos.shape[0], _p(pos), _p(np.ascontiguousarray(charges, dtype=dt).reshape(-1)), _p(bonded),
-        bonded.shape[1], _p(pbc), _p(pbc_inv), C.c_double(k), _p(forces), C.byref(e))
-    return forces, e.value
+    q = np.ascontiguousarray(charges, dtype=dt).reshape(-1)
+    fn = getattr(lib(), 'ora_coulomb_allpairs' + suf)
+
+    def piece(rng):
+        forces = np.empty_like(pos)
+        e = C.c_double(0)
+        fn(pos.shape[0], _p(pos), _p(q), _p(bonded), bonded.shape[1], _p(pbc), _p(pbc_inv), C.c_double(k),
+           int(rng[0]), int(rng[1]), _p(forces), C.byref(e))
+        return forces, e.value
+    parts = _run_slices(piece, (0, pos.shape[0]) if i_range is None else i_range, threads)
+    return sum(p[0] for p in parts), sum(p[1] for p in parts)
 
 
 def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn):

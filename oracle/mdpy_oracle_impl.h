@@ -93,11 +93,13 @@ static inline int FN(in_list)(const int *row, int width, int id) {
 long long FN(ora_lj_cell)(int n, const REAL *pos, const REAL *params /* [n,4] */, const REAL *pbc,
                           const REAL *pbc_inv, REAL rc, const int *bonded, int wb,
                           const int *scaling, int ws, const int *pci, const int *cell_list,
-                          const int *ncell, int P, REAL *forces, double *energy) {
+                          const int *ncell, int P, int i0, int i1, REAL *forces, double *energy) {
+    /* [i0, i1): the outer-loop slice this call evaluates (the reference runs [0, n) on one
+     * thread; bench.py's reference arm runs disjoint slices on the host threads and adds up) */
     memset(forces, 0, sizeof(REAL) * 3 * (size_t)n);
     double e_acc = 0.0;
     long long visits = 0;
-    for (int id1 = 0; id1 < n; ++id1) {
+    for (int id1 = i0; id1 < i1; ++id1) {
         const int *b1 = bonded + (size_t)id1 * wb;
         const int *s1 = scaling + (size_t)id1 * ws;
         for (int ti = -1; ti <= 1; ++ti)
@@ -151,11 +153,11 @@ long long FN(ora_lj_cell)(int n, const REAL *pos, const REAL *params /* [n,4] */
  * bonded[id1] (:63-64), minimum image (:67-70), f = -q1 q2 / k / r^2 on id1 (:73-75),
  * E += q1 q2 / k / r (:78), k = 4 pi eps0 (:60).  No cutoff, no 1-4 scaling. */
 void FN(ora_coulomb_allpairs)(int n, const REAL *pos, const REAL *charges, const int *bonded,
-                              int wb, const REAL *pbc, const REAL *pbc_inv, double k,
+                              int wb, const REAL *pbc, const REAL *pbc_inv, double k, int i0, int i1,
                               REAL *forces, double *energy) {
     memset(forces, 0, sizeof(REAL) * 3 * (size_t)n);
     double e_acc = 0.0;
-    for (int id1 = 0; id1 < n; ++id1) {
+    for (int id1 = i0; id1 < i1; ++id1) {
         const int *b1 = bonded + (size_t)id1 * wb;
         for (int id2 = id1 + 1; id2 < n; ++id2) {
             if (FN(in_list)(b1, wb, id2)) continue;

@@ -328,6 +328,7 @@ class EnsembleContext:
     def compute_fused(self, constraints):
         terms = 0
         for c in constraints:
+            c._configure()
             terms |= c.terms
         e = self.compute(terms)
         forces = self.dev.forces(np.float64)

@@ -30,7 +30,7 @@ k_coulomb_bare(int n, const float4 *__restrict__ xs, const float *__restrict__ q
         __syncthreads();
         int lim = min(BARE_T, n - base);
         for (int t = 0; t < lim; ++t) {
-            if (base + t == i) continue;
+            if (base + t == i || i >= n) continue;  // idle lanes sit at the origin: 0 * inf otherwise
             double4 b = sj[t];
             double dx = b.x - xi, dy = b.y - yi, dz = b.z - zi;
             dx -= Lx * rint(dx / Lx); dy -= Ly * rint(dy / Ly); dz -= Lz * rint(dz / Lz);

@@ -220,14 +220,14 @@ def nonbonded_bruteforce(positions, box, params, charges, bonded, scaling, rc_lj
     bonded, scaling = _pad_rows(bonded), _pad_rows(scaling)
     i0, i1 = (0, n) if i_range is None else i_range
     f_lj = np.zeros((n, 3)); f_c = np.zeros((n, 3))
-    en = np.zeros(3); cnt = np.zeros(2, dtype=np.int64)
+    en = np.zeros(5); cnt = np.zeros(2, dtype=np.int64)
     lib().ora_nonbonded_bruteforce(
         n, _p(pos), _p(box), _p(params), _p(q), _p(bonded), bonded.shape[1], _p(scaling),
         scaling.shape[1], C.c_double(rc_lj), C.c_double(rc_lj if r_on is None else r_on),
         int(coul_mode), C.c_double(k_e), C.c_double(alpha),
         C.c_double(rc_lj if rc_coul is None else rc_coul), int(i0), int(i1), _p(f_lj), _p(f_c),
         _p(en), _p(cnt))
-    return dict(f_lj=f_lj, f_coul=f_c, e_lj=en[0], e_coul=en[1], e_excl=en[2],
+    return dict(f_lj=f_lj, f_coul=f_c, e_lj=en[0], e_coul=en[1], e_excl=en[2], e_lj_abs=en[3], e_coul_abs=en[4],
                 n_lj=int(cnt[0]), n_coul=int(cnt[1]))
 
 

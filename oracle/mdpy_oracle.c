@@ -70,6 +70,7 @@ static inline double minimg(double d, double L) { return d - L * rint(d / L); }
  * sub-range can be checked on large systems; energies are half the ordered-pair sums over
  * that range (== the total when the range is [0, n)).
  * energies[0]=E_lj  [1]=E_coul (direct or bare)  [2]=E_excluded-pair correction
+ * [3]=sum of |LJ pair energies|  [4]=sum of |Coulomb pair energies| (the scale a cancelling total is judged on)
  * counts[0]=ordered in-cutoff LJ pairs, counts[1]=ordered in-cutoff Coulomb pairs */
 void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const double *params,
                               const double *charges, const int *bonded, int wb,
@@ -78,7 +79,7 @@ void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const
                               int i1, double *f_lj, double *f_coul, double *energies,
                               long long *counts) {
     const double two_over_sqrtpi = 1.1283791670955126;
-    double e_lj = 0, e_c = 0, e_x = 0;
+    double e_lj = 0, e_c = 0, e_x = 0, e_lj_abs = 0, e_c_abs = 0;
     long long n_lj = 0, n_c = 0;
     const double a2 = rc_lj * rc_lj, b2 = r_on * r_on;
     const int use_switch = (r_on < rc_lj);
@@ -109,7 +110,7 @@ void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const
                     dedr = dedr * S + e * dS;
                     e *= S;
                 }
-                e_lj += 0.5 * e;
+                e_lj += 0.5 * e; e_lj_abs += 0.5 * fabs(e);
                 ++n_lj;
                 for (int a = 0; a < 3; ++a) fl[a] += dedr * d[a] / r; /* F_i = +dE/dr * rhat(i->j) */
                 (void)fscal;
@@ -117,7 +118,7 @@ void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const
             double qq = k_e * charges[i] * charges[j];
             if (coul_mode == 2) {
                 if (!excluded) {
-                    e_c += 0.5 * qq / r;
+                    e_c += 0.5 * qq / r; e_c_abs += 0.5 * fabs(qq / r);
                     ++n_c;
                     for (int a = 0; a < 3; ++a) fc[a] += -qq / r2 * d[a] / r;
                 }
@@ -126,7 +127,7 @@ void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const
                     if (r <= rc_c) {
                         double ar = alpha * r;
                         double erfc_ar = erfc(ar);
-                        e_c += 0.5 * qq * erfc_ar / r;
+                        e_c += 0.5 * qq * erfc_ar / r; e_c_abs += 0.5 * fabs(qq * erfc_ar / r);
                         ++n_c;
                         double dedr = -qq * (erfc_ar / r2 + two_over_sqrtpi * alpha * exp(-ar * ar) / r);
                         for (int a = 0; a < 3; ++a) fc[a] += dedr * d[a] / r;
@@ -147,7 +148,7 @@ void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const
             if (f_coul) f_coul[3 * i + a] = fc[a];
         }
     }
-    energies[0] = e_lj; energies[1] = e_c; energies[2] = e_x;
+    energies[0] = e_lj; energies[1] = e_c; energies[2] = e_x; energies[3] = e_lj_abs; energies[4] = e_c_abs;
     counts[0] = n_lj; counts[1] = n_c;
 }
 

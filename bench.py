@@ -196,7 +196,7 @@ def run_b200(args, cfg):
 
     # relax the lattice start (untimed): short, strongly damped steps, then the production step
     for dt, gamma, steps in ((0.1, 0.2, 200), (0.5, 0.05, 200), (1.0, 0.01, 300)):
-        LangevinIntegrator(dt, TEMPERATURE, gamma, seed=1).integrate(ens, steps)
+        LangevinIntegrator(dt, TEMPERATURE, gamma, seed=1).integrate(ens, max(1, int(steps * args.relax)))
     integ = LangevinIntegrator(cfg['dt'], TEMPERATURE, GAMMA, seed=1)
     integ.integrate(ens, max(args.warmup, 3))
     terms = 0
@@ -230,6 +230,11 @@ def run_b200(args, cfg):
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
+        return
+
+    if args.skip_extras:
+        print(json.dumps(dict(metric='ns_per_day', value=value, unit='ns/day', steps=args.steps, warmup=args.warmup,
+                              ms_per_step=dev_ms / args.steps, gpu_launches=launches, note='skip-extras (profiling run)')))
         return
 
     # ---- per-phase profile (separate pass, per-phase events add syncs: not part of `value`) ----
@@ -333,6 +338,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='water_23k', choices=sorted(CONFIGS))
+    ap.add_argument('--relax', type=float, default=1.0, help='scale of the untimed lattice-relaxation phase')
+    ap.add_argument('--skip-extras', action='store_true', help='only the timed region (for ncu runs)')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == 'reference':

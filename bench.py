@@ -167,15 +167,15 @@ def run_reference(args, cfg):
 
 # ---------------------------------------------------------------------------------------------
 def run_b200(args, cfg):
-    import mdpy_b200 as md
-    from mdpy_b200 import _native
+    import mdpy_b200 as md  # noqa: F401
+    from mdpy_b200 import _native, multigpu
     from mdpy_b200.integrator import LangevinIntegrator
     from mdpy_b200.unit import KB, Quantity, default_energy_unit, kelvin
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    dist = None
+    dist = torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -189,23 +189,58 @@ def run_b200(args, cfg):
                           order=4, bonded=True)
     ctx = _native.context_of(ens)
     dev = ctx.dev
-    if world > 1:
-        from mdpy_b200 import multigpu
-        multigpu.attach(ctx, dist, rank, world)
     kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
-
-    # relax the lattice start (untimed): short, strongly damped steps, then the production step
-    for dt, gamma, steps in ((0.1, 0.2, 200), (0.5, 0.05, 200), (1.0, 0.01, 300)):
-        LangevinIntegrator(dt, TEMPERATURE, gamma, seed=1).integrate(ens, max(1, int(steps * args.relax)))
-    integ = LangevinIntegrator(cfg['dt'], TEMPERATURE, GAMMA, seed=1)
-    integ.integrate(ens, max(args.warmup, 3))
-    terms = 0
-    for c in ens.constraints:
-        terms |= c.terms
+    dt = cfg['dt']
 
     def barrier():
         if dist is not None:
             dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # relax the lattice start (untimed; every rank runs it redundantly and deterministically, so all
+    # ranks hold bit-identical state): short, strongly damped steps, then the production step
+    for rdt, gamma, steps in ((0.1, 0.2, 200), (0.5, 0.05, 200), (1.0, 0.01, 300)):
+        LangevinIntegrator(rdt, TEMPERATURE, gamma, seed=1).integrate(ens, max(1, int(steps * args.relax)))
+    integ = LangevinIntegrator(dt, TEMPERATURE, GAMMA, seed=1)
+    integ.integrate(ens, 20)
+    terms = 0
+    for c in ens.constraints:
+        terms |= c.terms
+
+    # ---- per-phase profile (separate untimed pass; per-phase events add syncs) ----
+    prof_steps = 50 if n > 200000 else 200
+    dev.set_profiling(2)
+    dev.step_langevin(dt, kT, GAMMA, 1, prof_steps, terms)
+    ph = dev.timing()
+    dev.set_profiling(0)
+    pair_ms = ph['pair_ms'] / prof_steps
+    pme_ms = (ph['spread_ms'] + ph['fft_ms'] + ph['gather_ms']) / prof_steps
+    bonded_ms = ph['bonded_ms'] / prof_steps
+    lj = ens.constraints[0]
+    ens.state._positions = dev.download_positions()
+    ctx._pos_rev = None
+    n_pairs = len(lj.neighbor_pairs())      # in-cutoff pair count of the current configuration (flop model)
+    slots_single = dev.timing()['j_chunks'] * 1024.0
+
+    # ---- multi-GPU: join the communicator, deal i-blocks to ranks weighted by the extra roles ----
+    weights = None
+    if world > 1:
+        weights = multigpu.role_weights(world, pair_ms + ph['nlist_ms'] / prof_steps, pme_ms, bonded_ms)
+        multigpu.attach(ctx, dist, rank, world, weights)
+    integ.integrate(ens, max(args.warmup, 3))
 
     # ---- timed region: K steps, state resident on the device, CUDA events on the ctx stream ----
     dev.set_profiling(1)
@@ -213,90 +248,86 @@ def run_b200(args, cfg):
     barrier()
     with ClockSampler(local) as clocks:
         w0 = time.perf_counter()
-        dev.step_langevin(cfg['dt'], kT, GAMMA, 1, args.steps, terms)
+        dev.step_langevin(dt, kT, GAMMA, 1, args.steps, terms)
         wall = time.perf_counter() - w0
     barrier()
     t_after = dev.timing()
-    dev_ms = t_after['total_ms']
-    if dist is not None:
-        import torch
-        tt = torch.tensor([dev_ms], device='cuda', dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms = float(tt.item())
-    launches = int(t_after['launches'] - t_before['launches'])
+    dev_ms = max_over_ranks(t_after['total_ms'])
+    launches = int(sum_over_ranks(t_after['launches'] - t_before['launches']))
     rebuilds = int(t_after['rebuilds'] - t_before['rebuilds'])
-    value = ns_per_day(args.steps, dev_ms * 1e-3, cfg['dt'])
+    value = ns_per_day(args.steps, dev_ms * 1e-3, dt)
 
-    if rank != 0:
+    if args.skip_extras:
+        if rank == 0:
+            print(json.dumps(dict(metric='ns_per_day', value=value, unit='ns/day', steps=args.steps, warmup=args.warmup,
+                                  n_gpus=world, ms_per_step=dev_ms / args.steps, gpu_launches=launches,
+                                  note='skip-extras (profiling run)')))
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    if args.skip_extras:
-        print(json.dumps(dict(metric='ns_per_day', value=value, unit='ns/day', steps=args.steps, warmup=args.warmup,
-                              ms_per_step=dev_ms / args.steps, gpu_launches=launches, note='skip-extras (profiling run)')))
-        return
-
-    # ---- per-phase profile (separate pass, per-phase events add syncs: not part of `value`) ----
-    prof_steps = min(200, max(20, args.steps))
+    # per-phase profile of the (possibly sharded) step, every rank in lockstep
     dev.set_profiling(2)
-    dev.step_langevin(cfg['dt'], kT, GAMMA, 1, prof_steps, terms)
-    ph = dev.timing()
-    dev.set_profiling(0)
-    pair_ms = ph['pair_ms'] / prof_steps
-    pme_ms = (ph['spread_ms'] + ph['fft_ms'] + ph['gather_ms']) / prof_steps
-    # L2-flushed variant: one step at a time with a 256 MB memset in between (outside the events)
+    dev.step_langevin(dt, kT, GAMMA, 1, prof_steps, terms)
+    ph_n = dev.timing()
     dev.set_profiling(1)
+    # L2-flushed variant: one step at a time with a 256 MB memset in between (outside the events)
     fl = []
     for _ in range(min(50, args.steps)):
         dev.flush_l2()
-        dev.step_langevin(cfg['dt'], kT, GAMMA, 1, 1, terms)
+        dev.step_langevin(dt, kT, GAMMA, 1, 1, terms)
         fl.append(dev.timing()['total_ms'])
     dev.set_profiling(0)
 
-    # in-cutoff pair count of the current configuration (for the flop model)
-    lj = ens.constraints[0]
-    ctx._pos_rev = None
+    # ---- e2e: the drop-in per-step path with host buffers (all ranks in lockstep, same seeds) ----
+    e2e_steps = min(args.steps, 300 if n < 200000 else 30)
     ens.state._positions = dev.download_positions()
-    n_pairs = len(lj.neighbor_pairs())
-
-    peaks = measured_peaks()
-    fp32_peak = 148 * 128 * 2 * peaks['sm_max_mhz'] * 1e6 / 1e12
-    achieved = FLOP_PER_PAIR * n_pairs / (pair_ms * 1e-3) / 1e12
-    K = int(np.prod(cfg['grid']))
-    pme_bytes = 44.0 * n + 34.0 * K
-    pme_gbs = pme_bytes / (pme_ms * 1e-3) / 1e9
-
-    # ---- e2e: the drop-in per-step path with host buffers ----
-    e2e_steps = min(args.steps, 300)
+    ens.state._velocities = dev.download_velocities()
     x = ens.state.positions.astype(np.float64)
     v = ens.state.velocities.astype(np.float64)
     m = np.asarray(ens.topology.masses, dtype=np.float64).reshape(-1, 1)
     rng = np.random.default_rng(0)
-    dt = cfg['dt']
     ca = (1 - GAMMA * dt / 2) / (1 + GAMMA * dt / 2); cb = 1 / (1 + GAMMA * dt / 2)
-    ens.state.set_positions(x.astype(np.float32)); ens.update()
-    f = ens.forces.copy()
+    noise = np.sqrt(2 * GAMMA * kT * dt * m)
     for _ in range(3):   # warm-up of the host path
         ens.state.set_positions(x.astype(np.float32)); ens.update()
+    f = ens.forces.copy()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        beta = np.sqrt(2 * GAMMA * kT * dt * m) * rng.standard_normal(x.shape)
+        beta = noise * rng.standard_normal(x.shape)
         x = x + cb * dt * v + cb * dt * dt / (2 * m) * f + cb * dt / (2 * m) * beta
         xw = (x - system.box * np.round(x / system.box)).astype(np.float32)
-        ens.state.set_positions(xw)            # host -> State (wrap), H2D inside update()
-        ens.update()                           # one fused device evaluation, forces D2H
+        ens.state.set_positions(xw)            # host -> State (wrap); H2D inside update()
+        ens.update()                           # one fused device evaluation; forces D2H
         f_new = ens.forces
         v = ca * v + dt / (2 * m) * (ca * f + f_new) + cb / m * beta
-        f = f_new.copy()
-    e2e_sec = time.perf_counter() - t0
+        f = f_new
+    e2e_sec = max_over_ranks(time.perf_counter() - t0)
     e2e_value = ns_per_day(e2e_steps, e2e_sec, dt)
 
-    # ---- CPU baseline (bounded sample) ----
-    threads = os.cpu_count() or 1
-    cpu_sec, sample = reference_step_seconds(system, cfg, 1, budget_s=10.0)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
 
-    stats = dev.timing()
+    peaks = measured_peaks()
+    fp32_peak = 148 * 128 * 2 * peaks['sm_max_mhz'] * 1e6 / 1e12
+    pair_ms_n = ph_n['pair_ms'] / prof_steps
+    # this rank evaluates its share of the pair slots; at N=1 that is everything
+    share = (ph_n['j_chunks'] * 1024.0) / max(1.0, slots_single)
+    achieved = FLOP_PER_PAIR * n_pairs * share / (pair_ms_n * 1e-3) / 1e12
+    K = int(np.prod(cfg['grid']))
+    pme_bytes = 44.0 * n + 34.0 * K
+    pme_gbs = pme_bytes / (pme_ms * 1e-3) / 1e9
+
+    # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1:
+        cpu_sec, sample = reference_step_seconds(system, cfg, 1, budget_s=10.0)
+        cpu = dict(value=ns_per_day(1, cpu_sec, dt), unit='ns/day', cores=1, kind='port', sample=sample,
+                   host_cores=os.cpu_count(), seconds_per_step=cpu_sec)
+
+    phase_keys = ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms', 'comm_ms')
     line = dict(
         metric='ns_per_day', value=value, unit='ns/day', n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
@@ -304,6 +335,9 @@ def run_b200(args, cfg):
         config=dict(workload=args.config, atoms=n, cutoff_A=cfg['cutoff'], switch_A=cfg['switch'], pme_grid=list(cfg['grid']),
                     pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=2.0,
                     terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_in_timed=rebuilds,
+                    parallelism='single GPU' if world == 1 else
+                    'replicated positions, i-block sharded pair forces (weights %s), PME on last rank, int64 all-reduce per step'
+                    % np.round(weights, 3).tolist(),
                     l2='steady-state MD trajectory: every step consumes the previous step\'s output, nothing is re-timed '
                        'on a repeated input; working set %.1f MB; l2_flushed_ms_per_step gives the same step with a '
                        '256 MB L2 flush before it' % ((32.0 * n + 12.0 * K) / 1e6)),
@@ -313,19 +347,20 @@ def run_b200(args, cfg):
                  steps=e2e_steps, ms_per_step=e2e_sec * 1e3 / e2e_steps,
                  path='State.set_positions + Ensemble.update (fused mdk_compute) per step, numpy G-JF update on the host'),
         roofline=dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak, traffic=None,
-                      kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=pair_ms,
-                      peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source']),
+                      kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=pair_ms_n,
+                      peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source'],
+                      note='rank 0 share of the pair work at N > 1' if world > 1 else 'whole pair kernel'),
         roofline_pme=dict(bound='hbm', achieved=pme_gbs, peak=peaks['hbm_gbs'], unit='GB/s', frac=pme_gbs / peaks['hbm_gbs'],
                           bytes_per_step=pme_bytes, kernels_ms=pme_ms, peak_source=peaks['source'],
-                          note='spread + convert + cuFFT R2C/C2R + convolve + gather; mesh is L2 resident'),
-        phases_ms_per_step={k: ph[k] / prof_steps for k in ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms',
-                                                            'bonded_ms', 'integrate_ms')},
-        nlist=dict(work_units=int(stats['work_units']), j_chunks=int(stats['j_chunks']), masked_chunks=int(stats['masked_chunks']),
-                   seg_chunks=int(stats['seg_chunks']), pair_slots=int(stats['j_chunks']) * 1024,
-                   slot_efficiency=n_pairs / max(1.0, stats['j_chunks'] * 1024.0)),
-        cpu_baseline=dict(value=ns_per_day(1, cpu_sec, dt), unit='ns/day', cores=1, kind='port', sample=sample,
-                          host_cores=threads, seconds_per_step=cpu_sec),
+                          note='spread + convert + cuFFT R2C/C2R + convolve + gather (single-GPU pass); mesh is L2 resident'),
+        phases_ms_per_step={k: ph_n[k] / prof_steps for k in phase_keys},
+        phases_ms_per_step_single_gpu={k: ph[k] / prof_steps for k in phase_keys},
+        nlist=dict(work_units=int(ph_n['work_units']), j_chunks=int(ph_n['j_chunks']), masked_chunks=int(ph_n['masked_chunks']),
+                   seg_chunks=int(ph_n['seg_chunks']), pair_slots=int(slots_single),
+                   slot_efficiency=n_pairs / max(1.0, slots_single)),
     )
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -158,8 +158,10 @@ MDK_API int mdk_get_pairs(mdk_ctx *ctx, int32_t *out_i, int32_t *out_j, int64_t 
 /* Device time (ms, CUDA events on the ctx stream) of the last mdk_compute / step call,
  * per phase: [0]=nlist rebuild [1]=pair kernel [2]=pme spread [3]=fft+convolve
  * [4]=pme gather [5]=bonded+special pairs [6]=integrate [7]=bare coulomb
- * [8]=total; plus counters [9]=kernel launches [10]=nlist rebuilds [11]=pair-kernel launches. */
-MDK_API int mdk_get_timing(mdk_ctx *ctx, double *out16);
+ * [8]=total [9]=NCCL all-reduce; plus counters [10]=kernel launches [11]=nlist rebuilds
+ * [12]=pair-kernel launches [13]=work units [14]=j-chunks [15]=masked chunks [16]=chunks per unit
+ * [17]=i-blocks. */
+MDK_API int mdk_get_timing(mdk_ctx *ctx, double *out24);
 /* Event timing level: 0 off (default), 1 whole-call CUDA events only, 2 per-phase events (adds stream syncs). */
 MDK_API int mdk_set_profiling(mdk_ctx *ctx, int level);
 /* Raw device pointer + element count of the int64 fixed-point force accumulator in
@@ -167,9 +169,16 @@ MDK_API int mdk_set_profiling(mdk_ctx *ctx, int level);
 MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);
-/* Restrict the pair-kernel work units this ctx evaluates to those with
- * (unit_index % nranks) == rank (replicated-data force decomposition). */
-MDK_API int mdk_set_shard(mdk_ctx *ctx, int rank, int nranks);
+/* Restrict the i-blocks whose work units this ctx builds and evaluates to those with
+ * (block % modulus) in [lo, hi) (replicated-data force decomposition; weights = range widths). */
+MDK_API int mdk_set_shard(mdk_ctx *ctx, int lo, int hi, int modulus);
+/* Multi-GPU: one process per GPU.  mdk_comm_unique_id wraps ncclGetUniqueId (rank 0 calls it and
+ * ships the 128 bytes to the other ranks by any means, e.g. torch.distributed.broadcast);
+ * mdk_comm_init joins the communicator.  Afterwards every force evaluation ends with one
+ * ncclAllReduce(sum) of the int64 force accumulator; bonded / excluded-pair terms run on rank 0
+ * only, the PME mesh on the last rank. */
+MDK_API int mdk_comm_unique_id(void *out128);
+MDK_API int mdk_comm_init(mdk_ctx *ctx, int rank, int nranks, const void *unique_id128);
 
 #ifdef __cplusplus
 }

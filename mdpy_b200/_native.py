@@ -40,7 +40,7 @@ EXPORTS = [
     'mdk_download_positions_f64', 'mdk_download_velocities', 'mdk_build_nlist', 'mdk_compute',
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
-    'mdk_set_shard', 'mdk_flush_l2',
+    'mdk_set_shard', 'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init',
 ]
 
 _lib = None
@@ -88,7 +88,9 @@ def load_library():
         'mdk_get_timing': (i32, [vp, vp]),
         'mdk_set_profiling': (i32, [vp, i32]),
         'mdk_force_accumulator': (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
-        'mdk_set_shard': (i32, [vp, i32, i32]),
+        'mdk_set_shard': (i32, [vp, i32, i32, i32]),
+        'mdk_comm_unique_id': (i32, [vp]),
+        'mdk_comm_init': (i32, [vp, i32, i32, vp]),
         'mdk_flush_l2': (i32, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -178,8 +180,19 @@ class Device:
     def set_stream(self, cuda_stream):
         self._ck(self._lib.mdk_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
-    def set_shard(self, rank, nranks):
-        self._ck(self._lib.mdk_set_shard(self._h, int(rank), int(nranks)))
+    def set_shard(self, lo, hi, modulus):
+        self._ck(self._lib.mdk_set_shard(self._h, int(lo), int(hi), int(modulus)))
+
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        rc = self._lib.mdk_comm_unique_id(buf)
+        if rc != MDK_OK:
+            raise RuntimeError(self._lib.mdk_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._ck(self._lib.mdk_comm_init(self._h, int(rank), int(nranks), buf))
 
     # -- state
     def upload_positions(self, xyz):
@@ -257,10 +270,11 @@ class Device:
             cap = int(cnt.value)
 
     def timing(self):
-        t = np.zeros(16, dtype=np.float64)
+        t = np.zeros(24, dtype=np.float64)
         self._ck(self._lib.mdk_get_timing(self._h, _ptr(t)))
         keys = ['nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms', 'bare_ms',
-                'total_ms', 'launches', 'rebuilds', 'pair_launches', 'work_units', 'j_chunks', 'masked_chunks', 'seg_chunks']
+                'total_ms', 'comm_ms', 'launches', 'rebuilds', 'pair_launches', 'work_units', 'j_chunks', 'masked_chunks',
+                'seg_chunks', 'i_blocks']
         return dict(zip(keys, t.tolist()))
 
     def set_profiling(self, level=1):

@@ -119,6 +119,7 @@ void mdk_destroy(mdk_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    comm_destroy(c);
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
     c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release();
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
@@ -449,14 +450,15 @@ int mdk_get_pairs(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64
     return pair_enumerate(c, out_i, out_j, cap, n_out);
 }
 
-int mdk_get_timing(mdk_ctx *c, double *out16) {
+int mdk_get_timing(mdk_ctx *c, double *out24) {
     NEED_CTX(c);
-    if (!out16) return fail(c, MDK_ERR_BAD_ARG, "out is NULL");
-    for (int k = 0; k < 16; ++k) out16[k] = 0;
-    for (int k = 0; k < PH_COUNT; ++k) out16[k] = c->phase_ms[k];
-    out16[9] = (double)c->n_launches; out16[10] = (double)c->n_rebuilds; out16[11] = (double)c->n_pair_launches;
-    out16[12] = (double)c->stat_units; out16[13] = (double)c->stat_chunks; out16[14] = (double)c->stat_masks;
-    out16[15] = (double)c->seg_chunks;
+    if (!out24) return fail(c, MDK_ERR_BAD_ARG, "out is NULL");
+    for (int k = 0; k < 24; ++k) out24[k] = 0;
+    for (int k = 0; k <= PH_TOTAL; ++k) out24[k] = c->phase_ms[k];
+    out24[9] = c->phase_ms[PH_COMM];
+    out24[10] = (double)c->n_launches; out24[11] = (double)c->n_rebuilds; out24[12] = (double)c->n_pair_launches;
+    out24[13] = (double)c->stat_units; out24[14] = (double)c->stat_chunks; out24[15] = (double)c->stat_masks;
+    out24[16] = (double)c->seg_chunks; out24[17] = (double)c->n_blocks;
     return MDK_OK;
 }
 
@@ -476,13 +478,6 @@ int mdk_flush_l2(mdk_ctx *c) {
     const size_t bytes = (size_t)256 << 20;  // > 126 MB of L2
     MDK_CUDA(c, c->sort_tmp.reserve(bytes));
     MDK_CUDA(c, cudaMemsetAsync(c->sort_tmp.p, 0xA5, bytes, c->stream));
-    return MDK_OK;
-}
-
-int mdk_set_shard(mdk_ctx *c, int rank, int nranks) {
-    NEED_CTX(c);
-    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_shard(%d, %d)", rank, nranks);
-    c->shard_rank = rank; c->shard_n = nranks;
     return MDK_OK;
 }
 

@@ -60,7 +60,7 @@ struct BondedSet {
     DevBuf<float> par;
 };
 
-enum Phase { PH_NLIST = 0, PH_PAIR, PH_SPREAD, PH_FFT, PH_GATHER, PH_BONDED, PH_INTEGRATE, PH_BARE, PH_TOTAL, PH_COUNT };
+enum Phase { PH_NLIST = 0, PH_PAIR, PH_SPREAD, PH_FFT, PH_GATHER, PH_BONDED, PH_INTEGRATE, PH_BARE, PH_TOTAL, PH_COMM, PH_COUNT };
 
 }  // namespace mdk
 
@@ -122,7 +122,9 @@ struct mdk_ctx {
     bool nlist_valid = false;
     int seg_chunks = 8;
     int64_t stat_units = 0, stat_chunks = 0, stat_masks = 0;
-    int shard_rank = 0, shard_n = 1;
+    int shard_lo = 0, shard_hi = 1, shard_mod = 1;   // this rank owns i-blocks b with (b % mod) in [lo, hi)
+    void *nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
 
     // ---- PME ----
     int pme_n[3] = {0, 0, 0};
@@ -192,6 +194,9 @@ int bonded_compute(mdk_ctx *c, unsigned terms);
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms);
 int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);
+int comm_allreduce_forces(mdk_ctx *c);
+int comm_allreduce_energies(mdk_ctx *c);
+void comm_destroy(mdk_ctx *c);
 
 // ---------------------------------------------------------------------------
 // device helpers

@@ -29,6 +29,7 @@ struct GridParams {
     float inv_cw[3];
     float R, R2;
     float skin_half2;
+    int shard_lo, shard_hi, shard_mod;
 };
 
 // ---------------------------------------------------------------------------
@@ -254,6 +255,10 @@ k_build_lists(GridParams g, const float4 *__restrict__ xs, const float4 *__restr
     int *stage = stage_all[wid];
     int warp_global = blockIdx.x * BUILD_WARPS + wid, n_warps = gridDim.x * BUILD_WARPS;
     for (int b = warp_global; b < g.n_blocks; b += n_warps) {
+        if (g.shard_mod > 1) {  // multi-GPU: another rank owns this i-block
+            int r = b % g.shard_mod;
+            if (r < g.shard_lo || r >= g.shard_hi) continue;
+        }
         float4 c = bbc[b], h = bbh[b];
         BlockEmitter em;
         em.b = b; em.lane = lane; em.n = g.n;
@@ -341,6 +346,7 @@ static GridParams make_grid_params(mdk_ctx *c) {
     g.R = rc + c->skin;
     g.R2 = g.R * g.R;
     g.skin_half2 = 0.25f * c->skin * c->skin;
+    g.shard_lo = c->shard_lo; g.shard_hi = c->shard_hi; g.shard_mod = c->shard_mod;
     return g;
 }
 

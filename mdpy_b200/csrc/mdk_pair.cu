@@ -21,7 +21,6 @@ struct PairParams {
     float rc2_lj, ron2, inv_ab3, rc2_max;  // CHARMM switch: (rc^2 - ron^2)^-3
     float rc2_c, alpha, two_alpha_over_sqrtpi;
     int n;
-    int shard_rank, shard_n;
 };
 
 // erfc(x) * exp(x^2) ~= t * P(t), t = 1 / (1 + 0.4 x): degree-8 least-squares fit on
@@ -56,7 +55,7 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(cursor, 1);
-        u = __shfl_sync(0xffffffffu, u, 0) * P.shard_n + P.shard_rank;
+        u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
         const int4 unit = nl.units[u];
         const int ia = unit.x * TILE + lane;
@@ -177,7 +176,6 @@ static PairParams make_pair_params(mdk_ctx *c, bool do_lj, bool do_coul) {
     P.alpha = (float)c->alpha;
     P.two_alpha_over_sqrtpi = (float)(2.0 * c->alpha / sqrt(M_PI));
     P.n = c->n;
-    P.shard_rank = c->shard_rank; P.shard_n = c->shard_n;
     return P;
 }
 

@@ -290,15 +290,20 @@ int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
     MDK_TRY(nlist_ensure(c));
     MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
     MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
+    // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units; the O(N) terms
+    // run once — bonded / excluded-pair / bare Coulomb on rank 0, the PME mesh on the last rank
+    const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
     MDK_TRY(pair_compute(c, terms & MDK_TERM_LJ, terms & MDK_TERM_COUL_DIRECT));
     if (terms & MDK_TERM_PME_RECIP) {
-        MDK_TRY(pme_compute(c));
-        MDK_TRY(pair_special(c, true));
+        if (last) MDK_TRY(pme_compute(c));
+        if (first) MDK_TRY(pair_special(c, true));
     }
-    if (terms & MDK_TERM_COUL_BARE) MDK_TRY(coulomb_bare(c));
-    if (terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER))
+    if ((terms & MDK_TERM_COUL_BARE) && first) MDK_TRY(coulomb_bare(c));
+    if ((terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER)) && first)
         MDK_TRY(bonded_compute(c, terms));
+    MDK_TRY(comm_allreduce_forces(c));
     if (sync_energies) {
+        MDK_TRY(comm_allreduce_energies(c));
         long long h[MDK_NUM_ENERGIES];
         MDK_CUDA(c, cudaMemcpyAsync(h, c->e_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -470,8 +475,11 @@ static StepGeom make_geom(mdk_ctx *c) {
 
 static int fetch_energies(mdk_ctx *c, unsigned terms) {
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
-    k_kinetic<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->mass.p, c->vel.p, e_acc);
-    ++c->n_launches;
+    if (c->rank == 0) {
+        k_kinetic<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->mass.p, c->vel.p, e_acc);
+        ++c->n_launches;
+    }
+    MDK_TRY(comm_allreduce_energies(c));
     long long h[MDK_NUM_ENERGIES];
     MDK_CUDA(c, cudaMemcpyAsync(h, c->e_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -1,0 +1,95 @@
+"""Multi-GPU host layer: one process per GPU (torchrun), NCCL over NVLink/NVSwitch.
+
+The reference is single-process, single-device; this is new design:
+
+* positions are replicated; every rank integrates all atoms (O(N), deterministic, so all ranks
+  stay bit-identical);
+* the i-blocks of the tile list are dealt to ranks by `block % modulus in [lo, hi)` — tile order is
+  spatial, so this is a fine spatial interleave that also balances the half-shell list lengths;
+  each rank builds and evaluates only its own blocks' work units;
+* the PME mesh runs on the last rank, bonded and excluded-pair terms on rank 0; the range widths
+  are weighted so that those ranks get fewer pair units;
+* every force evaluation ends with ONE `ncclAllReduce(sum)` of the int64 fixed-point force
+  accumulator, issued by libmdpyb200 on its own stream (mdk_comm.cu).  Integer sums are exact and
+  order independent: the N-GPU forces equal the 1-GPU forces bit for bit.
+
+torch.distributed is used for the rendezvous only (broadcast of the 128-byte NCCL unique id).
+"""
+import numpy as np
+
+RESIDUES_PER_RANK = 32   # interleave period = 32 * world i-blocks: fine enough to balance the half-shell lists
+
+
+def shard_ranges(weights, modulus=None):
+    """Split residues [0, modulus) into len(weights) consecutive ranges with widths proportional to
+    weights (largest-remainder rounding, every positive weight gets at least one residue).
+    Returns a list of (lo, hi)."""
+    w = np.asarray(weights, dtype=np.float64)
+    if modulus is None:
+        modulus = RESIDUES_PER_RANK * len(w)
+    if (w < 0).any() or w.sum() <= 0:
+        raise ValueError('weights must be non-negative with a positive sum')
+    if len(w) > modulus:
+        raise ValueError('more ranks than residues')
+    ideal = w / w.sum() * modulus
+    width = np.floor(ideal).astype(int)
+    width[(w > 0) & (width == 0)] = 1
+    # distribute what is left (or take back what the minimum-one rule overspent) by largest remainder
+    while width.sum() < modulus:
+        k = int(np.argmax(ideal - width)); width[k] += 1
+    while width.sum() > modulus:
+        k = int(np.argmax(np.where(width > 1, width - ideal, -np.inf))); width[k] -= 1
+    hi = np.cumsum(width)
+    lo = hi - width
+    return [(int(a), int(b)) for a, b in zip(lo, hi)]
+
+
+def role_weights(nranks, pair_ms, pme_ms, bonded_ms=0.0):
+    """Pair-work weights that equalise rank times when the last rank also runs the PME mesh
+    (pme_ms) and rank 0 the bonded / excluded-pair terms (bonded_ms); pair_ms is the single-GPU
+    pair-kernel time.  Solves  pair_ms * x_r + extra_r = T  with  sum x_r = 1."""
+    extra = np.zeros(nranks)
+    extra[-1] += pme_ms
+    extra[0] += bonded_ms
+    if nranks == 1:
+        return np.ones(1)
+    active = np.ones(nranks, dtype=bool)
+    for _ in range(nranks):
+        T = (pair_ms + extra[active].sum()) / active.sum()
+        x = np.where(active, (T - extra) / pair_ms, 0.0)
+        if (x[active] >= 0).all():
+            break
+        active &= x > 0       # a rank whose extra work already exceeds T gets no pair work
+    x = np.clip(x, 0, None)
+    if x.sum() <= 0:
+        x = np.ones(nranks)
+    return x / x.sum()
+
+
+def broadcast_unique_id(dist, dev, rank):
+    """Rank 0 asks NCCL (through libmdpyb200) for a unique id and ships it with torch.distributed."""
+    import torch
+    if dist.get_backend() == 'nccl':
+        buf = torch.zeros(128, dtype=torch.uint8, device='cuda')
+    else:
+        buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = dev.comm_unique_id()
+        buf.copy_(torch.frombuffer(bytearray(uid), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def attach(ctx, dist, rank, world, weights=None):
+    """Join this rank's device context to the job: communicator + i-block shard."""
+    dev = ctx.dev
+    uid = broadcast_unique_id(dist, dev, rank)
+    dev.comm_init(rank, world, uid)
+    set_weights(ctx, rank, world, np.ones(world) if weights is None else weights)
+
+
+def set_weights(ctx, rank, world, weights):
+    modulus = RESIDUES_PER_RANK * world
+    lo, hi = shard_ranges(weights, modulus)[rank]
+    ctx.dev.set_shard(lo, hi, modulus)
+    ctx.shard = (lo, hi, modulus)

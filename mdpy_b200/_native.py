@@ -274,7 +274,7 @@ class Device:
         self._ck(self._lib.mdk_get_timing(self._h, _ptr(t)))
         keys = ['nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms', 'bare_ms',
                 'total_ms', 'comm_ms', 'launches', 'rebuilds', 'pair_launches', 'work_units', 'j_chunks', 'masked_chunks',
-                'seg_chunks', 'i_blocks']
+                'seg_chunks', 'i_blocks', 'shift_ok']
         return dict(zip(keys, t.tolist()))
 
     def set_profiling(self, level=1):

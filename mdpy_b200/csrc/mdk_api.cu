@@ -103,12 +103,17 @@ int mdk_create(int device, mdk_ctx **out) {
         return fail(nullptr, MDK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
-    if (c->counters.reserve(8) != cudaSuccess || c->flags.reserve(4) != cudaSuccess ||
+    cudaStreamCreateWithFlags(&c->s_pme, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_pme, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
+    if (c->counters.reserve(16) != cudaSuccess || c->flags.reserve(4) != cudaSuccess ||
         c->e_acc.reserve(MDK_NUM_ENERGIES) != cudaSuccess) {
         mdk_destroy(c);
         return fail(nullptr, MDK_ERR_OOM, "cudaMalloc failed in mdk_create");
     }
-    cudaMemset(c->counters.p, 0, 8 * sizeof(int));
+    cudaMemset(c->counters.p, 0, 16 * sizeof(int));
     cudaMemset(c->flags.p, 0, 4 * sizeof(int));
     cudaMemset(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long));
     *out = c;
@@ -132,6 +137,11 @@ void mdk_destroy(mdk_ctx *c) {
     c->counters.release();
     c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_pme) cudaEventDestroy(c->ev_pme);
+    if (c->ev_aux) cudaEventDestroy(c->ev_aux);
+    if (c->s_pme) cudaStreamDestroy(c->s_pme);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -458,7 +468,7 @@ int mdk_get_timing(mdk_ctx *c, double *out24) {
     out24[9] = c->phase_ms[PH_COMM];
     out24[10] = (double)c->n_launches; out24[11] = (double)c->n_rebuilds; out24[12] = (double)c->n_pair_launches;
     out24[13] = (double)c->stat_units; out24[14] = (double)c->stat_chunks; out24[15] = (double)c->stat_masks;
-    out24[16] = (double)c->seg_chunks; out24[17] = (double)c->n_blocks;
+    out24[16] = (double)c->seg_chunks; out24[17] = (double)c->n_blocks; out24[18] = c->shift_ok ? 1.0 : 0.0;
     return MDK_OK;
 }
 

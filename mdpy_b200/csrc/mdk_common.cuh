@@ -69,6 +69,10 @@ struct mdk_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    // side streams: the PME mesh chain and the O(N) bonded / excluded-pair kernels run beside k_pair
+    cudaStream_t s_pme = nullptr, s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_pme = nullptr, ev_aux = nullptr;
+    bool concurrent = true;
     std::string err;
 
     // ---- system (matrix_id order) ----
@@ -117,9 +121,11 @@ struct mdk_ctx {
     mdk::DevBuf<int4> units;
     mdk::DevBuf<int> chunk_j, chunk_mask;
     mdk::DevBuf<unsigned> mask_excl, mask_14;
-    mdk::DevBuf<int> counters;                // [0]=units [1]=chunks [2]=mask slots [3]=work cursor
+    mdk::DevBuf<int> counters;                // [0]=units [1]=chunks [2]=mask slots [3]=work cursor [8..10]=max bbox half extents (float bits)
     size_t cap_units = 0, cap_chunks = 0, cap_masks = 0;
     bool nlist_valid = false;
+    bool force_canonical = false;             // test hook: always the per-pair canonical minimum image
+    bool shift_ok = false;                    // box large enough to hoist the minimum image out of the pair loop
     int seg_chunks = 8;
     int64_t stat_units = 0, stat_chunks = 0, stat_masks = 0;
     int shard_lo = 0, shard_hi = 1, shard_mod = 1;   // this rank owns i-blocks b with (b % mod) in [lo, hi)
@@ -214,6 +220,11 @@ __device__ __forceinline__ long long to_fix(float f) { return __float2ll_rn(f * 
 __device__ __forceinline__ long long to_fix(double f) { return __double2ll_rn(f * FIX_SCALE); }
 __device__ __forceinline__ void atomic_add_fix(long long *p, long long v) {
     atomicAdd(reinterpret_cast<unsigned long long *>(p), static_cast<unsigned long long>(v));
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -127,7 +127,7 @@ __global__ void k_refresh_sorted(int n, const int *__restrict__ order, const dou
 
 // one warp per i-block: periodic bounding box relative to the block's first atom
 __global__ void k_block_bbox(GridParams g, const float4 *__restrict__ xs, float4 *__restrict__ bbc,
-                             float4 *__restrict__ bbh) {
+                             float4 *__restrict__ bbh, int *__restrict__ bb_max) {
     int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (b >= g.n_blocks) return;
@@ -153,6 +153,9 @@ __global__ void k_block_bbox(GridParams g, const float4 *__restrict__ xs, float4
                              rz + 0.5f * (mn[2] + mx[2]), 0.f);
         bbh[b] = make_float4(0.5f * (mx[0] - mn[0]) + 1e-4f, 0.5f * (mx[1] - mn[1]) + 1e-4f,
                              0.5f * (mx[2] - mn[2]) + 1e-4f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)  // non-negative floats order like their bit patterns
+            atomicMax(&bb_max[a], __float_as_int(0.5f * (mx[a] - mn[a]) + 1e-4f));
     }
 }
 
@@ -184,7 +187,7 @@ struct BlockEmitter {
         if (seg_fill > 0) {
             int u = alloc(&o.counters[0], 1);
             if (u < o.cap_units) {
-                if (lane == 0) o.units[u] = make_int4(b, seg_base, seg_fill, 0);
+                if (lane == 0) { o.units[u] = make_int4(b, seg_base, seg_fill, 0); atomicAdd(&o.counters[4], seg_fill); }
             } else if (lane == 0) o.flags[2] = 1;
         }
         seg_fill = 0;
@@ -246,15 +249,19 @@ __device__ __forceinline__ int imod(int a, int m) { int r = a % m; return r < 0 
 constexpr int BUILD_WARPS = 4;
 
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
-k_build_lists(GridParams g, const float4 *__restrict__ xs, const float4 *__restrict__ bbc,
+k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const float4 *__restrict__ bbc,
               const float4 *__restrict__ bbh, const int *__restrict__ cell_start,
               const int *__restrict__ excl_s, int wb, const int *__restrict__ p14_s, int ws,
               BuildOut o) {
     __shared__ int stage_all[BUILD_WARPS][64];
+    __shared__ float4 s_xi[BUILD_WARPS][32];
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int *stage = stage_all[wid];
     int warp_global = blockIdx.x * BUILD_WARPS + wid, n_warps = gridDim.x * BUILD_WARPS;
-    for (int b = warp_global; b < g.n_blocks; b += n_warps) {
+    // work item = (i-block, part): the candidate rows of a block are dealt round-robin to n_parts warps,
+    // each emitting its own work units, so small systems still fill the machine during a rebuild
+    for (int w = warp_global; w < g.n_blocks * n_parts; w += n_warps) {
+        const int b = w / n_parts, part = w - b * n_parts;
         if (g.shard_mod > 1) {  // multi-GPU: another rank owns this i-block
             int r = b % g.shard_mod;
             if (r < g.shard_lo || r >= g.shard_hi) continue;
@@ -265,8 +272,12 @@ k_build_lists(GridParams g, const float4 *__restrict__ xs, const float4 *__restr
         em.i_valid = (b * TILE + lane) < g.n;
         em.ragged = (b == g.n_blocks - 1) && (g.n & 31);
         em.excl_s = excl_s; em.p14_s = p14_s; em.wb = wb; em.ws = ws; em.o = o;
+        // i-atom positions of this block for the exact filter (ragged lanes repeat the first atom)
+        __syncwarp();
+        s_xi[wid][lane] = xs[em.i_valid ? b * TILE + lane : b * TILE];
+        __syncwarp();
         em.begin();
-        {
+        if (part == 0) {
             int k = b * TILE + lane;
             em.emit(k < g.n ? k : -1, true);
         }
@@ -288,6 +299,7 @@ k_build_lists(GridParams g, const float4 *__restrict__ xs, const float4 *__restr
         for (int iz = 0; iz < len[2]; ++iz) {
             int zz = lo[2] + iz; if (zz >= g.ncell[2]) zz -= g.ncell[2];
             for (int iy = 0; iy < len[1]; ++iy) {
+                if ((iz * len[1] + iy) % n_parts != part) continue;
                 int yy = lo[1] + iy; if (yy >= g.ncell[1]) yy -= g.ncell[1];
                 int row = (zz * g.ncell[1] + yy) * g.ncell[0];
                 // one or two contiguous x segments
@@ -301,13 +313,39 @@ k_build_lists(GridParams g, const float4 *__restrict__ xs, const float4 *__restr
                     s = max(s, first_j);
                     for (int base = s; base < e; base += 32) {
                         int j = base + lane;
-                        bool pass = false;
+                        bool pass = false, unsure = false;
+                        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (j < e) {
-                            float4 p = xs[j];
+                            p = xs[j];
                             float dx = fmaxf(fabsf(min_image(p.x - cc[0], g.L[0], g.invL[0])) - hh[0], 0.f);
                             float dy = fmaxf(fabsf(min_image(p.y - cc[1], g.L[1], g.invL[1])) - hh[1], 0.f);
                             float dz = fmaxf(fabsf(min_image(p.z - cc[2], g.L[2], g.invL[2])) - hh[2], 0.f);
-                            pass = (dx * dx + dy * dy + dz * dz) <= g.R2;
+                            unsure = (dx * dx + dy * dy + dz * dz) <= g.R2;
+                            // quick accept: within R of one of four representative i-atoms
+#pragma unroll
+                            for (int t = 3; t < 32 && unsure && !pass; t += 8) {
+                                const float4 q = s_xi[wid][t];
+                                const float ex = min_image(p.x - q.x, g.L[0], g.invL[0]);
+                                const float ey = min_image(p.y - q.y, g.L[1], g.invL[1]);
+                                const float ez = min_image(p.z - q.z, g.L[2], g.invL[2]);
+                                if (dist2(ex, ey, ez) <= g.R2) pass = true;
+                            }
+                            unsure = unsure && !pass;
+                        }
+                        // exact filter for the rest (the box test alone keeps ~25 % more atoms than needed):
+                        // the warp tests one candidate against all 32 i-atoms at a time
+                        unsigned todo = __ballot_sync(0xffffffffu, unsure);
+                        const float4 qi = s_xi[wid][lane];
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const float px = __shfl_sync(0xffffffffu, p.x, src), py = __shfl_sync(0xffffffffu, p.y, src),
+                                        pz = __shfl_sync(0xffffffffu, p.z, src);
+                            const float ex = min_image(px - qi.x, g.L[0], g.invL[0]);
+                            const float ey = min_image(py - qi.y, g.L[1], g.invL[1]);
+                            const float ez = min_image(pz - qi.z, g.L[2], g.invL[2]);
+                            const bool hit = __any_sync(0xffffffffu, dist2(ex, ey, ez) <= g.R2);
+                            if (lane == src) pass = hit;
                         }
                         unsigned bal = __ballot_sync(0xffffffffu, pass);
                         if (pass) stage[nstage + __popc(bal & ((1u << lane) - 1u))] = j;
@@ -441,7 +479,9 @@ int nlist_rebuild(mdk_ctx *c) {
     if (c->ws > 0)
         k_tables_sorted<<<(n * c->ws + T - 1) / T, T, 0, c->stream>>>(n, c->order.p, c->inv_order.p, c->p14.p,
                                                                       c->ws, c->p14_s.p);
-    k_block_bbox<<<(c->n_blocks * 32 + T - 1) / T, T, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p);
+    MDK_CUDA(c, cudaMemsetAsync(c->counters.p + 8, 0, 4 * sizeof(int), c->stream));
+    k_block_bbox<<<(c->n_blocks * 32 + T - 1) / T, T, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p,
+                                                                    c->counters.p + 8);
     c->n_launches += 7;
     MDK_CUDA(c, cudaGetLastError());
 
@@ -454,9 +494,9 @@ int nlist_rebuild(mdk_ctx *c) {
         if (seg < 2) seg = 2;
         if (seg > 16) seg = 16;
         c->seg_chunks = seg;
-        size_t est_chunks = (size_t)(total_chunks * 1.3) + (size_t)c->n_blocks * (seg + 1) + 1024;
+        size_t est_chunks = (size_t)(total_chunks * 1.3) + (size_t)c->n_blocks * 8 * (seg + 1) + 1024;  // <= 8 parts per block
         if (c->cap_chunks < est_chunks) c->cap_chunks = est_chunks;
-        size_t est_units = est_chunks / seg + (size_t)c->n_blocks * 2 + 1024;
+        size_t est_units = est_chunks / seg + (size_t)c->n_blocks * 9 + 1024;
         if (c->cap_units < est_units) c->cap_units = est_units;
         size_t est_masks = (size_t)c->n_blocks * 8 + 1024;
         if (c->cap_masks < est_masks) c->cap_masks = est_masks;
@@ -475,20 +515,31 @@ int nlist_rebuild(mdk_ctx *c) {
         o.counters = c->counters.p; o.flags = c->flags.p;
         o.cap_units = (int)c->cap_units; o.cap_chunks = (int)c->cap_chunks; o.cap_masks = (int)c->cap_masks;
         o.seg = c->seg_chunks;
-        int blocks = (c->n_blocks + BUILD_WARPS - 1) / BUILD_WARPS;
+        int n_parts = (int)((4096 + c->n_blocks - 1) / c->n_blocks);
+        if (n_parts < 1) n_parts = 1;
+        if (n_parts > 8) n_parts = 8;
+        int blocks = (c->n_blocks * n_parts + BUILD_WARPS - 1) / BUILD_WARPS;
         int max_blocks = c->sm_count * 16;
         if (blocks > max_blocks) blocks = max_blocks;
-        k_build_lists<<<blocks, BUILD_WARPS * 32, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p,
+        k_build_lists<<<blocks, BUILD_WARPS * 32, 0, c->stream>>>(g, n_parts, c->xs.p, c->bb_center.p, c->bb_half.p,
                                                                  c->cell_start.p, c->excl_s.p, c->wb,
                                                                  c->p14_s.p, c->ws, o);
         ++c->n_launches;
         MDK_CUDA(c, cudaGetLastError());
-        int h_cnt[8], h_flags[4];
+        int h_cnt[16], h_flags[4];
         MDK_CUDA(c, cudaMemcpyAsync(h_cnt, c->counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
         if (!h_flags[2]) {
-            c->stat_units = h_cnt[0]; c->stat_chunks = h_cnt[1]; c->stat_masks = h_cnt[2];
+            c->stat_units = h_cnt[0]; c->stat_chunks = h_cnt[4]; c->stat_masks = h_cnt[2];  // [4] = filled chunks
+            // hoisted minimum image (k_pair<..., SHIFT>): every listed j must have a unique image within
+            // L/2 of the block centre: R + 2 h_max <= L/2 on every axis
+            c->shift_ok = true;
+            for (int a = 0; a < 3; ++a) {
+                float hmax;
+                memcpy(&hmax, &h_cnt[8 + a], sizeof(float));
+                if (g.R + 2.f * hmax + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
+            }
             c->nlist_valid = true;
             ++c->n_rebuilds;
             return MDK_OK;

@@ -42,15 +42,25 @@ __device__ __forceinline__ float erfcx_poly(float x) {
 
 constexpr int PAIR_WARPS = 8;
 
-template <bool DO_LJ, bool DO_COUL, bool SWITCH>
+// SHIFT: the box is large enough (nlist_rebuild sets ctx->shift_ok) that every atom of a unit has a
+// unique periodic image within L/2 of the i-block centre; positions are reduced to that frame once
+// per atom (i: once per unit, j: once per chunk when it is staged) and the 32 x 32 inner loop works on
+// plain differences.  Without SHIFT the loop applies the canonical minimum image to every pair
+// (small boxes, and the criterion the pair-set hook k_enumerate reproduces bit for bit); with SHIFT
+// the same criterion is evaluated on d rounded once more (pairs within an ulp of rc may differ).
+// ONECUT: LJ and Coulomb share one cutoff, so the in-range test is done once.
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
-       long long *__restrict__ f_acc, long long *__restrict__ e_acc, int *__restrict__ cursor) {
+       const float4 *__restrict__ bbc, long long *__restrict__ f_acc, long long *__restrict__ e_acc,
+       int *__restrict__ cursor) {
     __shared__ float4 s_x[PAIR_WARPS][32];
     __shared__ float4 s_lj[PAIR_WARPS][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_units = *nl.n_units;
-    double e_lj_tot = 0.0, e_c_tot = 0.0;
+    // per-unit energies are converted to fixed point one by one: the total is then independent of
+    // which warp (or which rank) happened to evaluate which unit
+    long long e_lj_tot = 0, e_c_tot = 0;
 
     for (;;) {
         int u = 0;
@@ -59,8 +69,16 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
         if (u >= n_units) break;
         const int4 unit = nl.units[u];
         const int ia = unit.x * TILE + lane;
-        const float4 xi = xs[ia];
+        float4 xi = xs[ia];
         const float4 li = ljs[ia];
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (SHIFT) {
+            const float4 c = bbc[unit.x];
+            cx = c.x; cy = c.y; cz = c.z;
+            xi.x = min_image(xi.x - cx, P.L[0], P.invL[0]);
+            xi.y = min_image(xi.y - cy, P.L[1], P.invL[1]);
+            xi.z = min_image(xi.z - cz, P.L[2], P.invL[2]);
+        }
         float fix = 0.f, fiy = 0.f, fiz = 0.f;
         float e_lj = 0.f, e_c = 0.f;
 
@@ -73,25 +91,34 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
                 excl = nl.mask_excl[(size_t)mslot * 32 + lane];
                 if (DO_LJ) m14 = nl.mask_14[(size_t)mslot * 32 + lane];
             }
+            float4 xj_own = xs[j];
+            if (SHIFT) {
+                xj_own.x = min_image(xj_own.x - cx, P.L[0], P.invL[0]);
+                xj_own.y = min_image(xj_own.y - cy, P.L[1], P.invL[1]);
+                xj_own.z = min_image(xj_own.z - cz, P.L[2], P.invL[2]);
+            }
             __syncwarp();
-            s_x[wid][lane] = xs[j];
+            s_x[wid][lane] = xj_own;
             if (DO_LJ) s_lj[wid][lane] = ljs[j];
             __syncwarp();
             float fjx = 0.f, fjy = 0.f, fjz = 0.f;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 32; ++k) {
                 const int slot = (lane + k) & 31;
                 const float4 xj = s_x[wid][slot];
-                const float dx = min_image(xj.x - xi.x, P.L[0], P.invL[0]);
-                const float dy = min_image(xj.y - xi.y, P.L[1], P.invL[1]);
-                const float dz = min_image(xj.z - xi.z, P.L[2], P.invL[2]);
+                float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+                if (!SHIFT) {
+                    dx = min_image(dx, P.L[0], P.invL[0]);
+                    dy = min_image(dy, P.L[1], P.invL[1]);
+                    dz = min_image(dz, P.L[2], P.invL[2]);
+                }
                 const float r2 = dist2(dx, dy, dz);
                 if (r2 <= P.rc2_max && !((excl >> k) & 1u)) {
                     const float rinv = rsqrtf(r2);
                     const float r2inv = rinv * rinv;
                     float g = 0.f;  // dE/dr / r : F_i = g d, F_j = -g d  (d = x_j - x_i)
                     if (DO_LJ) {
-                        if (r2 <= P.rc2_lj) {
+                        if (ONECUT || r2 <= P.rc2_lj) {
                             const float4 lj = s_lj[wid][slot];
                             const bool is14 = (m14 >> k) & 1u;
                             const float a = is14 ? li.z * lj.z : li.x * lj.x;       // 4 eps_ij
@@ -115,7 +142,7 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
                         }
                     }
                     if (DO_COUL) {
-                        if (r2 <= P.rc2_c) {
+                        if (ONECUT || r2 <= P.rc2_c) {
                             const float qq = xi.w * xj.w;
                             const float r = r2 * rinv;
                             const float ar = P.alpha * r;
@@ -148,16 +175,16 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
             atomic_add_fix(&f_acc[3 * (size_t)ia + 1], to_fix(fiy));
             atomic_add_fix(&f_acc[3 * (size_t)ia + 2], to_fix(fiz));
         }
-        e_lj_tot += (double)e_lj;
-        e_c_tot += (double)e_c;
+        e_lj_tot += to_fix((double)e_lj);
+        e_c_tot += to_fix((double)e_c);
     }
     if (DO_LJ) {
-        double v = warp_sum(e_lj_tot);
-        if (lane == 0 && v != 0.0) atomic_add_fix(&e_acc[MDK_E_LJ], to_fix(v));
+        long long v = warp_sum_ll(e_lj_tot);
+        if (lane == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_LJ], v);
     }
     if (DO_COUL) {
-        double v = warp_sum(e_c_tot);
-        if (lane == 0 && v != 0.0) atomic_add_fix(&e_acc[MDK_E_COUL_DIRECT], to_fix(v));
+        long long v = warp_sum_ll(e_c_tot);
+        if (lane == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_COUL_DIRECT], v);
     }
 }
 
@@ -188,18 +215,24 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     NlistView nl = nlist_view(c);
     MDK_CUDA(c, cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
     const bool sw = do_lj && c->r_switch < c->rc_lj;
+    const bool shift = c->shift_ok && !c->force_canonical;
+    const bool onecut = !(do_lj && do_coul) || c->rc_lj == c->rc_coul;
     int grid = c->sm_count * 4;
     long long max_blocks = (c->stat_units + PAIR_WARPS - 1) / PAIR_WARPS;
     if (max_blocks < 1) max_blocks = 1;
     if (grid > max_blocks) grid = (int)max_blocks;
     dim3 g(grid), b(PAIR_WARPS * 32);
     int *cursor = c->counters.p + 3;
-#define LAUNCH(LJ, CO, SW)                                                                             \
-    k_pair<LJ, CO, SW><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->f_acc.p,                  \
-                                                 reinterpret_cast<long long *>(c->e_acc.p), cursor)
-    if (do_lj && do_coul) { if (sw) LAUNCH(true, true, true); else LAUNCH(true, true, false); }
-    else if (do_lj)       { if (sw) LAUNCH(true, false, true); else LAUNCH(true, false, false); }
-    else                  LAUNCH(false, true, false);
+#define LAUNCH(LJ, CO, SW, SH, OC)                                                                          \
+    k_pair<LJ, CO, SW, SH, OC><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
+                                                         c->e_acc.p, cursor)
+#define PICK_OC(LJ, CO, SW, SH) do { if (onecut) LAUNCH(LJ, CO, SW, SH, true); else LAUNCH(LJ, CO, SW, SH, false); } while (0)
+#define PICK_SH(LJ, CO, SW) do { if (shift) PICK_OC(LJ, CO, SW, true); else PICK_OC(LJ, CO, SW, false); } while (0)
+    if (do_lj && do_coul) { if (sw) PICK_SH(true, true, true); else PICK_SH(true, true, false); }
+    else if (do_lj)       { if (sw) PICK_SH(true, false, true); else PICK_SH(true, false, false); }
+    else                  PICK_SH(false, true, false);
+#undef PICK_SH
+#undef PICK_OC
 #undef LAUNCH
     c->n_launches += 1;
     c->n_pair_launches += 1;

@@ -293,14 +293,33 @@ int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
     // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units; the O(N) terms
     // run once — bonded / excluded-pair / bare Coulomb on rank 0, the PME mesh on the last rank
     const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
-    MDK_TRY(pair_compute(c, terms & MDK_TERM_LJ, terms & MDK_TERM_COUL_DIRECT));
-    if (terms & MDK_TERM_PME_RECIP) {
-        if (last) MDK_TRY(pme_compute(c));
-        if (first) MDK_TRY(pair_special(c, true));
+    // Three independent chains, all adding into the same int64 accumulators (integer atomics commute,
+    // so concurrency does not change a single bit): k_pair on the main stream, the PME mesh on s_pme,
+    // the O(N) kernels on s_aux.  Per-phase profiling (level 2) serialises them on the main stream.
+    const bool fork = c->concurrent && c->profiling < 2;
+    const bool want_pme = (terms & MDK_TERM_PME_RECIP) && last;
+    const unsigned bonded_bits = terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER);
+    const bool want_aux = first && (bonded_bits || (terms & (MDK_TERM_PME_RECIP | MDK_TERM_COUL_BARE)));
+    cudaStream_t main_stream = c->stream;
+    if (fork && (want_pme || want_aux)) MDK_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+    if (want_pme) {
+        if (fork) { MDK_CUDA(c, cudaStreamWaitEvent(c->s_pme, c->ev_fork, 0)); c->stream = c->s_pme; }
+        int rc = pme_compute(c);
+        if (fork) { cudaEventRecord(c->ev_pme, c->s_pme); c->stream = main_stream; }
+        MDK_TRY(rc);
     }
-    if ((terms & MDK_TERM_COUL_BARE) && first) MDK_TRY(coulomb_bare(c));
-    if ((terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER)) && first)
-        MDK_TRY(bonded_compute(c, terms));
+    if (want_aux) {
+        if (fork) { MDK_CUDA(c, cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); c->stream = c->s_aux; }
+        int rc = MDK_OK;
+        if (terms & MDK_TERM_PME_RECIP) rc = pair_special(c, true);
+        if (rc == MDK_OK && (terms & MDK_TERM_COUL_BARE)) rc = coulomb_bare(c);
+        if (rc == MDK_OK && bonded_bits) rc = bonded_compute(c, terms);
+        if (fork) { cudaEventRecord(c->ev_aux, c->s_aux); c->stream = main_stream; }
+        MDK_TRY(rc);
+    }
+    MDK_TRY(pair_compute(c, terms & MDK_TERM_LJ, terms & MDK_TERM_COUL_DIRECT));
+    if (fork && want_pme) MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_pme, 0));
+    if (fork && want_aux) MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));
     MDK_TRY(comm_allreduce_forces(c));
     if (sync_energies) {
         MDK_TRY(comm_allreduce_energies(c));

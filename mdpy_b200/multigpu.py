@@ -82,9 +82,20 @@ def broadcast_unique_id(dist, dev, rank):
 
 def attach(ctx, dist, rank, world, weights=None):
     """Join this rank's device context to the job: communicator + i-block shard."""
+    import os
+    import sys
     dev = ctx.dev
     uid = broadcast_unique_id(dist, dev, rank)
-    dev.comm_init(rank, world, uid)
+    # NCCL may print its version banner on stdout at the first communicator; keep stdout clean for
+    # callers that emit machine-readable output there (bench.py's single JSON line)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        dev.comm_init(rank, world, uid)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     set_weights(ctx, rank, world, np.ones(world) if weights is None else weights)
 
 

@@ -167,6 +167,10 @@ MDK_API int mdk_set_profiling(mdk_ctx *ctx, int level);
 /* Raw device pointer + element count of the int64 fixed-point force accumulator in
  * tile order (multi-GPU reduction by the host layer; scale = 2^40). */
 MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64);
+/* Execution options: key 0 = CUDA-graph integrator steps (default 1), 1 = PME / bonded kernels on side
+ * streams beside the pair kernel (default 1), 2 = always apply the canonical minimum image per pair
+ * (default 0: hoisted out of the pair loop when the box allows it). */
+MDK_API int mdk_set_option(mdk_ctx *ctx, int key, double value);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);
 /* Restrict the i-blocks whose work units this ctx builds and evaluates to those with

@@ -40,7 +40,7 @@ EXPORTS = [
     'mdk_download_positions_f64', 'mdk_download_velocities', 'mdk_build_nlist', 'mdk_compute',
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
-    'mdk_set_shard', 'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init',
+    'mdk_set_shard', 'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def load_library():
         'mdk_comm_unique_id': (i32, [vp]),
         'mdk_comm_init': (i32, [vp, i32, i32, vp]),
         'mdk_flush_l2': (i32, [vp]),
+        'mdk_set_option': (i32, [vp, i32, f64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -281,6 +282,11 @@ class Device:
         """0 off, 1 whole-call CUDA events (total_ms), 2 per-phase events (adds stream syncs)."""
         self._ck(self._lib.mdk_set_profiling(self._h, int(level)))
 
+    def set_option(self, key, value):
+        """key: 'graph' | 'concurrent' | 'canonical_min_image'."""
+        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2}[key]
+        self._ck(self._lib.mdk_set_option(self._h, k, float(value)))
+
     def flush_l2(self):
         self._ck(self._lib.mdk_flush_l2(self._h))
 
@@ -347,9 +353,14 @@ class EnsembleContext:
         e = self.compute(terms)
         forces = self.dev.forces(np.float64)
         total = 0.0
+        zeros = getattr(self, '_zeros', None)
+        if zeros is None or zeros.shape != forces.shape:
+            zeros = self._zeros = np.zeros(forces.shape, dtype=env.NUMPY_FLOAT)
+            zeros.setflags(write=False)
         for k, c in enumerate(constraints):
             c._potential_energy = c._energy_from(e)
-            c._forces = forces.astype(env.NUMPY_FLOAT) if k == 0 else np.zeros_like(forces, dtype=env.NUMPY_FLOAT)
+            # one shared accumulator: the sum lives on the first constraint, the others report zero
+            c._forces = forces if k == 0 else zeros
             total += c._potential_energy
         return forces, total
 

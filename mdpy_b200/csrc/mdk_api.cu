@@ -19,7 +19,7 @@ int fail(mdk_ctx *c, int code, const char *fmt, ...) {
     return code;
 }
 
-static void invalidate(mdk_ctx *c) { c->nlist_valid = false; }
+static void invalidate(mdk_ctx *c) { c->nlist_valid = false; c->xs_current = false; ++c->graph_epoch; }
 
 __global__ void k_f32_to_f64(size_t n, const float *__restrict__ in, double *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,22 +58,39 @@ __global__ void k_f64_to_f32(size_t n, const double *__restrict__ in, float *__r
 
 using namespace mdk;
 
+// Persistent staging for host transfers: a device scratch buffer plus a pinned host mirror, grown
+// on demand — no cudaMalloc / cudaFree (implicit device syncs) on the per-step drop-in path.
+static int stage_reserve(mdk_ctx *c, size_t bytes) {
+    MDK_CUDA(c, c->io_dev.reserve(bytes));
+    if (bytes > c->io_host_cap) {
+        if (c->io_host) cudaFreeHost(c->io_host);
+        c->io_host = nullptr; c->io_host_cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        MDK_CUDA(c, cudaHostAlloc(&c->io_host, want, cudaHostAllocDefault));
+        c->io_host_cap = want;
+    }
+    return MDK_OK;
+}
+// device scratch -> caller's buffer through the pinned mirror
+static int stage_download(mdk_ctx *c, void *out, size_t bytes) {
+    MDK_CUDA(c, cudaMemcpyAsync(c->io_host, c->io_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(out, c->io_host, bytes);
+    return MDK_OK;
+}
+
 #define NEED_CTX(c) \
     if (!(c)) return MDK_ERR_BAD_ARG
 
 template <typename T>
 static int download_forces(mdk_ctx *c, T *out) {
     if (!c->nlist_valid || !out) return fail(c, MDK_ERR_NOT_BOUND, "mdk_download_forces before mdk_compute");
-    T *tmp = nullptr;
     size_t m = (size_t)3 * c->n;
-    MDK_CUDA(c, cudaMalloc(&tmp, m * sizeof(T)));
-    k_unpermute_forces<T><<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->order.p, c->f_acc.p, tmp);
+    MDK_TRY(stage_reserve(c, m * sizeof(T)));
+    k_unpermute_forces<T><<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->order.p, c->f_acc.p,
+                                                                      reinterpret_cast<T *>(c->io_dev.p));
     ++c->n_launches;
-    cudaError_t e = cudaMemcpyAsync(out, tmp, m * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(tmp);
-    MDK_CUDA(c, e);
-    return MDK_OK;
+    return stage_download(c, out, m * sizeof(T));
 }
 
 extern "C" {
@@ -125,6 +142,7 @@ void mdk_destroy(mdk_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     comm_destroy(c);
+    graph_destroy(c);
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
     c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release();
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
@@ -132,10 +150,12 @@ void mdk_destroy(mdk_ctx *c) {
     c->order.release(); c->inv_order.release(); c->xs.release(); c->xs_ref.release(); c->ljs.release();
     c->excl_s.release(); c->p14_s.release(); c->f_acc.release(); c->e_acc.release(); c->flags.release();
     c->cell_key.release(); c->cell_key_sorted.release(); c->idx_tmp.release(); c->cell_start.release();
-    c->sort_tmp.release(); c->bb_center.release(); c->bb_half.release();
+    c->sort_tmp.release(); c->sort_buf.release(); c->bb_center.release(); c->bb_half.release();
     c->units.release(); c->chunk_j.release(); c->chunk_mask.release(); c->mask_excl.release(); c->mask_14.release();
     c->counters.release();
     c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release();
+    c->io_dev.release();
+    if (c->io_host) cudaFreeHost(c->io_host);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_pme) cudaEventDestroy(c->ev_pme);
@@ -296,13 +316,15 @@ int mdk_upload_positions(mdk_ctx *c, const float *xyz) {
     if (!xyz) return fail(c, MDK_ERR_BAD_ARG, "xyz is NULL");
     MDK_TRY(check_lost(c, nullptr, xyz));
     size_t m = (size_t)3 * c->n;
-    MDK_CUDA(c, c->x_prev.reserve(m));  // staging (also the Verlet history buffer; cache is reset below)
-    float *stage = reinterpret_cast<float *>(c->x_prev.p);
-    MDK_CUDA(c, cudaMemcpyAsync(stage, xyz, m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    MDK_TRY(stage_reserve(c, m * sizeof(float)));
+    memcpy(c->io_host, xyz, m * sizeof(float));
+    float *stage = reinterpret_cast<float *>(c->io_dev.p);
+    MDK_CUDA(c, cudaMemcpyAsync(stage, c->io_host, m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     k_f32_to_f64<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, stage, c->x_cur.p);
     ++c->n_launches;
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_pos = true;
+    c->xs_current = false;
     c->verlet_cached = false; c->langevin_cached = false;
     return MDK_OK;
 }
@@ -315,6 +337,7 @@ int mdk_upload_positions_f64(mdk_ctx *c, const double *xyz) {
     MDK_CUDA(c, cudaMemcpyAsync(c->x_cur.p, xyz, (size_t)3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_pos = true;
+    c->xs_current = false;
     c->verlet_cached = false; c->langevin_cached = false;
     return MDK_OK;
 }
@@ -337,16 +360,12 @@ int mdk_upload_velocities(mdk_ctx *c, const float *v) {
 int mdk_download_positions(mdk_ctx *c, float *out) {
     NEED_CTX(c);
     if (!c->have_pos || !out) return fail(c, MDK_ERR_NOT_BOUND, "no positions on the device");
-    float *tmp = nullptr;
     size_t m = (size_t)3 * c->n;
-    MDK_CUDA(c, cudaMalloc(&tmp, m * sizeof(float)));
-    k_wrapped_positions<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->x_cur.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], tmp);
+    MDK_TRY(stage_reserve(c, m * sizeof(float)));
+    k_wrapped_positions<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->x_cur.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2],
+                                                                    reinterpret_cast<float *>(c->io_dev.p));
     ++c->n_launches;
-    cudaError_t e = cudaMemcpyAsync(out, tmp, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(tmp);
-    MDK_CUDA(c, e);
-    return MDK_OK;
+    return stage_download(c, out, m * sizeof(float));
 }
 
 int mdk_download_positions_f64(mdk_ctx *c, double *out) {
@@ -360,16 +379,11 @@ int mdk_download_positions_f64(mdk_ctx *c, double *out) {
 int mdk_download_velocities(mdk_ctx *c, float *out) {
     NEED_CTX(c);
     if (c->n <= 0 || !out) return fail(c, MDK_ERR_NOT_BOUND, "no velocities on the device");
-    float *tmp = nullptr;
     size_t m = (size_t)3 * c->n;
-    MDK_CUDA(c, cudaMalloc(&tmp, m * sizeof(float)));
-    k_f64_to_f32<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, c->vel.p, tmp);
+    MDK_TRY(stage_reserve(c, m * sizeof(float)));
+    k_f64_to_f32<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, c->vel.p, reinterpret_cast<float *>(c->io_dev.p));
     ++c->n_launches;
-    cudaError_t e = cudaMemcpyAsync(out, tmp, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(tmp);
-    MDK_CUDA(c, e);
-    return MDK_OK;
+    return stage_download(c, out, m * sizeof(float));
 }
 
 // ---- hot path ----
@@ -479,6 +493,18 @@ int mdk_force_accumulator(mdk_ctx *c, void **dev_ptr, int64_t *n_int64) {
     if (!dev_ptr || !n_int64) return fail(c, MDK_ERR_BAD_ARG, "NULL output");
     *dev_ptr = c->f_acc.p;
     *n_int64 = (int64_t)c->n_pad * 3;
+    return MDK_OK;
+}
+
+int mdk_set_option(mdk_ctx *c, int key, double value) {
+    NEED_CTX(c);
+    switch (key) {
+        case 0: c->use_graph = value != 0; break;          // CUDA-graph steps in the integrators
+        case 1: c->concurrent = value != 0; break;         // PME / bonded on side streams
+        case 2: c->force_canonical = value != 0; break;    // per-pair canonical minimum image even in large boxes
+        default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
+    }
+    ++c->graph_epoch;
     return MDK_OK;
 }
 

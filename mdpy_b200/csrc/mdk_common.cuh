@@ -115,7 +115,13 @@ struct mdk_ctx {
     mdk::DevBuf<unsigned> cell_key, cell_key_sorted;
     mdk::DevBuf<int> idx_tmp;
     mdk::DevBuf<int> cell_start;              // [ncells + 1]
-    mdk::DevBuf<unsigned char> sort_tmp;
+    mdk::DevBuf<unsigned char> sort_tmp;      // scratch (L2 flush)
+    mdk::DevBuf<unsigned char> sort_buf;      // CUB radix sort temporary storage
+    size_t sort_tmp_bytes = 0;
+    int sort_end_bit = 1;
+    long long n_cells = 0;
+    int n_parts = 1;
+    bool graph_pools = false;                 // size the list pools for rebuilds that run inside a CUDA graph
     mdk::DevBuf<float4> bb_center, bb_half;   // [n_blocks]
     // tile list pools
     mdk::DevBuf<int4> units;
@@ -143,6 +149,21 @@ struct mdk_ctx {
     cufftHandle plan_r2c = 0, plan_c2r = 0;
     bool have_plans = false;
     double e_self_bg = 0.0;
+
+    // ---- CUDA-graph step ----
+    bool use_graph = true, in_capture = false;
+    bool xs_current = false;                  // tile-order positions already match x_cur (integrator just published them)
+    cudaGraph_t step_graph = nullptr;
+    cudaGraphExec_t step_exec = nullptr;
+    mdk::DevBuf<unsigned long long> step_dev;
+    double graph_key[8] = {0};
+    long long graph_epoch = 0, graph_epoch_built = -1;
+    int graph_launches_per_step = 0;
+
+    // ---- host transfer staging ----
+    mdk::DevBuf<unsigned char> io_dev;
+    void *io_host = nullptr;
+    size_t io_host_cap = 0;
 
     // ---- bookkeeping ----
     double last_e[MDK_NUM_ENERGIES] = {0};
@@ -188,6 +209,7 @@ struct PhaseTimer {
 // translation-unit entry points
 int nlist_refresh_sorted(mdk_ctx *c);          // xs <- wrap(x_cur) in tile order + displacement check
 int nlist_rebuild(mdk_ctx *c);
+int nlist_enqueue(mdk_ctx *c, bool in_graph);  // device work of a rebuild only (capturable)
 int nlist_ensure(mdk_ctx *c);                  // rebuild if flagged / invalid
 NlistView nlist_view(mdk_ctx *c);
 int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul);
@@ -200,6 +222,8 @@ int bonded_compute(mdk_ctx *c, unsigned terms);
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms);
 int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);
+int forces_enqueue(mdk_ctx *c, unsigned terms);
+void graph_destroy(mdk_ctx *c);
 int comm_allreduce_forces(mdk_ctx *c);
 int comm_allreduce_energies(mdk_ctx *c);
 void comm_destroy(mdk_ctx *c);

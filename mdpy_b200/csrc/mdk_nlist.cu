@@ -418,11 +418,12 @@ NlistView nlist_view(mdk_ctx *c) {
     return v;
 }
 
-int nlist_rebuild(mdk_ctx *c) {
+// ---- rebuild = plan (host) + enqueue (device work only) ------------------------------------
+// plan: cell geometry, work-unit granularity and pool capacities from the box and the density.
+static int nlist_plan(mdk_ctx *c) {
     if (!c->have_box || c->n <= 0 || !c->have_pos)
         return fail(c, MDK_ERR_NOT_BOUND, "neighbour list needs box, atoms and positions");
     MDK_TRY(check_cutoff(c));
-    PhaseTimer pt(c, PH_NLIST);
     const int n = c->n;
     c->n_blocks = (n + TILE - 1) / TILE;
     c->n_pad = c->n_blocks * TILE;
@@ -445,8 +446,25 @@ int nlist_rebuild(mdk_ctx *c) {
         c->cellw[a] = (float)(c->box.Ld[a] / nc);
         ncells *= nc;
     }
-    GridParams g = make_grid_params(c);
-    double3 Ld = make_double3(c->box.Ld[0], c->box.Ld[1], c->box.Ld[2]);
+    c->n_cells = ncells;
+    c->n_parts = (int)((4096 + c->n_blocks - 1) / c->n_blocks);
+    if (c->n_parts < 1) c->n_parts = 1;
+    if (c->n_parts > 8) c->n_parts = 8;
+    // work-unit granularity: enough units to fill the machine a few times over
+    double per_block = rho * (4.0 / 3.0) * M_PI * R * R * R * 0.5 * 2.2 / 32.0 + 1.0;  // chunks (estimate)
+    double total_chunks = per_block * c->n_blocks;
+    double want_units = 8.0 * c->sm_count * 8;  // ~8 resident warps per SM, 8 waves
+    int seg = (int)(total_chunks / want_units);
+    if (seg < 2) seg = 2;
+    if (seg > 16) seg = 16;
+    c->seg_chunks = seg;
+    const double slack = c->graph_pools ? 2.0 : 1.3;  // rebuilds inside a CUDA graph cannot grow the pools
+    size_t est_chunks = (size_t)(total_chunks * slack) + (size_t)c->n_blocks * c->n_parts * (seg + 1) + 1024;
+    if (c->cap_chunks < est_chunks) c->cap_chunks = est_chunks;
+    size_t est_units = est_chunks / seg + (size_t)c->n_blocks * (c->n_parts + 1) + 1024;
+    if (c->cap_units < est_units) c->cap_units = est_units;
+    size_t est_masks = (size_t)c->n_blocks * (c->graph_pools ? 24 : 12) + 1024;
+    if (c->cap_masks < est_masks) c->cap_masks = est_masks;
 
     MDK_CUDA(c, c->cell_key.reserve(n)); MDK_CUDA(c, c->cell_key_sorted.reserve(n));
     MDK_CUDA(c, c->idx_tmp.reserve(n)); MDK_CUDA(c, c->order.reserve(n));
@@ -456,17 +474,57 @@ int nlist_rebuild(mdk_ctx *c) {
     MDK_CUDA(c, c->bb_center.reserve(c->n_blocks)); MDK_CUDA(c, c->bb_half.reserve(c->n_blocks));
     MDK_CUDA(c, c->excl_s.reserve((size_t)n * (c->wb > 0 ? c->wb : 1)));
     MDK_CUDA(c, c->p14_s.reserve((size_t)n * (c->ws > 0 ? c->ws : 1)));
-
-    const int T = 256;
-    k_cell_keys<<<(n + T - 1) / T, T, 0, c->stream>>>(n, c->x_cur.p, g, Ld, c->cell_key.p, c->idx_tmp.p);
-    int end_bit = 1;
-    while ((1ll << end_bit) < ncells) ++end_bit;
+    c->sort_end_bit = 1;
+    while ((1ll << c->sort_end_bit) < ncells) ++c->sort_end_bit;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->cell_key.p, c->cell_key_sorted.p, c->idx_tmp.p,
-                                    c->order.p, n, 0, end_bit, c->stream);
-    MDK_CUDA(c, c->sort_tmp.reserve(tmp_bytes));
-    MDK_CUDA(c, cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp_bytes, c->cell_key.p, c->cell_key_sorted.p,
-                                                c->idx_tmp.p, c->order.p, n, 0, end_bit, c->stream));
+                                    c->order.p, n, 0, c->sort_end_bit, c->stream);
+    c->sort_tmp_bytes = tmp_bytes;
+    {
+        const void *p0 = c->sort_buf.p, *p1 = c->xs.p, *p2 = c->cell_start.p;
+        MDK_CUDA(c, c->sort_buf.reserve(tmp_bytes));
+        if (p0 != c->sort_buf.p || p1 != c->xs.p || p2 != c->cell_start.p) ++c->graph_epoch;
+    }
+    return MDK_OK;
+}
+
+static int nlist_reserve_pools(mdk_ctx *c) {
+    const void *before[3] = {c->units.p, c->chunk_j.p, c->mask_excl.p};
+    MDK_CUDA(c, c->units.reserve(c->cap_units));
+    MDK_CUDA(c, c->chunk_j.reserve(c->cap_chunks * 32));
+    MDK_CUDA(c, c->chunk_mask.reserve(c->cap_chunks));
+    MDK_CUDA(c, c->mask_excl.reserve(c->cap_masks * 32));
+    MDK_CUDA(c, c->mask_14.reserve(c->cap_masks * 32));
+    if (before[0] != c->units.p || before[1] != c->chunk_j.p || before[2] != c->mask_excl.p)
+        ++c->graph_epoch;   // a captured step graph holds the old pool addresses
+    return MDK_OK;
+}
+
+// Bookkeeping at the end of a rebuild that runs inside a CUDA graph (no host in the loop):
+// sticky error bits in flags[3] (1 = pool overflow, 2 = a block outgrew the hoisted-minimum-image
+// bound), rebuild counter and list sizes in counters[12..15].
+__global__ void k_after_build(int *counters, int *flags, float lim_x, float lim_y, float lim_z, int check_shift) {
+    if (flags[2]) flags[3] |= 1;
+    if (check_shift) {
+        if (__int_as_float(counters[8]) > lim_x || __int_as_float(counters[9]) > lim_y ||
+            __int_as_float(counters[10]) > lim_z)
+            flags[3] |= 2;
+    }
+    counters[12] += 1;
+    counters[13] = counters[0]; counters[14] = counters[4]; counters[15] = counters[2];
+}
+
+// enqueue: every kernel of a rebuild on c->stream, fixed launch shapes, no host synchronisation
+// (usable inside stream capture).
+int nlist_enqueue(mdk_ctx *c, bool in_graph) {
+    const int n = c->n, T = 256;
+    GridParams g = make_grid_params(c);
+    double3 Ld = make_double3(c->box.Ld[0], c->box.Ld[1], c->box.Ld[2]);
+    const long long ncells = c->n_cells;
+    k_cell_keys<<<(n + T - 1) / T, T, 0, c->stream>>>(n, c->x_cur.p, g, Ld, c->cell_key.p, c->idx_tmp.p);
+    size_t tmp_bytes = c->sort_tmp_bytes;
+    MDK_CUDA(c, cub::DeviceRadixSort::SortPairs(c->sort_buf.p, tmp_bytes, c->cell_key.p, c->cell_key_sorted.p,
+                                                c->idx_tmp.p, c->order.p, n, 0, c->sort_end_bit, c->stream));
     k_cell_start<<<(int)((ncells + 1 + T - 1) / T), T, 0, c->stream>>>(n, (int)ncells, c->cell_key_sorted.p,
                                                                        c->cell_start.p);
     float sqrt_ke = c->have_coul ? (float)sqrt(c->k_e) : 0.f;
@@ -479,53 +537,39 @@ int nlist_rebuild(mdk_ctx *c) {
     if (c->ws > 0)
         k_tables_sorted<<<(n * c->ws + T - 1) / T, T, 0, c->stream>>>(n, c->order.p, c->inv_order.p, c->p14.p,
                                                                       c->ws, c->p14_s.p);
-    MDK_CUDA(c, cudaMemsetAsync(c->counters.p + 8, 0, 4 * sizeof(int), c->stream));
+    MDK_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 12 * sizeof(int), c->stream));
+    MDK_CUDA(c, cudaMemsetAsync(c->flags.p + 1, 0, 2 * sizeof(int), c->stream));
     k_block_bbox<<<(c->n_blocks * 32 + T - 1) / T, T, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p,
                                                                     c->counters.p + 8);
-    c->n_launches += 7;
-    MDK_CUDA(c, cudaGetLastError());
-
-    // work-unit granularity: enough units to fill the machine a few times over
-    {
-        double per_block = rho * (4.0 / 3.0) * M_PI * R * R * R * 0.5 * 2.2 / 32.0 + 1.0;  // chunks (estimate)
-        double total_chunks = per_block * c->n_blocks;
-        double want_units = 8.0 * c->sm_count * 8;  // ~8 resident warps per SM, 8 waves
-        int seg = (int)(total_chunks / want_units);
-        if (seg < 2) seg = 2;
-        if (seg > 16) seg = 16;
-        c->seg_chunks = seg;
-        size_t est_chunks = (size_t)(total_chunks * 1.3) + (size_t)c->n_blocks * 8 * (seg + 1) + 1024;  // <= 8 parts per block
-        if (c->cap_chunks < est_chunks) c->cap_chunks = est_chunks;
-        size_t est_units = est_chunks / seg + (size_t)c->n_blocks * 9 + 1024;
-        if (c->cap_units < est_units) c->cap_units = est_units;
-        size_t est_masks = (size_t)c->n_blocks * 8 + 1024;
-        if (c->cap_masks < est_masks) c->cap_masks = est_masks;
+    BuildOut o;
+    o.units = c->units.p; o.chunk_j = c->chunk_j.p; o.chunk_mask = c->chunk_mask.p;
+    o.mask_excl = c->mask_excl.p; o.mask_14 = c->mask_14.p;
+    o.counters = c->counters.p; o.flags = c->flags.p;
+    o.cap_units = (int)c->cap_units; o.cap_chunks = (int)c->cap_chunks; o.cap_masks = (int)c->cap_masks;
+    o.seg = c->seg_chunks;
+    int blocks = (c->n_blocks * c->n_parts + BUILD_WARPS - 1) / BUILD_WARPS;
+    int max_blocks = c->sm_count * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    k_build_lists<<<blocks, BUILD_WARPS * 32, 0, c->stream>>>(g, c->n_parts, c->xs.p, c->bb_center.p, c->bb_half.p,
+                                                             c->cell_start.p, c->excl_s.p, c->wb, c->p14_s.p,
+                                                             c->ws, o);
+    if (in_graph) {
+        float lim[3];
+        for (int a = 0; a < 3; ++a) lim[a] = 0.5f * (0.5f * c->box.L[a] - g.R - 0.05f);
+        k_after_build<<<1, 1, 0, c->stream>>>(c->counters.p, c->flags.p, lim[0], lim[1], lim[2], c->shift_ok ? 1 : 0);
     }
+    c->n_launches += in_graph ? 0 : 9;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+int nlist_rebuild(mdk_ctx *c) {
+    MDK_TRY(nlist_plan(c));
+    PhaseTimer pt(c, PH_NLIST);
+    GridParams g = make_grid_params(c);
     for (int attempt = 0; attempt < 6; ++attempt) {
-        MDK_CUDA(c, c->units.reserve(c->cap_units));
-        MDK_CUDA(c, c->chunk_j.reserve(c->cap_chunks * 32));
-        MDK_CUDA(c, c->chunk_mask.reserve(c->cap_chunks));
-        MDK_CUDA(c, c->mask_excl.reserve(c->cap_masks * 32));
-        MDK_CUDA(c, c->mask_14.reserve(c->cap_masks * 32));
-        MDK_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(int), c->stream));
-        MDK_CUDA(c, cudaMemsetAsync(c->flags.p + 1, 0, 2 * sizeof(int), c->stream));
-        BuildOut o;
-        o.units = c->units.p; o.chunk_j = c->chunk_j.p; o.chunk_mask = c->chunk_mask.p;
-        o.mask_excl = c->mask_excl.p; o.mask_14 = c->mask_14.p;
-        o.counters = c->counters.p; o.flags = c->flags.p;
-        o.cap_units = (int)c->cap_units; o.cap_chunks = (int)c->cap_chunks; o.cap_masks = (int)c->cap_masks;
-        o.seg = c->seg_chunks;
-        int n_parts = (int)((4096 + c->n_blocks - 1) / c->n_blocks);
-        if (n_parts < 1) n_parts = 1;
-        if (n_parts > 8) n_parts = 8;
-        int blocks = (c->n_blocks * n_parts + BUILD_WARPS - 1) / BUILD_WARPS;
-        int max_blocks = c->sm_count * 16;
-        if (blocks > max_blocks) blocks = max_blocks;
-        k_build_lists<<<blocks, BUILD_WARPS * 32, 0, c->stream>>>(g, n_parts, c->xs.p, c->bb_center.p, c->bb_half.p,
-                                                                 c->cell_start.p, c->excl_s.p, c->wb,
-                                                                 c->p14_s.p, c->ws, o);
-        ++c->n_launches;
-        MDK_CUDA(c, cudaGetLastError());
+        MDK_TRY(nlist_reserve_pools(c));
+        MDK_TRY(nlist_enqueue(c, false));
         int h_cnt[16], h_flags[4];
         MDK_CUDA(c, cudaMemcpyAsync(h_cnt, c->counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
@@ -533,12 +577,13 @@ int nlist_rebuild(mdk_ctx *c) {
         if (!h_flags[2]) {
             c->stat_units = h_cnt[0]; c->stat_chunks = h_cnt[4]; c->stat_masks = h_cnt[2];  // [4] = filled chunks
             // hoisted minimum image (k_pair<..., SHIFT>): every listed j must have a unique image within
-            // L/2 of the block centre: R + 2 h_max <= L/2 on every axis
+            // L/2 of the block centre: R + 2 h_max <= L/2 on every axis (1 A spare when later rebuilds
+            // will run inside a graph and cannot switch kernels)
             c->shift_ok = true;
             for (int a = 0; a < 3; ++a) {
                 float hmax;
                 memcpy(&hmax, &h_cnt[8 + a], sizeof(float));
-                if (g.R + 2.f * hmax + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
+                if (g.R + 2.f * (hmax + (c->graph_pools ? 1.0f : 0.f)) + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
             }
             c->nlist_valid = true;
             ++c->n_rebuilds;

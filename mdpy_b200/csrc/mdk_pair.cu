@@ -220,7 +220,7 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     int grid = c->sm_count * 4;
     long long max_blocks = (c->stat_units + PAIR_WARPS - 1) / PAIR_WARPS;
     if (max_blocks < 1) max_blocks = 1;
-    if (grid > max_blocks) grid = (int)max_blocks;
+    if (grid > max_blocks && !c->in_capture) grid = (int)max_blocks;   // a captured launch must fit any later list
     dim3 g(grid), b(PAIR_WARPS * 32);
     int *cursor = c->counters.p + 3;
 #define LAUNCH(LJ, CO, SW, SH, OC)                                                                          \

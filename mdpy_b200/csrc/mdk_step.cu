@@ -283,11 +283,9 @@ int bonded_compute(mdk_ctx *c, unsigned terms) {
 
 // ===========================================================================
 // term dispatcher
-int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
-    if (!c->have_box || c->n <= 0 || !c->have_pos)
-        return fail(c, MDK_ERR_NOT_BOUND, "mdk_compute before box/atoms/positions were set");
-    MDK_TRY(nlist_refresh_sorted(c));
-    MDK_TRY(nlist_ensure(c));
+// Device work of one force evaluation on a valid tile list: enqueue only, no host synchronisation,
+// fixed launch shapes (this is what a CUDA-graph step captures).
+int forces_enqueue(mdk_ctx *c, unsigned terms) {
     MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
     MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
     // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units; the O(N) terms
@@ -321,6 +319,16 @@ int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
     if (fork && want_pme) MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_pme, 0));
     if (fork && want_aux) MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));
     MDK_TRY(comm_allreduce_forces(c));
+    return MDK_OK;
+}
+
+int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
+    if (!c->have_box || c->n <= 0 || !c->have_pos)
+        return fail(c, MDK_ERR_NOT_BOUND, "mdk_compute before box/atoms/positions were set");
+    if (!c->xs_current) MDK_TRY(nlist_refresh_sorted(c));
+    MDK_TRY(nlist_ensure(c));
+    c->xs_current = true;
+    MDK_TRY(forces_enqueue(c, terms));
     if (sync_energies) {
         MDK_TRY(comm_allreduce_energies(c));
         long long h[MDK_NUM_ENERGIES];
@@ -431,13 +439,15 @@ __global__ void k_verlet_velocity(int n, int quirks, double dt, const int *__res
 // mode bit 1 (ADVANCE): move x one step with noise index `step` using the newest force.
 // mode bit 2 (FROM_PREV): the newest force is f_prev (start of a call on a cached state).
 __global__ void k_langevin(int n, int mode, double dt, double ca, double cb, double two_g_kT_dt,
-                           uint64_t seed, uint64_t step, const int *__restrict__ order,
+                           uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_dev,
+                           const int *__restrict__ order,
                            const float *__restrict__ mass, const long long *__restrict__ f_acc,
                            double *__restrict__ x_cur, double *__restrict__ vel, double *__restrict__ f_prev,
                            StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
                            int *__restrict__ flags) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    if (step_dev) step = *step_dev;   // graph steps keep the noise counter on the device
     int a = order[k];
     double m = (double)mass[a], inv_m = 1.0 / m;
     double bs = sqrt(two_g_kT_dt * m);
@@ -529,6 +539,133 @@ int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quir
     return fetch_energies(c, terms);
 }
 
+// ===========================================================================
+// CUDA-graph step.  At 23 k atoms a step is ~25 kernels of 3-60 us: issuing them one by one, with a
+// host round trip per step to learn whether the list must be rebuilt, costs more than executing
+// them.  The steady-state Langevin step is therefore captured once into a graph whose rebuild
+// branch is a conditional (IF) node driven from the device: k_decide reads the skin/2 flag the
+// previous step's position update raised and arms the branch; its body is the whole list rebuild.
+__global__ void k_decide(cudaGraphConditionalHandle handle, const int *__restrict__ flags) {
+    cudaGraphSetConditional(handle, flags[1] != 0 ? 1u : 0u);
+}
+__global__ void k_tick(unsigned long long *step_dev) { *step_dev += 1ull; }
+
+void graph_destroy(mdk_ctx *c) {
+    if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
+    if (c->step_graph) cudaGraphDestroy(c->step_graph);
+    c->step_exec = nullptr; c->step_graph = nullptr;
+}
+
+static int graph_build_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed,
+                                unsigned terms) {
+    graph_destroy(c);
+    const int n = c->n, T = 256, B = (n + T - 1) / T;
+    StepGeom g = make_geom(c);
+    cudaStream_t s = c->stream;
+    if (terms & MDK_TERM_PME_RECIP) MDK_TRY(pme_prepare(c));
+    MDK_CUDA(c, c->step_dev.reserve(2));
+    c->in_capture = true;
+    const int64_t launches_before = c->n_launches, pair_before = c->n_pair_launches;
+    int rc = MDK_OK;
+    cudaGraph_t graph = nullptr;
+#define CAP(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess && rc == MDK_OK)                                                            \
+            rc = fail(c, MDK_ERR_CUDA, "%s failed while capturing the step graph: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+    CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    if (rc == MDK_OK) {
+        cudaStreamCaptureStatus status;
+        unsigned long long id = 0;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
+        cudaGraphConditionalHandle handle;
+        CAP(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+        k_decide<<<1, 1, 0, s>>>(handle, c->flags.p);
+        CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cond = nullptr;
+        CAP(cudaGraphAddNode(&cond, graph, deps, ndeps, &cp));
+        if (rc == MDK_OK) {
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            // the rebuild, captured into the branch body on a side stream
+            CAP(cudaStreamBeginCaptureToGraph(c->s_aux, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+            if (rc == MDK_OK) {
+                c->stream = c->s_aux;
+                int r2 = nlist_enqueue(c, true);
+                c->stream = s;
+                cudaGraph_t dummy = nullptr;
+                CAP(cudaStreamEndCapture(c->s_aux, &dummy));
+                if (r2 != MDK_OK && rc == MDK_OK) rc = r2;
+            }
+            CAP(cudaStreamUpdateCaptureDependencies(s, &cond, 1, cudaStreamSetCaptureDependencies));
+        }
+        if (rc == MDK_OK) rc = forces_enqueue(c, terms);
+        if (rc == MDK_OK) {
+            k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->order.p, c->mass.p, c->f_acc.p,
+                                       c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
+            k_tick<<<1, 1, 0, s>>>(c->step_dev.p);
+        }
+        cudaGraph_t done = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s, &done);
+        if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        graph = done;
+    }
+#undef CAP
+    c->in_capture = false;
+    c->stream = s;
+    c->graph_launches_per_step = (int)(c->n_launches - launches_before) + 4;   // + decide, langevin, tick, cursor
+    c->n_launches = launches_before; c->n_pair_launches = pair_before;         // capturing is not launching
+    if (rc != MDK_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    c->step_graph = graph;
+    cudaError_t e = cudaGraphInstantiate(&c->step_exec, graph, 0);
+    if (e != cudaSuccess) { graph_destroy(c); return fail(c, MDK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+    c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_key[2] = (double)seed; c->graph_key[3] = (double)terms;
+    c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
+    return MDK_OK;
+}
+
+// n steady-state steps (finish v of the pending step, advance x) as graph launches
+static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed, unsigned terms,
+                              int nsteps) {
+    if (!c->graph_pools) {           // first use: re-plan the pools with graph slack, on the host
+        c->graph_pools = true;
+        c->nlist_valid = false;
+        ++c->graph_epoch;
+    }
+    if (!c->xs_current) MDK_TRY(nlist_refresh_sorted(c));
+    MDK_TRY(nlist_ensure(c));
+    c->xs_current = true;
+    const bool stale = !c->step_exec || c->graph_epoch_built != c->graph_epoch || c->graph_key[0] != dt ||
+                       c->graph_key[1] != tg || c->graph_key[2] != (double)seed || c->graph_key[3] != (double)terms ||
+                       c->graph_key[4] != ca;
+    if (stale) MDK_TRY(graph_build_langevin(c, dt, ca, cb, tg, seed, terms));
+    unsigned long long h_step = c->langevin_step;
+    MDK_CUDA(c, cudaMemcpyAsync(c->step_dev.p, &h_step, sizeof(h_step), cudaMemcpyHostToDevice, c->stream));
+    int h_before[16];
+    MDK_CUDA(c, cudaMemcpyAsync(h_before, c->counters.p, sizeof(h_before), cudaMemcpyDeviceToHost, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < nsteps; ++s) MDK_CUDA(c, cudaGraphLaunch(c->step_exec, c->stream));
+    int h_after[16], h_flags[4];
+    MDK_CUDA(c, cudaMemcpyAsync(h_after, c->counters.p, sizeof(h_after), cudaMemcpyDeviceToHost, c->stream));
+    MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->langevin_step += (uint64_t)nsteps;
+    const int rebuilt = h_after[12] - h_before[12];
+    c->n_rebuilds += rebuilt;
+    if (rebuilt > 0) { c->stat_units = h_after[13]; c->stat_chunks = h_after[14]; c->stat_masks = h_after[15]; }
+    c->n_launches += (int64_t)nsteps * c->graph_launches_per_step + (int64_t)rebuilt * 10;
+    c->n_pair_launches += nsteps;
+    if (h_flags[3] & 1) return fail(c, MDK_ERR_OOM, "tile-list pool overflow inside a graph step (raise the pools: more atoms per box than planned)");
+    if (h_flags[3] & 2) return fail(c, MDK_ERR_NLIST_STALE, "an i-block outgrew the hoisted-minimum-image bound inside a graph step");
+    return MDK_OK;
+}
+
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms) {
     if (nsteps <= 0) return MDK_OK;
     const int n = c->n, T = 256, B = (n + T - 1) / T;
@@ -539,7 +676,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
 #define LANGEVIN(mode)                                                                                          \
     do {                                                                                                        \
         PhaseTimer pt(c, PH_INTEGRATE);                                                                         \
-        k_langevin<<<B, T, 0, c->stream>>>(n, (mode), dt, ca, cb, tg, seed, c->langevin_step, c->order.p,       \
+        k_langevin<<<B, T, 0, c->stream>>>(n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, c->order.p, \
                                            c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, \
                                            c->xs_ref.p, c->flags.p);                                            \
         ++c->n_launches;                                                                                        \
@@ -554,7 +691,12 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
         LANGEVIN(2 | 4);
     }
     ++c->langevin_step;
-    for (int s = 0; s < nsteps; ++s) {
+    int s0 = 0;
+    if (c->use_graph && c->profiling < 2 && c->nranks == 1 && nsteps > 4) {
+        MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps - 1));
+        s0 = nsteps - 1;
+    }
+    for (int s = s0; s < nsteps; ++s) {
         MDK_TRY(compute_terms(c, terms, false));  // f(x_n+1)
         const bool more = s + 1 < nsteps;
         LANGEVIN(more ? 3 : 1);

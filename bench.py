@@ -191,6 +191,11 @@ def run_b200(args, cfg):
     dev = ctx.dev
     kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
     dt = cfg['dt']
+    if args.no_graph:
+        dev.set_option('graph', 0)
+    for kv in filter(None, os.environ.get('MDK_OPTS', '').split(',')):   # experiments: MDK_OPTS=concurrent=0,graph=1
+        k, v = kv.split('=')
+        dev.set_option(k, float(v))
 
     def barrier():
         if dist is not None:
@@ -375,6 +380,7 @@ def main():
     ap.add_argument('--config', default='water_23k', choices=sorted(CONFIGS))
     ap.add_argument('--relax', type=float, default=1.0, help='scale of the untimed lattice-relaxation phase')
     ap.add_argument('--skip-extras', action='store_true', help='only the timed region (for ncu runs)')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host (no CUDA-graph steps)')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == 'reference':

@@ -555,7 +555,7 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph) {
                                                              c->ws, o);
     if (in_graph) {
         float lim[3];
-        for (int a = 0; a < 3; ++a) lim[a] = 0.5f * (0.5f * c->box.L[a] - g.R - 0.05f);
+        for (int a = 0; a < 3; ++a) lim[a] = 0.5f * c->box.L[a] - g.R - 0.05f;
         k_after_build<<<1, 1, 0, c->stream>>>(c->counters.p, c->flags.p, lim[0], lim[1], lim[2], c->shift_ok ? 1 : 0);
     }
     c->n_launches += in_graph ? 0 : 9;
@@ -577,13 +577,15 @@ int nlist_rebuild(mdk_ctx *c) {
         if (!h_flags[2]) {
             c->stat_units = h_cnt[0]; c->stat_chunks = h_cnt[4]; c->stat_masks = h_cnt[2];  // [4] = filled chunks
             // hoisted minimum image (k_pair<..., SHIFT>): every listed j must have a unique image within
-            // L/2 of the block centre: R + 2 h_max <= L/2 on every axis (1 A spare when later rebuilds
-            // will run inside a graph and cannot switch kernels)
+            // L/2 of the block centre.  An interacting j is within R of some i-atom, which is within h of
+            // the centre, so R + h_max <= L/2 on every axis is enough (pairs farther apart than R may then
+            // see a non-minimal image, but both distances exceed the cutoff).  1 A spare when later
+            // rebuilds will run inside a graph and cannot switch kernels.
             c->shift_ok = true;
             for (int a = 0; a < 3; ++a) {
                 float hmax;
                 memcpy(&hmax, &h_cnt[8 + a], sizeof(float));
-                if (g.R + 2.f * (hmax + (c->graph_pools ? 1.0f : 0.f)) + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
+                if (g.R + hmax + (c->graph_pools ? 1.0f : 0.f) + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
             }
             c->nlist_valid = true;
             ++c->n_rebuilds;

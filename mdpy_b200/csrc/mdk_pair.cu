@@ -20,8 +20,16 @@ struct PairParams {
     float L[3], invL[3];
     float rc2_lj, ron2, inv_ab3, rc2_max;  // CHARMM switch: (rc^2 - ron^2)^-3
     float rc2_c, alpha, two_alpha_over_sqrtpi;
+    float sw_c0, sw_12inv;      // rc^2 - 3 ron^2, 12 (rc^2 - ron^2)^-3
+    float alpha2_log2e;         // alpha^2 log2(e): exp(-alpha^2 r^2) = ex2(-alpha2_log2e r^2)
     int n;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // erfc(x) * exp(x^2) ~= t * P(t), t = 1 / (1 + 0.4 x): degree-8 least-squares fit on
 // x in [0, 4.2], max relative error 8e-9 in exact arithmetic, <4e-7 evaluated in fp32
@@ -42,14 +50,85 @@ __device__ __forceinline__ float erfcx_poly(float x) {
 
 constexpr int PAIR_WARPS = 8;
 
+// One chunk = 32 j-atoms against the warp's 32 i-atoms, 32 rotation steps.  MASKED chunks carry
+// exclusion / 1-4 bits (a few per i-block); the rest skip the bit tests entirely.
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool MASKED>
+__device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__restrict__ sx,
+                                           const float4 *__restrict__ slj, const int lane, const float4 xi,
+                                           const float4 li, const unsigned excl, const unsigned m14, float &fix,
+                                           float &fiy, float &fiz, float &fjx, float &fjy, float &fjz, float &e_lj,
+                                           float &e_c) {
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const int slot = (lane + k) & 31;
+        const float4 xj = sx[slot];
+        float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+        if (!SHIFT) {
+            dx = min_image(dx, P.L[0], P.invL[0]);
+            dy = min_image(dy, P.L[1], P.invL[1]);
+            dz = min_image(dz, P.L[2], P.invL[2]);
+        }
+        const float r2 = dist2(dx, dy, dz);
+        bool in = r2 <= P.rc2_max;
+        if (MASKED) in = in && !((excl >> k) & 1u);
+        if (in) {
+            const float rinv = rsqrtf(r2);
+            const float r2inv = rinv * rinv;
+            float g = 0.f;  // dE/dr / r : F_i = g d, F_j = -g d  (d = x_j - x_i)
+            if (DO_LJ) {
+                if (ONECUT || r2 <= P.rc2_lj) {
+                    const float4 lj = slj[slot];
+                    float a = li.x * lj.x, s = li.y + lj.y;             // 4 eps_ij, sigma_ij
+                    if (MASKED) {
+                        if ((m14 >> k) & 1u) { a = li.z * lj.z; s = li.w + lj.w; }
+                    }
+                    const float s2 = s * s * r2inv;
+                    const float s6 = s2 * s2 * s2;
+                    const float t = a * s6, w = t * s6;                 // 4 eps s^6, 4 eps s^12
+                    float e = w - t;
+                    float gl = fmaf(-12.f, w, 6.f * t) * r2inv;
+                    if (SWITCH) {
+                        if (r2 > P.ron2) {
+                            const float da = P.rc2_lj - r2;
+                            const float S = da * da * fmaf(2.f, r2, P.sw_c0) * P.inv_ab3;
+                            const float dS = P.sw_12inv * da * (P.ron2 - r2);   // (dS/dr)/r
+                            gl = fmaf(gl, S, e * dS);
+                            e *= S;
+                        }
+                    }
+                    if (ENERGY) e_lj += e;
+                    g = gl;
+                }
+            }
+            if (DO_COUL) {
+                if (ONECUT || r2 <= P.rc2_c) {
+                    // erfc(x) = P(t) exp(-x^2):  E = qq P ex / r,  dE/dr / r = -qq ex (P / r + 2 alpha / sqrt(pi)) / r^2
+                    const float u = xi.w * xj.w * ex2_approx(-P.alpha2_log2e * r2);
+                    const float v = erfcx_poly(P.alpha * (r2 * rinv)) * rinv;
+                    if (ENERGY) e_c = fmaf(u, v, e_c);
+                    g = fmaf(-u, (v + P.two_alpha_over_sqrtpi) * r2inv, g);
+                }
+            }
+            fix = fmaf(g, dx, fix); fiy = fmaf(g, dy, fiy); fiz = fmaf(g, dz, fiz);
+            fjx = fmaf(-g, dx, fjx); fjy = fmaf(-g, dy, fjy); fjz = fmaf(-g, dz, fjz);
+        }
+        // the accumulators follow the j-slot: lane l next serves slot (l + k + 1) & 31,
+        // whose running sum sits in lane l + 1
+        fjx = __shfl_sync(0xffffffffu, fjx, (lane + 1) & 31);
+        fjy = __shfl_sync(0xffffffffu, fjy, (lane + 1) & 31);
+        fjz = __shfl_sync(0xffffffffu, fjz, (lane + 1) & 31);
+    }
+}
+
 // SHIFT: the box is large enough (nlist_rebuild sets ctx->shift_ok) that every atom of a unit has a
 // unique periodic image within L/2 of the i-block centre; positions are reduced to that frame once
 // per atom (i: once per unit, j: once per chunk when it is staged) and the 32 x 32 inner loop works on
 // plain differences.  Without SHIFT the loop applies the canonical minimum image to every pair
 // (small boxes, and the criterion the pair-set hook k_enumerate reproduces bit for bit); with SHIFT
 // the same criterion is evaluated on d rounded once more (pairs within an ulp of rc may differ).
-// ONECUT: LJ and Coulomb share one cutoff, so the in-range test is done once.
-template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT>
+// ONECUT: LJ and Coulomb share one cutoff.  ENERGY: off for the steps of a graph run whose energies
+// nobody reads.
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
        const float4 *__restrict__ bbc, long long *__restrict__ f_acc, long long *__restrict__ e_acc,
@@ -86,11 +165,6 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
             const int chunk = unit.y + cidx;
             const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
             const int mslot = nl.chunk_mask[chunk];
-            unsigned excl = 0u, m14 = 0u;
-            if (mslot >= 0) {
-                excl = nl.mask_excl[(size_t)mslot * 32 + lane];
-                if (DO_LJ) m14 = nl.mask_14[(size_t)mslot * 32 + lane];
-            }
             float4 xj_own = xs[j];
             if (SHIFT) {
                 xj_own.x = min_image(xj_own.x - cx, P.L[0], P.invL[0]);
@@ -102,66 +176,14 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
             if (DO_LJ) s_lj[wid][lane] = ljs[j];
             __syncwarp();
             float fjx = 0.f, fjy = 0.f, fjz = 0.f;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const int slot = (lane + k) & 31;
-                const float4 xj = s_x[wid][slot];
-                float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
-                if (!SHIFT) {
-                    dx = min_image(dx, P.L[0], P.invL[0]);
-                    dy = min_image(dy, P.L[1], P.invL[1]);
-                    dz = min_image(dz, P.L[2], P.invL[2]);
-                }
-                const float r2 = dist2(dx, dy, dz);
-                if (r2 <= P.rc2_max && !((excl >> k) & 1u)) {
-                    const float rinv = rsqrtf(r2);
-                    const float r2inv = rinv * rinv;
-                    float g = 0.f;  // dE/dr / r : F_i = g d, F_j = -g d  (d = x_j - x_i)
-                    if (DO_LJ) {
-                        if (ONECUT || r2 <= P.rc2_lj) {
-                            const float4 lj = s_lj[wid][slot];
-                            const bool is14 = (m14 >> k) & 1u;
-                            const float a = is14 ? li.z * lj.z : li.x * lj.x;       // 4 eps_ij
-                            const float s = is14 ? li.w + lj.w : li.y + lj.y;       // sigma_ij
-                            const float s2 = s * s * r2inv;
-                            const float s6 = s2 * s2 * s2;
-                            const float t = a * s6, w = t * s6;                      // 4 eps s^6, 4 eps s^12
-                            float e = w - t;
-                            float gl = (6.f * t - 12.f * w) * r2inv;
-                            if (SWITCH) {
-                                if (r2 > P.ron2) {
-                                    const float da = P.rc2_lj - r2;
-                                    const float S = da * da * (P.rc2_lj + 2.f * r2 - 3.f * P.ron2) * P.inv_ab3;
-                                    const float dS = 12.f * da * (P.ron2 - r2) * P.inv_ab3;  // (dS/dr)/r
-                                    gl = gl * S + e * dS;
-                                    e *= S;
-                                }
-                            }
-                            e_lj += e;
-                            g += gl;
-                        }
-                    }
-                    if (DO_COUL) {
-                        if (ONECUT || r2 <= P.rc2_c) {
-                            const float qq = xi.w * xj.w;
-                            const float r = r2 * rinv;
-                            const float ar = P.alpha * r;
-                            const float ex = __expf(-ar * ar);
-                            const float erfc_ar = erfcx_poly(ar) * ex;
-                            const float qr = qq * rinv;
-                            e_c += qr * erfc_ar;
-                            g -= qq * (erfc_ar * rinv + P.two_alpha_over_sqrtpi * ex) * r2inv;
-                        }
-                    }
-                    const float fx = g * dx, fy = g * dy, fz = g * dz;
-                    fix += fx; fiy += fy; fiz += fz;
-                    fjx -= fx; fjy -= fy; fjz -= fz;
-                }
-                // the accumulators follow the j-slot: lane l next serves slot (l + k + 1) & 31,
-                // whose running sum sits in lane l + 1
-                fjx = __shfl_sync(0xffffffffu, fjx, (lane + 1) & 31);
-                fjy = __shfl_sync(0xffffffffu, fjy, (lane + 1) & 31);
-                fjz = __shfl_sync(0xffffffffu, fjz, (lane + 1) & 31);
+            if (mslot >= 0) {
+                const unsigned excl = nl.mask_excl[(size_t)mslot * 32 + lane];
+                const unsigned m14 = DO_LJ ? nl.mask_14[(size_t)mslot * 32 + lane] : 0u;
+                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, true>(P, s_x[wid], s_lj[wid], lane, xi, li, excl, m14,
+                                                                               fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c);
+            } else {
+                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, false>(P, s_x[wid], s_lj[wid], lane, xi, li, 0u, 0u,
+                                                                                fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c);
             }
             // after 32 rotations lane l holds the sum for slot l again
             if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {
@@ -175,14 +197,16 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
             atomic_add_fix(&f_acc[3 * (size_t)ia + 1], to_fix(fiy));
             atomic_add_fix(&f_acc[3 * (size_t)ia + 2], to_fix(fiz));
         }
-        e_lj_tot += to_fix((double)e_lj);
-        e_c_tot += to_fix((double)e_c);
+        if (ENERGY) {
+            e_lj_tot += to_fix((double)e_lj);
+            e_c_tot += to_fix((double)e_c);
+        }
     }
-    if (DO_LJ) {
+    if (ENERGY && DO_LJ) {
         long long v = warp_sum_ll(e_lj_tot);
         if (lane == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_LJ], v);
     }
-    if (DO_COUL) {
+    if (ENERGY && DO_COUL) {
         long long v = warp_sum_ll(e_c_tot);
         if (lane == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_COUL_DIRECT], v);
     }
@@ -202,6 +226,9 @@ static PairParams make_pair_params(mdk_ctx *c, bool do_lj, bool do_coul) {
     P.rc2_max = fmaxf(P.rc2_lj, P.rc2_c);
     P.alpha = (float)c->alpha;
     P.two_alpha_over_sqrtpi = (float)(2.0 * c->alpha / sqrt(M_PI));
+    P.alpha2_log2e = (float)(c->alpha * c->alpha * 1.4426950408889634);
+    P.sw_c0 = P.rc2_lj - 3.f * P.ron2;
+    P.sw_12inv = 12.f * P.inv_ab3;
     P.n = c->n;
     return P;
 }
@@ -223,16 +250,22 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     if (grid > max_blocks && !c->in_capture) grid = (int)max_blocks;   // a captured launch must fit any later list
     dim3 g(grid), b(PAIR_WARPS * 32);
     int *cursor = c->counters.p + 3;
-#define LAUNCH(LJ, CO, SW, SH, OC)                                                                          \
-    k_pair<LJ, CO, SW, SH, OC><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
-                                                         c->e_acc.p, cursor)
-#define PICK_OC(LJ, CO, SW, SH) do { if (onecut) LAUNCH(LJ, CO, SW, SH, true); else LAUNCH(LJ, CO, SW, SH, false); } while (0)
+    // inner graph steps do not report energies; the energy-less instantiation is only used where it
+    // measured faster (plain-cutoff LJ: -9 % at 23 k atoms; with the CHARMM switch ptxas schedules
+    // it 18 % slower than the energy-carrying one, so that combination keeps ENERGY on)
+    const bool energy = !c->in_capture || c->graph_energy || sw;   // the inner steps of a graph run never report energies
+#define LAUNCH(LJ, CO, SW, SH, OC, EN)                                                                          \
+    k_pair<LJ, CO, SW, SH, OC, EN><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
+                                                             c->e_acc.p, cursor)
+#define PICK_EN(LJ, CO, SW, SH, OC) do { if (energy) LAUNCH(LJ, CO, SW, SH, OC, true); else LAUNCH(LJ, CO, SW, SH, OC, false); } while (0)
+#define PICK_OC(LJ, CO, SW, SH) do { if (onecut) PICK_EN(LJ, CO, SW, SH, true); else PICK_EN(LJ, CO, SW, SH, false); } while (0)
 #define PICK_SH(LJ, CO, SW) do { if (shift) PICK_OC(LJ, CO, SW, true); else PICK_OC(LJ, CO, SW, false); } while (0)
     if (do_lj && do_coul) { if (sw) PICK_SH(true, true, true); else PICK_SH(true, true, false); }
     else if (do_lj)       { if (sw) PICK_SH(true, false, true); else PICK_SH(true, false, false); }
     else                  PICK_SH(false, true, false);
 #undef PICK_SH
 #undef PICK_OC
+#undef PICK_EN
 #undef LAUNCH
     c->n_launches += 1;
     c->n_pair_launches += 1;

@@ -553,9 +553,69 @@ __global__ void k_tick(unsigned long long *step_dev) { *step_dev += 1ull; }
 void graph_destroy(mdk_ctx *c) {
     if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
     if (c->step_graph) cudaGraphDestroy(c->step_graph);
+    if (c->upkeep_exec) cudaGraphExecDestroy(c->upkeep_exec);
+    if (c->upkeep_graph) cudaGraphDestroy(c->upkeep_graph);
     c->step_exec = nullptr; c->step_graph = nullptr;
+    c->upkeep_exec = nullptr; c->upkeep_graph = nullptr;
 }
 
+#define CAP(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess && rc == MDK_OK)                                                            \
+            rc = fail(c, MDK_ERR_CUDA, "%s failed while capturing the step graph: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+// Graph 1, "upkeep": k_decide -> IF(rebuild needed) { whole list rebuild }.  Kept separate from the
+// force/update graph: a graph that contains a conditional node is executed without branch
+// concurrency (measured: the PME / bonded branches stopped overlapping k_pair), so the conditional
+// lives in its own two-node graph.
+static int graph_build_upkeep(mdk_ctx *c) {
+    cudaStream_t s = c->stream;
+    int rc = MDK_OK;
+    cudaGraph_t graph = nullptr;
+    CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    if (rc != MDK_OK) return rc;
+    cudaStreamCaptureStatus status;
+    unsigned long long id = 0;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
+    cudaGraphConditionalHandle handle;
+    CAP(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+    k_decide<<<1, 1, 0, s>>>(handle, c->flags.p);
+    CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.size = 1;
+    cudaGraphNode_t cond = nullptr;
+    CAP(cudaGraphAddNode(&cond, graph, deps, ndeps, &cp));
+    if (rc == MDK_OK) {
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        // the rebuild, captured into the branch body on a side stream
+        CAP(cudaStreamBeginCaptureToGraph(c->s_aux, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        if (rc == MDK_OK) {
+            c->stream = c->s_aux;
+            int r2 = nlist_enqueue(c, true);
+            c->stream = s;
+            cudaGraph_t dummy = nullptr;
+            CAP(cudaStreamEndCapture(c->s_aux, &dummy));
+            if (r2 != MDK_OK && rc == MDK_OK) rc = r2;
+        }
+        CAP(cudaStreamUpdateCaptureDependencies(s, &cond, 1, cudaStreamSetCaptureDependencies));
+    }
+    cudaGraph_t done = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &done);
+    if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    if (rc != MDK_OK) { if (done) cudaGraphDestroy(done); cudaGetLastError(); return rc; }
+    c->upkeep_graph = done;
+    e = cudaGraphInstantiate(&c->upkeep_exec, done, 0);
+    if (e != cudaSuccess) return fail(c, MDK_ERR_CUDA, "cudaGraphInstantiate(upkeep): %s", cudaGetErrorString(e));
+    return MDK_OK;
+}
+
+// Graph 2, "step": forces (three concurrent branches) -> Langevin finish + advance -> step counter.
 static int graph_build_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed,
                                 unsigned terms) {
     graph_destroy(c);
@@ -566,62 +626,27 @@ static int graph_build_langevin(mdk_ctx *c, double dt, double ca, double cb, dou
     MDK_CUDA(c, c->step_dev.reserve(2));
     c->in_capture = true;
     const int64_t launches_before = c->n_launches, pair_before = c->n_pair_launches;
-    int rc = MDK_OK;
+    int rc = graph_build_upkeep(c);
     cudaGraph_t graph = nullptr;
-#define CAP(call)                                                                                          \
-    do {                                                                                                   \
-        cudaError_t e__ = (call);                                                                          \
-        if (e__ != cudaSuccess && rc == MDK_OK)                                                            \
-            rc = fail(c, MDK_ERR_CUDA, "%s failed while capturing the step graph: %s", #call, cudaGetErrorString(e__)); \
-    } while (0)
-    CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
     if (rc == MDK_OK) {
-        cudaStreamCaptureStatus status;
-        unsigned long long id = 0;
-        const cudaGraphNode_t *deps = nullptr;
-        size_t ndeps = 0;
-        CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
-        cudaGraphConditionalHandle handle;
-        CAP(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
-        k_decide<<<1, 1, 0, s>>>(handle, c->flags.p);
-        CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
-        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
-        cp.conditional.handle = handle;
-        cp.conditional.type = cudaGraphCondTypeIf;
-        cp.conditional.size = 1;
-        cudaGraphNode_t cond = nullptr;
-        CAP(cudaGraphAddNode(&cond, graph, deps, ndeps, &cp));
+        CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
         if (rc == MDK_OK) {
-            cudaGraph_t body = cp.conditional.phGraph_out[0];
-            // the rebuild, captured into the branch body on a side stream
-            CAP(cudaStreamBeginCaptureToGraph(c->s_aux, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+            rc = forces_enqueue(c, terms);
             if (rc == MDK_OK) {
-                c->stream = c->s_aux;
-                int r2 = nlist_enqueue(c, true);
-                c->stream = s;
-                cudaGraph_t dummy = nullptr;
-                CAP(cudaStreamEndCapture(c->s_aux, &dummy));
-                if (r2 != MDK_OK && rc == MDK_OK) rc = r2;
+                k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->order.p, c->mass.p,
+                                           c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, c->xs_ref.p,
+                                           c->flags.p);
+                k_tick<<<1, 1, 0, s>>>(c->step_dev.p);
             }
-            CAP(cudaStreamUpdateCaptureDependencies(s, &cond, 1, cudaStreamSetCaptureDependencies));
+            cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
         }
-        if (rc == MDK_OK) rc = forces_enqueue(c, terms);
-        if (rc == MDK_OK) {
-            k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->order.p, c->mass.p, c->f_acc.p,
-                                       c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
-            k_tick<<<1, 1, 0, s>>>(c->step_dev.p);
-        }
-        cudaGraph_t done = nullptr;
-        cudaError_t e = cudaStreamEndCapture(s, &done);
-        if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-        graph = done;
     }
-#undef CAP
     c->in_capture = false;
     c->stream = s;
-    c->graph_launches_per_step = (int)(c->n_launches - launches_before) + 4;   // + decide, langevin, tick, cursor
+    c->graph_launches_per_step = (int)(c->n_launches - launches_before) + 3;   // + decide, langevin, tick
     c->n_launches = launches_before; c->n_pair_launches = pair_before;         // capturing is not launching
-    if (rc != MDK_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    if (rc != MDK_OK) { if (graph) cudaGraphDestroy(graph); graph_destroy(c); cudaGetLastError(); return rc; }
     c->step_graph = graph;
     cudaError_t e = cudaGraphInstantiate(&c->step_exec, graph, 0);
     if (e != cudaSuccess) { graph_destroy(c); return fail(c, MDK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
@@ -629,6 +654,7 @@ static int graph_build_langevin(mdk_ctx *c, double dt, double ca, double cb, dou
     c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
     return MDK_OK;
 }
+#undef CAP
 
 // n steady-state steps (finish v of the pending step, advance x) as graph launches
 static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed, unsigned terms,
@@ -650,7 +676,10 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
     int h_before[16];
     MDK_CUDA(c, cudaMemcpyAsync(h_before, c->counters.p, sizeof(h_before), cudaMemcpyDeviceToHost, c->stream));
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int s = 0; s < nsteps; ++s) MDK_CUDA(c, cudaGraphLaunch(c->step_exec, c->stream));
+    for (int s = 0; s < nsteps; ++s) {
+        MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
+        MDK_CUDA(c, cudaGraphLaunch(c->step_exec, c->stream));
+    }
     int h_after[16], h_flags[4];
     MDK_CUDA(c, cudaMemcpyAsync(h_after, c->counters.p, sizeof(h_after), cudaMemcpyDeviceToHost, c->stream));
     MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
@@ -659,7 +688,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
     const int rebuilt = h_after[12] - h_before[12];
     c->n_rebuilds += rebuilt;
     if (rebuilt > 0) { c->stat_units = h_after[13]; c->stat_chunks = h_after[14]; c->stat_masks = h_after[15]; }
-    c->n_launches += (int64_t)nsteps * c->graph_launches_per_step + (int64_t)rebuilt * 10;
+    c->n_launches += (int64_t)nsteps * c->graph_launches_per_step + (int64_t)rebuilt * 9;
     c->n_pair_launches += nsteps;
     if (h_flags[3] & 1) return fail(c, MDK_ERR_OOM, "tile-list pool overflow inside a graph step (raise the pools: more atoms per box than planned)");
     if (h_flags[3] & 2) return fail(c, MDK_ERR_NLIST_STALE, "an i-block outgrew the hoisted-minimum-image bound inside a graph step");

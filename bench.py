@@ -177,6 +177,11 @@ def run_b200(args, cfg):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     dist = torch = None
     if world > 1:
+        # NCCL / torchrun may print banners on stdout: park fd 1 on stderr and keep the real stdout for the JSON line
+        sys.stdout.flush()
+        real_stdout = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+        sys.stdout = real_stdout
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)

@@ -502,7 +502,8 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 0: c->use_graph = value != 0; break;          // CUDA-graph steps in the integrators
         case 1: c->concurrent = value != 0; break;         // PME / bonded on side streams
         case 2: c->force_canonical = value != 0; break;
-        case 3: c->graph_energy = value != 0; break;       // energies in every graph step    // per-pair canonical minimum image even in large boxes
+        case 3: c->graph_energy = value != 0; break;       // energies in every graph step
+        case 4: c->graph_nccl = value != 0; break;         // graph steps with the NCCL all-reduce inside (N > 1)    // per-pair canonical minimum image even in large boxes
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

@@ -152,6 +152,7 @@ struct mdk_ctx {
 
     // ---- CUDA-graph step ----
     bool use_graph = true, in_capture = false;
+    bool graph_nccl = false;                  // capture the per-step ncclAllReduce into the step graph (N > 1): hung at N = 2 in round 1, off
     bool graph_energy = false;                // energies in every graph step (the energy-less k_pair variant measured 18 % slower at 92k atoms: ptxas schedules it worse)
     bool xs_current = false;                  // tile-order positions already match x_cur (integrator just published them)
     cudaGraph_t step_graph = nullptr;

@@ -721,7 +721,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
     }
     ++c->langevin_step;
     int s0 = 0;
-    if (c->use_graph && c->profiling < 2 && c->nranks == 1 && nsteps > 4) {
+    if (c->use_graph && c->profiling < 2 && (c->nranks == 1 || c->graph_nccl) && nsteps > 4) {
         MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps - 1));
         s0 = nsteps - 1;
     }

@@ -1,6 +1,6 @@
 #!/bin/bash
 CFG=${1:-water_23k}; STEPS=${2:-1000}; TAG=${3:-x}
-python -u bench.py --config $CFG --steps $STEPS --warmup 50 > gpurun_out/bench_${CFG}_${TAG}.json 2> gpurun_out/bench_${CFG}_${TAG}.err
+timeout 420 python -u bench.py --config $CFG --steps $STEPS --warmup 50 > gpurun_out/bench_${CFG}_${TAG}.json 2> gpurun_out/bench_${CFG}_${TAG}.err
 echo rc=$? ; tail -c 600 gpurun_out/bench_${CFG}_${TAG}.err; python - <<PY
 import json
 try:

@@ -1,6 +1,6 @@
 #!/bin/bash
 N=${1:-2}; CFG=${2:-protein_92k}; STEPS=${3:-300}
-python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus $N --config $CFG --steps $STEPS --warmup 30 > gpurun_out/bench_${CFG}_g$N.json 2> gpurun_out/bench_${CFG}_g$N.err
+timeout 420 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus $N --config $CFG --steps $STEPS --warmup 30 > gpurun_out/bench_${CFG}_g$N.json 2> gpurun_out/bench_${CFG}_g$N.err
 echo rc=$? ; tail -c 1500 gpurun_out/bench_${CFG}_g$N.err; python - <<PY
 import json
 try:

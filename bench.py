@@ -8,10 +8,13 @@ erfc direct space over the tile list, PME reciprocal (spread, cuFFT, influence f
 bonded terms and the Langevin position/velocity update.  Default workload = BASELINE.json configs[1]:
 23 556-atom TIP3P box, 9 A cutoff, PME 64^3 order 4, Langevin 300 K, 2 fs.
 
-Prints ONE JSON line (rank 0).  value = ns/day with the state resident on the device (CUDA events
-around K steps); e2e = the same metric through the drop-in Constraint API with host buffers
-(positions H2D and forces D2H every step, numpy integrator on the host — the way the reference's
-own integrators drive Constraint.update).  roofline = the pair kernel against the FP32 CUDA-core
+Prints ONE JSON line (rank 0).  metric = atom-steps/s (BASELINE.json names "ns/day and atom-steps/s";
+atom-steps/s is the one that stays comparable when the box changes with the GPU count: N = 1 runs
+configs[1], the 23k water box; N > 1 runs configs[3], the 1.07 M-atom box the 1/2/4/8-GPU numbers are
+quoted on); ns_per_day rides along.  value = state resident on the device (CUDA events around K
+steps); e2e = the same metric through the drop-in integrator call with HOST state: every step is one
+LangevinIntegrator.integrate(ensemble, 1), i.e. positions + velocities H2D from page-locked memory,
+one step, positions + velocities + energies D2H (mdk_step_langevin_host).  roofline = the pair kernel against the FP32 CUDA-core
 peak (70 flop per in-cutoff pair), roofline_pme = spread/FFT/gather against measured
 HBM bandwidth.  cpu_baseline / --impl reference = the reference's per-step work (27-cell-list LJ +
 all-pairs Coulomb, no PME) restated in C (oracle/), on the host cores.
@@ -154,14 +157,14 @@ def run_reference(args, cfg):
         if it >= args.warmup:
             times.append(t)
     sec = float(np.mean(times))
-    value = ns_per_day(1, sec, cfg['dt'])
-    line = dict(metric='ns_per_day', value=value, unit='ns/day', impl='reference', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='strong', vs_baseline=None,
-                dtype='f32', data='synthetic', atom_steps_per_s=system.num_particles / sec,
+    value = system.num_particles / sec
+    line = dict(metric='atom_steps_per_s', value=value, unit='atom-steps/s', impl='reference', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='strong',
+                vs_baseline=None, dtype='f32', data='synthetic', ns_per_day=ns_per_day(1, sec, cfg['dt']),
                 config=dict(workload=args.config, atoms=system.num_particles, cutoff_A=cfg['cutoff'], dt_fs=cfg['dt'],
                             note='reference path = plain-cutoff LJ + bare all-pairs Coulomb (no PME in the reference tree)'),
-                cpu_baseline=dict(value=value, unit='ns/day', cores=threads, kind='port', sample=sample),
-                e2e=dict(value=value, unit='ns/day', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                cpu_baseline=dict(value=value, unit='atom-steps/s', cores=threads, kind='port', sample=sample),
+                e2e=dict(value=value, unit='atom-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
@@ -248,7 +251,7 @@ def run_b200(args, cfg):
     # ---- multi-GPU: join the communicator, deal i-blocks to ranks weighted by the extra roles ----
     weights = None
     if world > 1:
-        weights = multigpu.role_weights(world, pair_ms + ph['nlist_ms'] / prof_steps, pme_ms, bonded_ms)
+        weights = multigpu.role_weights(world, pair_ms + ph['nlist_ms'] / prof_steps, pme_ms, 0.0)   # bonded terms are split evenly
         multigpu.attach(ctx, dist, rank, world, weights)
     integ.integrate(ens, max(args.warmup, 3))
 
@@ -269,8 +272,9 @@ def run_b200(args, cfg):
 
     if args.skip_extras:
         if rank == 0:
-            print(json.dumps(dict(metric='ns_per_day', value=value, unit='ns/day', steps=args.steps, warmup=args.warmup,
-                                  n_gpus=world, ms_per_step=dev_ms / args.steps, gpu_launches=launches,
+            print(json.dumps(dict(metric='atom_steps_per_s', value=n * args.steps / (dev_ms * 1e-3), unit='atom-steps/s',
+                                  ns_per_day=value, steps=args.steps, warmup=args.warmup,
+                                  n_gpus=world, ms_per_step=dev_ms / args.steps, gpu_launches=launches, rebuilds=rebuilds,
                                   note='skip-extras (profiling run)')))
         if dist is not None:
             dist.destroy_process_group()
@@ -289,32 +293,26 @@ def run_b200(args, cfg):
         fl.append(dev.timing()['total_ms'])
     dev.set_profiling(0)
 
-    # ---- e2e: the drop-in per-step path with host buffers (all ranks in lockstep, same seeds) ----
-    e2e_steps = min(args.steps, 300 if n < 200000 else 30)
-    ens.state._positions = dev.download_positions()
+    # ---- e2e: the drop-in integrator call with host state, one call per step (all ranks in lockstep) ----
+    # Every call uploads ensemble.state (positions + velocities, float32, page-locked), runs one step and
+    # downloads the new state and the energies; between calls the state lives in host memory only as far
+    # as the API is concerned (the device continues its float64 trajectory when the host copy is unchanged).
+    e2e_steps = min(args.steps, 1000 if n < 200000 else 100)
+    ens.state._positions = dev.download_positions()      # the timed region above stepped the device directly
     ens.state._velocities = dev.download_velocities()
-    x = ens.state.positions.astype(np.float64)
-    v = ens.state.velocities.astype(np.float64)
-    m = np.asarray(ens.topology.masses, dtype=np.float64).reshape(-1, 1)
-    rng = np.random.default_rng(0)
-    ca = (1 - GAMMA * dt / 2) / (1 + GAMMA * dt / 2); cb = 1 / (1 + GAMMA * dt / 2)
-    noise = np.sqrt(2 * GAMMA * kT * dt * m)
-    for _ in range(3):   # warm-up of the host path
-        ens.state.set_positions(x.astype(np.float32)); ens.update()
-    f = ens.forces.copy()
+    ens.state.revision += 1
+    e2e_integ = LangevinIntegrator(dt, TEMPERATURE, GAMMA, seed=2)
+    for _ in range(5):   # warm-up of the host path (graph capture of the single-step variant, pinned buffers)
+        e2e_integ.integrate(ens, 1)
+    l_before = dev.timing()['launches']
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        beta = noise * rng.standard_normal(x.shape)
-        x = x + cb * dt * v + cb * dt * dt / (2 * m) * f + cb * dt / (2 * m) * beta
-        xw = (x - system.box * np.round(x / system.box)).astype(np.float32)
-        ens.state.set_positions(xw)            # host -> State (wrap); H2D inside update()
-        ens.update()                           # one fused device evaluation; forces D2H
-        f_new = ens.forces
-        v = ca * v + dt / (2 * m) * (ca * f + f_new) + cb / m * beta
-        f = f_new
+        e2e_integ.integrate(ens, 1)
     e2e_sec = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = ns_per_day(e2e_steps, e2e_sec, dt)
+    e2e_launches = (dev.timing()['launches'] - l_before) / e2e_steps
+    e2e_value = n * e2e_steps / e2e_sec
+    e2e_energy = float(ens.potential_energy)
 
     if rank != 0:
         dist.destroy_process_group()
@@ -334,28 +332,30 @@ def run_b200(args, cfg):
     cpu = None
     if world == 1:
         cpu_sec, sample = reference_step_seconds(system, cfg, 1, budget_s=10.0)
-        cpu = dict(value=ns_per_day(1, cpu_sec, dt), unit='ns/day', cores=1, kind='port', sample=sample,
-                   host_cores=os.cpu_count(), seconds_per_step=cpu_sec)
+        cpu = dict(value=n / cpu_sec, unit='atom-steps/s', cores=1, kind='port', sample=sample,
+                   host_cores=os.cpu_count(), seconds_per_step=cpu_sec, ns_per_day=ns_per_day(1, cpu_sec, dt))
 
     phase_keys = ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms', 'comm_ms')
     line = dict(
-        metric='ns_per_day', value=value, unit='ns/day', n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
-        data='synthetic', atom_steps_per_s=n * args.steps / (dev_ms * 1e-3), wall_ms_per_step=wall * 1e3 / args.steps,
+        metric='atom_steps_per_s', value=n * args.steps / (dev_ms * 1e-3), unit='atom-steps/s', n_gpus=world,
+        steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong',
+        vs_baseline=None, dtype='f32', data='synthetic', ns_per_day=value, wall_ms_per_step=wall * 1e3 / args.steps,
         config=dict(workload=args.config, atoms=n, cutoff_A=cfg['cutoff'], switch_A=cfg['switch'], pme_grid=list(cfg['grid']),
                     pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=2.0,
                     terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_in_timed=rebuilds,
                     parallelism='single GPU' if world == 1 else
-                    'replicated positions, i-block sharded pair forces (weights %s), PME on last rank, int64 all-reduce per step'
+                    'replicated positions, i-block sharded pair forces (weights %s), bonded terms split evenly, PME on last rank, int64 all-reduce per step'
                     % np.round(weights, 3).tolist(),
                     l2='steady-state MD trajectory: every step consumes the previous step\'s output, nothing is re-timed '
                        'on a repeated input; working set %.1f MB; l2_flushed_ms_per_step gives the same step with a '
                        '256 MB L2 flush before it' % ((32.0 * n + 12.0 * K) / 1e6)),
         l2_flushed_ms_per_step=float(np.median(fl)),
         clocks=clocks.summary(), gpu_launches=launches,
-        e2e=dict(value=e2e_value, unit='ns/day', h2d_bytes_per_step=12 * n, d2h_bytes_per_step=24 * n,
-                 steps=e2e_steps, ms_per_step=e2e_sec * 1e3 / e2e_steps,
-                 path='State.set_positions + Ensemble.update (fused mdk_compute) per step, numpy G-JF update on the host'),
+        e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=24 * n, d2h_bytes_per_step=24 * n + 128,
+                 steps=e2e_steps, ms_per_step=e2e_sec * 1e3 / e2e_steps, ns_per_day=ns_per_day(e2e_steps, e2e_sec, dt),
+                 gpu_launches_per_step=e2e_launches, potential_energy_last_step=e2e_energy,
+                 path='LangevinIntegrator.integrate(ensemble, 1) per step: host State (float32 positions + velocities, '
+                      'page-locked) -> mdk_step_langevin_host -> host State + energies; wall clock, max over ranks'),
         roofline=dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak, traffic=None,
                       kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=pair_ms_n,
                       peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source'],
@@ -382,11 +382,14 @@ def main():
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default='water_23k', choices=sorted(CONFIGS))
+    ap.add_argument('--config', default=None, choices=sorted(CONFIGS),
+                    help='default: water_23k (BASELINE configs[1]) at --gpus 1, protein_1m (configs[3]) at --gpus > 1')
     ap.add_argument('--relax', type=float, default=1.0, help='scale of the untimed lattice-relaxation phase')
     ap.add_argument('--skip-extras', action='store_true', help='only the timed region (for ncu runs)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host (no CUDA-graph steps)')
     args = ap.parse_args()
+    if args.config is None:
+        args.config = 'water_23k' if args.gpus <= 1 else 'protein_1m'
     cfg = CONFIGS[args.config]
     if args.impl == 'reference':
         run_reference(args, cfg)

@@ -14,6 +14,7 @@
 #ifndef MDPY_B200_H
 #define MDPY_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -148,6 +149,22 @@ MDK_API void mdk_verlet_reset(mdk_ctx *ctx); /* Integrator.erase_cache, integrat
  * (langevin_integrator.py:23-31; textbook update), Philox4x32-10 noise. */
 MDK_API int mdk_step_langevin(mdk_ctx *ctx, double dt, double kT, double gamma, uint64_t seed,
                       int nsteps, unsigned terms);
+/* LangevinIntegrator.integrate(ensemble, nsteps) with the host State as input and output
+ * (langevin_integrator.py:38-72 reads ensemble.state.positions / velocities and writes them back;
+ * integrator.py:14-50).  x_in / v_in: float32 [n,3] host arrays (NULL = keep the device state);
+ * an atom whose host value equals the float32 image of the device state keeps its float64 device
+ * coordinate, so feeding back what the previous call returned continues the trajectory without a
+ * restart; any other atom takes the host value and the step caches are dropped.  x_out / v_out:
+ * float32 [n,3] (wrapped positions / velocities after the last step; NULL = skip), energies
+ * [MDK_NUM_ENERGIES] or NULL.  Buffers from mdk_host_alloc are copied without staging.  One stream
+ * synchronisation after the upload, one at the end. */
+MDK_API int mdk_step_langevin_host(mdk_ctx *ctx, const float *x_in, const float *v_in, float *x_out, float *v_out,
+                           double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
+                           double *energies);
+/* Page-locked host memory owned by the ctx (freed by mdk_destroy at the latest): State arrays that
+ * live in it move to / from the device by DMA without a staging copy. */
+MDK_API int mdk_host_alloc(mdk_ctx *ctx, size_t bytes, void **out);
+MDK_API int mdk_host_free(mdk_ctx *ctx, void *ptr);
 /* Energies of the most recent force evaluation inside a step call (no extra work). */
 MDK_API int mdk_last_energies(mdk_ctx *ctx, double *energies);
 

@@ -41,6 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_set_shard', 'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
+    'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free',
 ]
 
 _lib = None
@@ -93,6 +94,9 @@ def load_library():
         'mdk_comm_init': (i32, [vp, i32, i32, vp]),
         'mdk_flush_l2': (i32, [vp]),
         'mdk_set_option': (i32, [vp, i32, f64]),
+        'mdk_step_langevin_host': (i32, [vp, vp, vp, vp, vp, f64, f64, f64, u64, i32, C.c_uint, vp]),
+        'mdk_host_alloc': (i32, [vp, C.c_size_t, C.POINTER(vp)]),
+        'mdk_host_free': (i32, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -251,6 +255,36 @@ class Device:
     def step_langevin(self, dt, kT, gamma, seed, nsteps, terms):
         self._ck(self._lib.mdk_step_langevin(self._h, float(dt), float(kT), float(gamma), int(seed), int(nsteps), int(terms)))
 
+    def pinned_empty(self, shape, dtype=np.float32):
+        """numpy array over page-locked memory of this context (mdk_host_alloc): host State arrays kept
+        in it are copied to / from the device without a staging pass.  Lives as long as the context."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        p = C.c_void_p()
+        self._ck(self._lib.mdk_host_alloc(self._h, max(1, count * dtype.itemsize), C.byref(p)))
+        buf = (C.c_char * (count * dtype.itemsize)).from_address(p.value)
+        buf._owner = self                     # the array's base keeps the context (and its memory) alive
+        arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        arr.fill(0)
+        return arr
+
+    def step_langevin_host(self, x_in, v_in, x_out, v_out, dt, kT, gamma, seed, nsteps, terms):
+        """mdk_step_langevin_host: host State in (float32 [n,3] or None), nsteps steps, host State out."""
+        def chk(a, name, writable=False):
+            if a is None:
+                return None
+            if a.dtype != np.float32 or a.shape != (self.n, 3) or not a.flags.c_contiguous:
+                raise _err.ArrayDimError('%s should be C-contiguous float32 [%d, 3]' % (name, self.n))
+            if writable and not a.flags.writeable:
+                raise ValueError('%s is read-only' % name)
+            return _ptr(a)
+        e = np.zeros(NUM_ENERGIES, dtype=np.float64)
+        self._ck(self._lib.mdk_step_langevin_host(self._h, chk(x_in, 'positions'), chk(v_in, 'velocities'),
+                                                  chk(x_out, 'positions out', True), chk(v_out, 'velocities out', True),
+                                                  float(dt), float(kT), float(gamma), int(seed), int(nsteps), int(terms),
+                                                  _ptr(e)))
+        return e
+
     def reset_integrator(self):
         self._lib.mdk_verlet_reset(self._h)
 
@@ -315,11 +349,30 @@ class EnsembleContext:
         self.dev.set_exclusions(topo.bonded_particles, topo.scaling_particles)
         self.integrator_owner = None
 
+    def state_buffers(self):
+        """(positions, velocities) float32 [n,3] arrays in page-locked memory for the next host-state step
+        call to fill.  Two pairs alternate, so the arrays handed out by the previous call (which are the
+        current State, and the next call's input) are never the ones being written."""
+        bufs = getattr(self, '_state_bufs', None)
+        if bufs is None or bufs[0][0].shape[0] != self.dev.n:
+            # positions and velocities share one block, so each direction is a single DMA
+            blocks = [self.dev.pinned_empty((2, self.dev.n, 3)) for _ in range(2)]
+            bufs = self._state_bufs = [(b[0], b[1]) for b in blocks]
+            self._state_turn = 0
+        self._state_turn ^= 1
+        return bufs[self._state_turn]
+
     def check_box(self):
-        pbc = np.asarray(self.ensemble.state.pbc_matrix, dtype=np.float64)
+        m = self.ensemble.state.pbc_matrix
+        seen = getattr(self, '_box_seen', None)
+        if seen is not None and seen[0] is m:     # State replaces the matrix object when the box changes
+            return seen[1].copy()
+        pbc = np.asarray(m, dtype=np.float64)
         if np.abs(pbc - np.diag(pbc.diagonal())).max() > 0:
             raise _err.PBCPoorDefinedError('mdpy_b200 supports orthorhombic boxes only (SURVEY Q3)')
-        return pbc.diagonal().copy()
+        box = pbc.diagonal().copy()
+        self._box_seen = (m, box)
+        return box.copy()
 
     @staticmethod
     def _revision(state):

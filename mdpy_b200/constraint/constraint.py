@@ -52,7 +52,10 @@ class Constraint:
         """Push this constraint's parameters into the shared device context (idempotent)."""
 
     def _energy_from(self, energies):
-        return float(sum(energies[s] for t, slots in _native.TERM_ENERGY_SLOTS.items() if self.terms & t for s in slots))
+        slots = self.__dict__.get('_energy_slots')
+        if slots is None or slots[0] != self.terms:
+            slots = self._energy_slots = (self.terms, [s for t, sl in _native.TERM_ENERGY_SLOTS.items() if self.terms & t for s in sl])
+        return float(sum(energies[s] for s in slots[1]))
 
     def update(self):
         """Constraint.update: one device evaluation of this constraint's terms; forces come back as

@@ -9,6 +9,7 @@ erfc direct space over the tile list + smooth PME reciprocal space + self / back
 excluded-pair terms.  alpha from erfc(alpha rc)/rc = ewald_error (the reference's only hint is the
 ewald_error=1e-6 default of CharmmForcefield, forcefield/charmm_forcefield.py:23).
 """
+import functools
 import math
 
 import numpy as np
@@ -42,6 +43,7 @@ class ElectrostaticConstraint(Constraint):
             self._configured = True
 
 
+@functools.lru_cache(maxsize=64)
 def ewald_alpha(cutoff_radius, ewald_error):
     """alpha such that erfc(alpha rc) / rc == ewald_error (bisection)."""
     lo, hi = 0.0, 10.0 / cutoff_radius

@@ -54,6 +54,54 @@ __global__ void k_f64_to_f32(size_t n, const double *__restrict__ in, float *__r
     if (i < n) out[i] = (float)in[i];
 }
 
+// Host state handed to a step call (float32, positions wrapped, matrix_id order) against the device
+// state (float64, unwrapped): an atom whose float32 image equals the host value keeps its float64
+// coordinate, any other takes the host value.  flags[4]: a position changed (integrator caches are then
+// stale), flags[5]: a velocity changed, flags[0]: an atom is 2 or more images away (utils/pbc.py:29-34).
+__global__ void k_accept_state(int n, const float *__restrict__ x_in, const float *__restrict__ v_in,
+                               double *__restrict__ x_cur, double *__restrict__ vel, double Lx, double Ly, double Lz,
+                               int *__restrict__ flags) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const double L[3] = {Lx, Ly, Lz};
+    bool changed = false, lost = false, vchanged = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const size_t i = 3 * (size_t)a + d;
+        if (x_in) {
+            const float h = x_in[i];
+            const double x = x_cur[i];
+            const float w = (float)(x - L[d] * rint(x / L[d]));
+            if (w != h) {
+                x_cur[i] = (double)h;
+                changed = true;
+                if (!(fabs(rint((double)h / L[d])) < 2.0)) lost = true;
+            }
+        }
+        if (v_in) {
+            const float h = v_in[i];
+            if ((float)vel[i] != h) { vel[i] = (double)h; vchanged = true; }
+        }
+    }
+    if (changed) flags[4] = 1;
+    if (vchanged) flags[5] = 1;
+    if (lost) flags[0] = 1;
+}
+
+// wrapped float32 positions and float32 velocities for the host State, one pass
+__global__ void k_export_state(int n, const double *__restrict__ x_cur, const double *__restrict__ vel, double Lx,
+                               double Ly, double Lz, float *__restrict__ x_out, float *__restrict__ v_out) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const double L[3] = {Lx, Ly, Lz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const size_t i = 3 * (size_t)a + d;
+        if (x_out) { const double x = x_cur[i]; x_out[i] = (float)(x - L[d] * rint(x / L[d])); }
+        if (v_out) v_out[i] = (float)vel[i];
+    }
+}
+
 }  // namespace mdk
 
 using namespace mdk;
@@ -76,6 +124,24 @@ static int stage_download(mdk_ctx *c, void *out, size_t bytes) {
     MDK_CUDA(c, cudaMemcpyAsync(c->io_host, c->io_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(out, c->io_host, bytes);
+    return MDK_OK;
+}
+
+static bool is_pinned(const mdk_ctx *c, const void *p, size_t bytes) {
+    const char *q = static_cast<const char *>(p);
+    for (const auto &b : c->pinned)
+        if (q >= b.first && q + bytes <= b.first + b.second) return true;
+    return false;
+}
+// host -> device on the ctx stream, asynchronous: straight from mdk_host_alloc memory, through the
+// pinned mirror (at byte offset `off`, which also is the offset into io_dev) otherwise
+static int h2d_async(mdk_ctx *c, size_t off, const void *src, size_t bytes) {
+    char *dst = reinterpret_cast<char *>(c->io_dev.p) + off;
+    if (!is_pinned(c, src, bytes)) {
+        memcpy(static_cast<char *>(c->io_host) + off, src, bytes);
+        src = static_cast<char *>(c->io_host) + off;
+    }
+    MDK_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     return MDK_OK;
 }
 
@@ -125,14 +191,17 @@ int mdk_create(int device, mdk_ctx **out) {
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_pme, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
-    if (c->counters.reserve(16) != cudaSuccess || c->flags.reserve(4) != cudaSuccess ||
-        c->e_acc.reserve(MDK_NUM_ENERGIES) != cudaSuccess) {
+    if (c->readback.reserve(32) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void **>(&c->pin_words), 64 * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) {
         mdk_destroy(c);
         return fail(nullptr, MDK_ERR_OOM, "cudaMalloc failed in mdk_create");
     }
-    cudaMemset(c->counters.p, 0, 16 * sizeof(int));
-    cudaMemset(c->flags.p, 0, 4 * sizeof(int));
-    cudaMemset(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long));
+    // aliases into the read-back block (cap stays 0: they are not owned)
+    c->e_acc.p = c->readback.p;
+    c->counters.p = reinterpret_cast<int *>(c->readback.p + 16);
+    c->flags.p = reinterpret_cast<int *>(c->readback.p + 24);
+    cudaMemset(c->readback.p, 0, 32 * sizeof(long long));
+    memset(c->pin_words, 0, 64 * sizeof(long long));
     *out = c;
     return MDK_OK;
 }
@@ -148,14 +217,15 @@ void mdk_destroy(mdk_ctx *c) {
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
     c->x_cur.release(); c->x_prev.release(); c->vel.release(); c->f_prev.release();
     c->order.release(); c->inv_order.release(); c->xs.release(); c->xs_ref.release(); c->ljs.release();
-    c->excl_s.release(); c->p14_s.release(); c->f_acc.release(); c->e_acc.release(); c->flags.release();
+    c->excl_s.release(); c->p14_s.release(); c->f_acc.release(); c->readback.release();
     c->cell_key.release(); c->cell_key_sorted.release(); c->idx_tmp.release(); c->cell_start.release();
     c->sort_tmp.release(); c->sort_buf.release(); c->bb_center.release(); c->bb_half.release();
     c->units.release(); c->chunk_j.release(); c->chunk_mask.release(); c->mask_excl.release(); c->mask_14.release();
-    c->counters.release();
     c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release();
     c->io_dev.release();
     if (c->io_host) cudaFreeHost(c->io_host);
+    if (c->pin_words) cudaFreeHost(c->pin_words);
+    for (auto &b : c->pinned) cudaFreeHost(b.first);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_pme) cudaEventDestroy(c->ev_pme);
@@ -449,13 +519,149 @@ int mdk_step_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t s
     if (!(dt > 0) || kT < 0 || gamma < 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_step_langevin: dt=%g kT=%g gamma=%g", dt, kT, gamma);
     prepare_pme_constants(c);
     if (c->profiling) { for (auto &p : c->phase_ms) p = 0; cudaEventRecord(c->ev[2 * PH_TOTAL], c->stream); }
-    MDK_TRY(integrate_langevin(c, dt, kT, gamma, seed, nsteps, terms));
+    MDK_TRY(integrate_langevin(c, dt, kT, gamma, seed, nsteps, terms, 5, false));
     if (c->profiling) {
         cudaEventRecord(c->ev[2 * PH_TOTAL + 1], c->stream);
         cudaEventSynchronize(c->ev[2 * PH_TOTAL + 1]);
         float ms = 0; cudaEventElapsedTime(&ms, c->ev[2 * PH_TOTAL], c->ev[2 * PH_TOTAL + 1]);
         c->phase_ms[PH_TOTAL] = ms;
     }
+    return MDK_OK;
+}
+
+int mdk_host_alloc(mdk_ctx *c, size_t bytes, void **out) {
+    NEED_CTX(c);
+    if (!out || bytes == 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_host_alloc: bad arguments");
+    cudaSetDevice(c->device);
+    void *p = nullptr;
+    MDK_CUDA(c, cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    c->pinned.emplace_back(static_cast<char *>(p), bytes);
+    *out = p;
+    return MDK_OK;
+}
+
+int mdk_host_free(mdk_ctx *c, void *p) {
+    NEED_CTX(c);
+    for (size_t k = 0; k < c->pinned.size(); ++k)
+        if (c->pinned[k].first == p) {
+            cudaStreamSynchronize(c->stream);
+            cudaFreeHost(p);
+            c->pinned.erase(c->pinned.begin() + k);
+            return MDK_OK;
+        }
+    return fail(c, MDK_ERR_BAD_ARG, "mdk_host_free: not a block of this context");
+}
+
+// Integrator.integrate with the host State as input and output (langevin_integrator.py:38-72 reads
+// ensemble.state.positions / velocities and writes them back): one call = host -> device copy of the
+// state, nsteps steps, device -> host copy of the new state and the energies.
+//
+// Steady state (cached force, valid list, graph steps) runs AHEAD of its own change check: the upload,
+// the comparison kernel, the steps and the download are queued back to back and the stream is
+// synchronised once.  Should the comparison find that the host positions differ from the device's
+// (flags[4]) the queued Langevin kernels have left the state alone (k_langevin), and the call is redone
+// on the careful path: read the flags first, drop the caches, evaluate f(x_0), then step.
+static int host_state_in(mdk_ctx *c, const float *x_in, const float *v_in, size_t m) {
+    const size_t mb = m * sizeof(float);
+    float *stage = reinterpret_cast<float *>(c->io_dev.p);
+    MDK_CUDA(c, cudaMemsetAsync(c->flags.p + 4, 0, 2 * sizeof(int), c->stream));
+    if (x_in && !c->have_pos)
+        MDK_CUDA(c, cudaMemsetAsync(c->x_cur.p, 0xff, m * sizeof(double), c->stream));  // NaN pattern: everything "differs"
+    if (x_in && v_in && v_in == x_in + m && is_pinned(c, x_in, 2 * mb)) {
+        MDK_CUDA(c, cudaMemcpyAsync(stage, x_in, 2 * mb, cudaMemcpyHostToDevice, c->stream));   // one block, one copy
+    } else {
+        if (x_in) MDK_TRY(h2d_async(c, 0, x_in, mb));
+        if (v_in) MDK_TRY(h2d_async(c, mb, v_in, mb));
+    }
+    k_accept_state<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, x_in ? stage : nullptr, v_in ? stage + m : nullptr,
+                                                              c->x_cur.p, c->vel.p, c->box.Ld[0], c->box.Ld[1],
+                                                              c->box.Ld[2], c->flags.p);
+    ++c->n_launches;
+    return MDK_OK;
+}
+
+static int host_state_out(mdk_ctx *c, float *x_out, float *v_out, size_t m, float **px, float **pv) {
+    const size_t mb = m * sizeof(float);
+    float *stage = reinterpret_cast<float *>(c->io_dev.p);
+    *px = *pv = nullptr;
+    if (!x_out && !v_out) return MDK_OK;
+    k_export_state<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->x_cur.p, c->vel.p, c->box.Ld[0], c->box.Ld[1],
+                                                              c->box.Ld[2], x_out ? stage + 2 * m : nullptr,
+                                                              v_out ? stage + 3 * m : nullptr);
+    ++c->n_launches;
+    if (x_out && v_out && v_out == x_out + m && is_pinned(c, x_out, 2 * mb)) {
+        MDK_CUDA(c, cudaMemcpyAsync(x_out, stage + 2 * m, 2 * mb, cudaMemcpyDeviceToHost, c->stream));
+        *px = x_out; *pv = v_out;
+        return MDK_OK;
+    }
+    if (x_out) {
+        *px = is_pinned(c, x_out, mb) ? x_out : reinterpret_cast<float *>(static_cast<char *>(c->io_host) + 2 * mb);
+        MDK_CUDA(c, cudaMemcpyAsync(*px, stage + 2 * m, mb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (v_out) {
+        *pv = is_pinned(c, v_out, mb) ? v_out : reinterpret_cast<float *>(static_cast<char *>(c->io_host) + 3 * mb);
+        MDK_CUDA(c, cudaMemcpyAsync(*pv, stage + 3 * m, mb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return MDK_OK;
+}
+
+int mdk_step_langevin_host(mdk_ctx *c, const float *x_in, const float *v_in, float *x_out, float *v_out, double dt,
+                           double kT, double gamma, uint64_t seed, int nsteps, unsigned terms, double *energies) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!(dt > 0) || kT < 0 || gamma < 0 || nsteps < 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_step_langevin_host: dt=%g kT=%g gamma=%g nsteps=%d", dt, kT, gamma, nsteps);
+    if (c->n <= 0 || !c->have_box) return fail(c, MDK_ERR_NOT_BOUND, "mdk_step_langevin_host before box/atoms");
+    if (!x_in && !c->have_pos) return fail(c, MDK_ERR_NOT_BOUND, "no positions on the device and none passed in");
+    prepare_pme_constants(c);
+    const size_t m = (size_t)3 * c->n, mb = m * sizeof(float);
+    MDK_TRY(stage_reserve(c, 4 * mb));
+    if (c->profiling) { for (auto &p : c->phase_ms) p = 0; cudaEventRecord(c->ev[2 * PH_TOTAL], c->stream); }
+    const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
+    const uint64_t step0 = c->langevin_step;
+    bool ahead = (x_in || v_in) && nsteps > 0 && c->have_pos && c->langevin_cached && c->nlist_valid && c->use_graph &&
+                 c->profiling < 2 && c->nranks == 1;
+    float *px = nullptr, *pv = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        if ((x_in || v_in) && pass == 0) MDK_TRY(host_state_in(c, x_in, v_in, m));
+        if ((x_in || v_in) && !ahead) {
+            // careful path: learn what changed before queueing anything that depends on it
+            MDK_CUDA(c, cudaMemcpyAsync(c->pin_words, c->readback.p, 28 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+            const bool lost = h_flags[0] != 0, changed = h_flags[4] != 0;
+            MDK_CUDA(c, cudaMemsetAsync(c->flags.p + 4, 0, 2 * sizeof(int), c->stream));
+            if (lost) {
+                cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream);
+                c->have_pos = false;
+                c->verlet_cached = false; c->langevin_cached = false;
+                return fail(c, MDK_ERR_PARTICLE_LOST, "Atom(s) moved beyond 2 PBC image.");
+            }
+            if (changed || !c->have_pos) {
+                c->have_pos = true;
+                c->xs_current = false;
+                c->verlet_cached = false; c->langevin_cached = false;
+            }
+        }
+        if (nsteps > 0) MDK_TRY(integrate_langevin(c, dt, kT, gamma, seed, nsteps, terms, 1, true));
+        MDK_TRY(host_state_out(c, x_out, v_out, m, &px, &pv));
+        if (c->profiling) cudaEventRecord(c->ev[2 * PH_TOTAL + 1], c->stream);
+        MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!ahead || !(h_flags[4] | h_flags[0])) break;
+        // ran ahead and lost the bet: nothing was advanced; redo with the flags in hand
+        c->graph_pending = 0;
+        c->langevin_step = step0;
+        ahead = false;
+    }
+    if (c->profiling) {
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[2 * PH_TOTAL], c->ev[2 * PH_TOTAL + 1]);
+        c->phase_ms[PH_TOTAL] = ms;
+    }
+    if (x_out && px != x_out) memcpy(x_out, px, mb);
+    if (v_out && pv != v_out) memcpy(v_out, pv, mb);
+    if (nsteps > 0) {
+        energies_finish(c, terms);
+        MDK_TRY(graph_finish(c));
+    }
+    if (energies) memcpy(energies, c->last_e, sizeof(c->last_e));
     return MDK_OK;
 }
 

@@ -3,7 +3,7 @@
 // The reference has no multi-GPU path at all.  Round-1 scheme:
 // positions replicated, i-blocks of the tile list sharded over ranks (each rank builds and
 // evaluates only its own blocks' work units), PME on the last rank, bonded / excluded-pair
-// terms on rank 0, then ONE ncclAllReduce(sum) of the int64 fixed-point force accumulator per
+// terms dealt evenly in contiguous ranges, then ONE ncclAllReduce(sum) of the int64 fixed-point force accumulator per
 // force evaluation.  Integer addition commutes, so every rank ends up with bit-identical forces
 // and integrates all atoms redundantly; the N-GPU trajectory equals the 1-GPU one.
 //

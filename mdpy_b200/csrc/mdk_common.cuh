@@ -108,7 +108,8 @@ struct mdk_ctx {
     mdk::DevBuf<int> excl_s, p14_s;           // exclusion tables in tile slots
     mdk::DevBuf<long long> f_acc;             // [n_pad,3] fixed-point forces
     mdk::DevBuf<long long> e_acc;             // [MDK_NUM_ENERGIES] fixed point
-    mdk::DevBuf<int> flags;                   // [0]=lost atoms [1]=needs rebuild [2]=pool overflow [3]=scratch
+    mdk::DevBuf<int> flags;                   // [0]=lost atoms [1]=needs rebuild [2]=pool overflow [3]=sticky graph errors
+                                              // [4]=host positions differed from the device state [5]=host velocities differed
     // cell grid
     int ncell[3] = {0, 0, 0};
     float cellw[3] = {0, 0, 0};
@@ -152,14 +153,18 @@ struct mdk_ctx {
 
     // ---- CUDA-graph step ----
     bool use_graph = true, in_capture = false;
+    bool capture_energy = false;              // the step graph being captured carries the pair-kernel energy sums
+    int graph_pending = 0;                    // graph steps queued whose bookkeeping (graph_finish) is still due
     bool graph_nccl = false;                  // capture the per-step ncclAllReduce into the step graph (N > 1): hung at N = 2 in round 1, off
     bool graph_energy = false;                // energies in every graph step (the energy-less k_pair variant measured 18 % slower at 92k atoms: ptxas schedules it worse)
     bool xs_current = false;                  // tile-order positions already match x_cur (integrator just published them)
-    cudaGraph_t step_graph = nullptr;
-    cudaGraphExec_t step_exec = nullptr;
+    // two instantiations of the step graph: [0] inner steps (pair kernel without energy sums where that
+    // is faster), [1] steps whose energies are read back (the last step of a call)
+    cudaGraph_t step_graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t step_exec[2] = {nullptr, nullptr};
     cudaGraph_t upkeep_graph = nullptr;       // k_decide -> IF { list rebuild }
     cudaGraphExec_t upkeep_exec = nullptr;
-    mdk::DevBuf<unsigned long long> step_dev;
+    mdk::DevBuf<unsigned long long> step_dev;  // [0] Langevin noise counter, [1] k_langevin mode of the next graph step
     double graph_key[8] = {0};
     long long graph_epoch = 0, graph_epoch_built = -1;
     int graph_launches_per_step = 0;
@@ -168,6 +173,12 @@ struct mdk_ctx {
     mdk::DevBuf<unsigned char> io_dev;
     void *io_host = nullptr;
     size_t io_host_cap = 0;
+    // One device block holds everything the host reads back after a call — e_acc (16 x int64), counters
+    // (16 x int), flags (8 x int) alias into it — so a single 256-byte copy into pin_words fetches it all.
+    mdk::DevBuf<long long> readback;          // [0..15] energies, [16..23] counters, [24..27] flags
+    long long *pin_words = nullptr;           // pinned mirror of `readback` (+ scratch words behind it)
+    int rebuilds_seen = 0;                    // counters[12] (rebuilds done inside graphs) at the last read-back
+    std::vector<std::pair<char *, size_t>> pinned;   // mdk_host_alloc blocks: copied to / from without staging
 
     // ---- bookkeeping ----
     double last_e[MDK_NUM_ENERGIES] = {0};
@@ -224,10 +235,14 @@ int pme_prepare(mdk_ctx *c);
 int pme_compute(mdk_ctx *c);
 int bonded_compute(mdk_ctx *c, unsigned terms);
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
-int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms);
+int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
+                       int graph_min_steps, bool defer_energies);
+int energies_enqueue(mdk_ctx *c);                    // kinetic energy + all-reduce + D2H into pin_words (no sync)
+void energies_finish(mdk_ctx *c, unsigned terms);    // after the stream was synchronised
 int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);
 int forces_enqueue(mdk_ctx *c, unsigned terms);
 void graph_destroy(mdk_ctx *c);
+int graph_finish(mdk_ctx *c);                        // counters / sticky errors of a queued graph run, after a sync
 int comm_allreduce_forces(mdk_ctx *c);
 int comm_allreduce_energies(mdk_ctx *c);
 void comm_destroy(mdk_ctx *c);

@@ -31,11 +31,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// MUFU.RSQ / MUFU.RCP without the denormal pre-scaling nvcc wraps around rsqrtf / __fdividef: the
+// arguments here are r^2 of a pair inside the cutoff and 1 + 0.4 alpha r — never denormal.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // erfc(x) * exp(x^2) ~= t * P(t), t = 1 / (1 + 0.4 x): degree-8 least-squares fit on
 // x in [0, 4.2], max relative error 8e-9 in exact arithmetic, <4e-7 evaluated in fp32
 // (fit script: oracle/fit_erfc.py).
 __device__ __forceinline__ float erfcx_poly(float x) {
-    float t = __fdividef(1.0f, __fmaf_rn(0.4f, x, 1.0f));
+    float t = rcp_approx(__fmaf_rn(0.4f, x, 1.0f));
     float p = 1.2938003984e-02f;
     p = __fmaf_rn(p, t, 8.5587749120e-03f);
     p = __fmaf_rn(p, t, -2.5232078617e-01f);
@@ -58,10 +71,12 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
                                            const float4 li, const unsigned excl, const unsigned m14, float &fix,
                                            float &fiy, float &fiz, float &fjx, float &fjy, float &fjz, float &e_lj,
                                            float &e_c) {
+    // the chunk is staged twice back to back (64 entries), so slot (lane + k) & 31 is entry lane + k: one
+    // base address per lane, the rotation step is an immediate offset of the LDS
+    sx += lane; slj += lane;
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) {
-        const int slot = (lane + k) & 31;
-        const float4 xj = sx[slot];
+        const float4 xj = sx[k];
         float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
         if (!SHIFT) {
             dx = min_image(dx, P.L[0], P.invL[0]);
@@ -72,12 +87,12 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
         bool in = r2 <= P.rc2_max;
         if (MASKED) in = in && !((excl >> k) & 1u);
         if (in) {
-            const float rinv = rsqrtf(r2);
+            const float rinv = rsqrt_approx(r2);
             const float r2inv = rinv * rinv;
             float g = 0.f;  // dE/dr / r : F_i = g d, F_j = -g d  (d = x_j - x_i)
             if (DO_LJ) {
                 if (ONECUT || r2 <= P.rc2_lj) {
-                    const float4 lj = slj[slot];
+                    const float4 lj = slj[k];
                     float a = li.x * lj.x, s = li.y + lj.y;             // 4 eps_ij, sigma_ij
                     if (MASKED) {
                         if ((m14 >> k) & 1u) { a = li.z * lj.z; s = li.w + lj.w; }
@@ -133,8 +148,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
        const float4 *__restrict__ bbc, long long *__restrict__ f_acc, long long *__restrict__ e_acc,
        int *__restrict__ cursor) {
-    __shared__ float4 s_x[PAIR_WARPS][32];
-    __shared__ float4 s_lj[PAIR_WARPS][32];
+    __shared__ float4 s_x[PAIR_WARPS][64];
+    __shared__ float4 s_lj[PAIR_WARPS][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_units = *nl.n_units;
     // per-unit energies are converted to fixed point one by one: the total is then independent of
@@ -172,8 +187,8 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
                 xj_own.z = min_image(xj_own.z - cz, P.L[2], P.invL[2]);
             }
             __syncwarp();
-            s_x[wid][lane] = xj_own;
-            if (DO_LJ) s_lj[wid][lane] = ljs[j];
+            s_x[wid][lane] = xj_own; s_x[wid][lane + 32] = xj_own;
+            if (DO_LJ) { const float4 lo = ljs[j]; s_lj[wid][lane] = lo; s_lj[wid][lane + 32] = lo; }
             __syncwarp();
             float fjx = 0.f, fjy = 0.f, fjz = 0.f;
             if (mslot >= 0) {
@@ -253,7 +268,7 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     // inner graph steps do not report energies; the energy-less instantiation is only used where it
     // measured faster (plain-cutoff LJ: -9 % at 23 k atoms; with the CHARMM switch ptxas schedules
     // it 18 % slower than the energy-carrying one, so that combination keeps ENERGY on)
-    const bool energy = !c->in_capture || c->graph_energy || sw;   // the inner steps of a graph run never report energies
+    const bool energy = !c->in_capture || c->graph_energy || c->capture_energy || sw;   // the inner steps of a graph run never report energies
 #define LAUNCH(LJ, CO, SW, SH, OC, EN)                                                                          \
     k_pair<LJ, CO, SW, SH, OC, EN><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
                                                              c->e_acc.p, cursor)
@@ -276,13 +291,13 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
 // ---------------------------------------------------------------------------
 // Excluded-pair Ewald correction: the reciprocal sum contains every pair, also the
 // bonded ones the direct sum skips; remove -k_e q_i q_j erf(alpha r)/r for each of them.
-__global__ void k_excl_correction(int n, int wb, const int *__restrict__ excl_s,
+__global__ void k_excl_correction(int first, int end, int wb, const int *__restrict__ excl_s,
                                   const float4 *__restrict__ xs, double Lx, double Ly, double Lz,
                                   double alpha, long long *__restrict__ f_acc,
                                   long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (t < n * wb) {
+    if (t < end) {
         int k = t / wb;
         int p = excl_s[t];
         if (p > k) {
@@ -304,16 +319,18 @@ __global__ void k_excl_correction(int n, int wb, const int *__restrict__ excl_s,
             }
         }
     }
-    e = warp_sum(e);
-    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[MDK_E_PME_EXCL], to_fix(e));
+    const long long v = warp_sum_ll(to_fix(e));   // per-pair fixed point: independent of the rank split
+    if ((threadIdx.x & 31) == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_PME_EXCL], v);
 }
 
 int pair_special(mdk_ctx *c, bool pme_excl) {
     if (!pme_excl || c->wb <= 0) return MDK_OK;
     PhaseTimer pt(c, PH_BONDED);
-    int total = c->n * c->wb;
-    k_excl_correction<<<(total + 255) / 256, 256, 0, c->stream>>>(
-        c->n, c->wb, c->excl_s.p, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,
+    const long long total = (long long)c->n * c->wb;      // multi-GPU: contiguous range of table entries per rank
+    const int first = (int)(total * c->rank / c->nranks), end = (int)(total * (c->rank + 1) / c->nranks);
+    if (end <= first) return MDK_OK;
+    k_excl_correction<<<(end - first + 255) / 256, 256, 0, c->stream>>>(
+        first, end, c->wb, c->excl_s.p, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,
         reinterpret_cast<long long *>(c->e_acc.p));
     ++c->n_launches;
     MDK_CUDA(c, cudaGetLastError());

@@ -120,16 +120,18 @@ __device__ __forceinline__ void add_force(long long *f_acc, int slot, V3 f) {
     atomic_add_fix(&f_acc[3 * (size_t)slot + 1], to_fix(f.y));
     atomic_add_fix(&f_acc[3 * (size_t)slot + 2], to_fix(f.z));
 }
+// per-term conversion to fixed point before the (integer) warp sum: the total does not depend on how
+// the terms are grouped into warps, blocks or ranks
 __device__ __forceinline__ void block_energy(double e, long long *e_acc, int which) {
-    e = warp_sum(e);
-    if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[which], to_fix(e));
+    const long long v = warp_sum_ll(to_fix(e));
+    if ((threadIdx.x & 31) == 0 && v != 0) atomic_add_fix(&e_acc[which], v);
 }
 
 // E = k (r - r0)^2   (charmm_bond_constraint.py:53-73)
-__global__ void k_bonds(int nb, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_bonds(int first, int nb, const int *__restrict__ idx, const float *__restrict__ par,
                         const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                         long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
     if (t < nb) {
         int s1 = inv_order[idx[2 * t]], s2 = inv_order[idx[2 * t + 1]];
@@ -146,10 +148,10 @@ __global__ void k_bonds(int nb, const int *__restrict__ idx, const float *__rest
 }
 
 // E = k (theta - theta0)^2 + k_ub (r13 - r_ub)^2   (charmm_angle_constraint.py:55-96)
-__global__ void k_angles(int na, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_angles(int first, int na, const int *__restrict__ idx, const float *__restrict__ par,
                          const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                          long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
     if (t < na) {
         int s1 = inv_order[idx[3 * t]], s2 = inv_order[idx[3 * t + 1]], s3 = inv_order[idx[3 * t + 2]];
@@ -204,10 +206,10 @@ __device__ __forceinline__ float torsion(float4 p1, float4 p2, float4 p3, float4
 
 // E = k (1 + cos(n phi - delta))   (charmm_dihedral_constraint.py:59-95; the force is the
 // analytic gradient of this energy — the reference's `-k (1 - n sin(..))` at :80 is not).
-__global__ void k_dihedrals(int nd, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_dihedrals(int first, int nd, const int *__restrict__ idx, const float *__restrict__ par,
                             const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                             long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
     if (t < nd) {
         int s[4];
@@ -227,10 +229,10 @@ __global__ void k_dihedrals(int nd, const int *__restrict__ idx, const float *__
 }
 
 // E = k (psi - psi0)^2   (charmm_improper_constraint.py:57-94)
-__global__ void k_impropers(int ni, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_impropers(int first, int ni, const int *__restrict__ idx, const float *__restrict__ par,
                             const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                             long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
     if (t < ni) {
         int s[4];
@@ -249,34 +251,34 @@ __global__ void k_impropers(int ni, const int *__restrict__ idx, const float *__
     block_energy(e, e_acc, MDK_E_IMPROPER);
 }
 
+// multi-GPU: the terms of each kind are dealt to the ranks in contiguous ranges (the forces meet in the
+// all-reduce, the energies in comm_allreduce_energies)
+static inline void rank_range(const mdk_ctx *c, int n, int &first, int &end) {
+    first = (int)((long long)n * c->rank / c->nranks);
+    end = (int)((long long)n * (c->rank + 1) / c->nranks);
+}
+
 int bonded_compute(mdk_ctx *c, unsigned terms) {
     BoxF bx;
     for (int a = 0; a < 3; ++a) { bx.L[a] = c->box.L[a]; bx.invL[a] = c->box.invL[a]; }
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
     PhaseTimer pt(c, PH_BONDED);
     const int T = 128;
-    if ((terms & MDK_TERM_BOND) && c->bonded[0].n > 0) {
-        k_bonds<<<(c->bonded[0].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[0].n, c->bonded[0].idx.p, c->bonded[0].par.p,
-                                                                  c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);
-        ++c->n_launches;
+    int f, e;
+#define BONDED(kind, bit, kernel)                                                                              \
+    if ((terms & (bit)) && c->bonded[kind].n > 0) {                                                            \
+        rank_range(c, c->bonded[kind].n, f, e);                                                                \
+        if (e > f) {                                                                                           \
+            kernel<<<(e - f + T - 1) / T, T, 0, c->stream>>>(f, e, c->bonded[kind].idx.p, c->bonded[kind].par.p, \
+                                                             c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);  \
+            ++c->n_launches;                                                                                   \
+        }                                                                                                      \
     }
-    if ((terms & MDK_TERM_ANGLE) && c->bonded[1].n > 0) {
-        k_angles<<<(c->bonded[1].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[1].n, c->bonded[1].idx.p, c->bonded[1].par.p,
-                                                                   c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);
-        ++c->n_launches;
-    }
-    if ((terms & MDK_TERM_DIHEDRAL) && c->bonded[2].n > 0) {
-        k_dihedrals<<<(c->bonded[2].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[2].n, c->bonded[2].idx.p,
-                                                                      c->bonded[2].par.p, c->inv_order.p, c->xs.p, bx,
-                                                                      c->f_acc.p, e_acc);
-        ++c->n_launches;
-    }
-    if ((terms & MDK_TERM_IMPROPER) && c->bonded[3].n > 0) {
-        k_impropers<<<(c->bonded[3].n + T - 1) / T, T, 0, c->stream>>>(c->bonded[3].n, c->bonded[3].idx.p,
-                                                                      c->bonded[3].par.p, c->inv_order.p, c->xs.p, bx,
-                                                                      c->f_acc.p, e_acc);
-        ++c->n_launches;
-    }
+    BONDED(0, MDK_TERM_BOND, k_bonds)
+    BONDED(1, MDK_TERM_ANGLE, k_angles)
+    BONDED(2, MDK_TERM_DIHEDRAL, k_dihedrals)
+    BONDED(3, MDK_TERM_IMPROPER, k_impropers)
+#undef BONDED
     MDK_CUDA(c, cudaGetLastError());
     return MDK_OK;
 }
@@ -288,8 +290,8 @@ int bonded_compute(mdk_ctx *c, unsigned terms) {
 int forces_enqueue(mdk_ctx *c, unsigned terms) {
     MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
     MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
-    // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units; the O(N) terms
-    // run once — bonded / excluded-pair / bare Coulomb on rank 0, the PME mesh on the last rank
+    // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units and its range of
+    // the bonded / excluded-pair terms; bare Coulomb runs on rank 0, the PME mesh on the last rank
     const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
     // Three independent chains, all adding into the same int64 accumulators (integer atomics commute,
     // so concurrency does not change a single bit): k_pair on the main stream, the PME mesh on s_pme,
@@ -297,7 +299,7 @@ int forces_enqueue(mdk_ctx *c, unsigned terms) {
     const bool fork = c->concurrent && c->profiling < 2;
     const bool want_pme = (terms & MDK_TERM_PME_RECIP) && last;
     const unsigned bonded_bits = terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER);
-    const bool want_aux = first && (bonded_bits || (terms & (MDK_TERM_PME_RECIP | MDK_TERM_COUL_BARE)));
+    const bool want_aux = bonded_bits || (terms & MDK_TERM_PME_RECIP) || (first && (terms & MDK_TERM_COUL_BARE));
     cudaStream_t main_stream = c->stream;
     if (fork && (want_pme || want_aux)) MDK_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
     if (want_pme) {
@@ -310,7 +312,7 @@ int forces_enqueue(mdk_ctx *c, unsigned terms) {
         if (fork) { MDK_CUDA(c, cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); c->stream = c->s_aux; }
         int rc = MDK_OK;
         if (terms & MDK_TERM_PME_RECIP) rc = pair_special(c, true);
-        if (rc == MDK_OK && (terms & MDK_TERM_COUL_BARE)) rc = coulomb_bare(c);
+        if (rc == MDK_OK && first && (terms & MDK_TERM_COUL_BARE)) rc = coulomb_bare(c);
         if (rc == MDK_OK && bonded_bits) rc = bonded_compute(c, terms);
         if (fork) { cudaEventRecord(c->ev_aux, c->s_aux); c->stream = main_stream; }
         MDK_TRY(rc);
@@ -440,14 +442,18 @@ __global__ void k_verlet_velocity(int n, int quirks, double dt, const int *__res
 // mode bit 2 (FROM_PREV): the newest force is f_prev (start of a call on a cached state).
 __global__ void k_langevin(int n, int mode, double dt, double ca, double cb, double two_g_kT_dt,
                            uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_dev,
-                           const int *__restrict__ order,
+                           const unsigned long long *__restrict__ mode_dev, const int *__restrict__ order,
                            const float *__restrict__ mass, const long long *__restrict__ f_acc,
                            double *__restrict__ x_cur, double *__restrict__ vel, double *__restrict__ f_prev,
                            StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
                            int *__restrict__ flags) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    if (step_dev) step = *step_dev;   // graph steps keep the noise counter on the device
+    // a host-state call that ran ahead of its own change check (mdk_step_langevin_host): the host
+    // positions turned out to differ from the device's, the cached force is stale — leave the state alone
+    if (flags[4] | flags[0]) return;
+    if (step_dev) step = *step_dev;   // graph steps keep the noise counter ...
+    if (mode_dev) mode = (int)*mode_dev;   // ... and the mode (3 inside a run, 1 for the last step of a call) on the device
     int a = order[k];
     double m = (double)mass[a], inv_m = 1.0 / m;
     double bs = sqrt(two_g_kT_dt * m);
@@ -502,18 +508,27 @@ static StepGeom make_geom(mdk_ctx *c) {
     return g;
 }
 
-static int fetch_energies(mdk_ctx *c, unsigned terms) {
+int energies_enqueue(mdk_ctx *c) {
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
     if (c->rank == 0) {
         k_kinetic<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->mass.p, c->vel.p, e_acc);
         ++c->n_launches;
     }
     MDK_TRY(comm_allreduce_energies(c));
-    long long h[MDK_NUM_ENERGIES];
-    MDK_CUDA(c, cudaMemcpyAsync(h, c->e_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < MDK_NUM_ENERGIES; ++k) c->last_e[k] = (double)h[k] / FIX_SCALE;
+    // energies, list counters and flags in one 224-byte copy
+    MDK_CUDA(c, cudaMemcpyAsync(c->pin_words, c->readback.p, 28 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    return MDK_OK;
+}
+
+void energies_finish(mdk_ctx *c, unsigned terms) {
+    for (int k = 0; k < MDK_NUM_ENERGIES; ++k) c->last_e[k] = (double)c->pin_words[k] / FIX_SCALE;
     if (terms & MDK_TERM_PME_RECIP) c->last_e[MDK_E_PME_SELF] = c->e_self_bg;
+}
+
+static int fetch_energies(mdk_ctx *c, unsigned terms) {
+    MDK_TRY(energies_enqueue(c));
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    energies_finish(c, terms);
     return MDK_OK;
 }
 
@@ -551,11 +566,13 @@ __global__ void k_decide(cudaGraphConditionalHandle handle, const int *__restric
 __global__ void k_tick(unsigned long long *step_dev) { *step_dev += 1ull; }
 
 void graph_destroy(mdk_ctx *c) {
-    if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
-    if (c->step_graph) cudaGraphDestroy(c->step_graph);
+    for (int v = 0; v < 2; ++v) {
+        if (c->step_exec[v]) cudaGraphExecDestroy(c->step_exec[v]);
+        if (c->step_graph[v]) cudaGraphDestroy(c->step_graph[v]);
+        c->step_exec[v] = nullptr; c->step_graph[v] = nullptr;
+    }
     if (c->upkeep_exec) cudaGraphExecDestroy(c->upkeep_exec);
     if (c->upkeep_graph) cudaGraphDestroy(c->upkeep_graph);
-    c->step_exec = nullptr; c->step_graph = nullptr;
     c->upkeep_exec = nullptr; c->upkeep_graph = nullptr;
 }
 
@@ -615,48 +632,48 @@ static int graph_build_upkeep(mdk_ctx *c) {
     return MDK_OK;
 }
 
-// Graph 2, "step": forces (three concurrent branches) -> Langevin finish + advance -> step counter.
-static int graph_build_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed,
-                                unsigned terms) {
-    graph_destroy(c);
+// Graph 2, "step": forces (three concurrent branches) -> Langevin update (mode read from the device:
+// finish + advance inside a run, finish only for the last step of a call) -> step counter.
+// variant 1 carries the energy sums in the pair kernel (the step whose energies are read back).
+static int graph_build_step(mdk_ctx *c, int variant, double dt, double ca, double cb, double tg, uint64_t seed,
+                            unsigned terms) {
     const int n = c->n, T = 256, B = (n + T - 1) / T;
     StepGeom g = make_geom(c);
     cudaStream_t s = c->stream;
-    if (terms & MDK_TERM_PME_RECIP) MDK_TRY(pme_prepare(c));
-    MDK_CUDA(c, c->step_dev.reserve(2));
     c->in_capture = true;
+    c->capture_energy = variant == 1;
     const int64_t launches_before = c->n_launches, pair_before = c->n_pair_launches;
-    int rc = graph_build_upkeep(c);
+    int rc = MDK_OK;
     cudaGraph_t graph = nullptr;
+    CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
     if (rc == MDK_OK) {
-        CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        rc = forces_enqueue(c, terms);
         if (rc == MDK_OK) {
-            rc = forces_enqueue(c, terms);
-            if (rc == MDK_OK) {
-                k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->order.p, c->mass.p,
-                                           c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, c->xs_ref.p,
-                                           c->flags.p);
-                k_tick<<<1, 1, 0, s>>>(c->step_dev.p);
-            }
-            cudaError_t e = cudaStreamEndCapture(s, &graph);
-            if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->step_dev.p + 1, c->order.p,
+                                       c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p,
+                                       c->xs_ref.p, c->flags.p);
+            k_tick<<<1, 1, 0, s>>>(c->step_dev.p);
         }
+        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
     }
     c->in_capture = false;
+    c->capture_energy = false;
     c->stream = s;
     c->graph_launches_per_step = (int)(c->n_launches - launches_before) + 3;   // + decide, langevin, tick
     c->n_launches = launches_before; c->n_pair_launches = pair_before;         // capturing is not launching
-    if (rc != MDK_OK) { if (graph) cudaGraphDestroy(graph); graph_destroy(c); cudaGetLastError(); return rc; }
-    c->step_graph = graph;
-    cudaError_t e = cudaGraphInstantiate(&c->step_exec, graph, 0);
-    if (e != cudaSuccess) { graph_destroy(c); return fail(c, MDK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
-    c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_key[2] = (double)seed; c->graph_key[3] = (double)terms;
-    c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
+    if (rc != MDK_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    c->step_graph[variant] = graph;
+    cudaError_t e = cudaGraphInstantiate(&c->step_exec[variant], graph, 0);
+    if (e != cudaSuccess) return fail(c, MDK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
     return MDK_OK;
 }
 #undef CAP
 
-// n steady-state steps (finish v of the pending step, advance x) as graph launches
+__global__ void k_set_word(unsigned long long *p, unsigned long long v) { *p = v; }
+
+// nsteps force evaluations as graph launches: nsteps - 1 steady-state steps (finish v of the pending
+// step, advance x) and a last one that only finishes v and carries the energies.
 static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed, unsigned terms,
                               int nsteps) {
     if (!c->graph_pools) {           // first use: re-plan the pools with graph slack, on the host
@@ -664,28 +681,52 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
         c->nlist_valid = false;
         ++c->graph_epoch;
     }
+    // a valid list needs no host round trip here: the upkeep graph reads the skin/2 flag on the device
     if (!c->xs_current) MDK_TRY(nlist_refresh_sorted(c));
-    MDK_TRY(nlist_ensure(c));
+    if (!c->nlist_valid) MDK_TRY(nlist_ensure(c));
     c->xs_current = true;
-    const bool stale = !c->step_exec || c->graph_epoch_built != c->graph_epoch || c->graph_key[0] != dt ||
-                       c->graph_key[1] != tg || c->graph_key[2] != (double)seed || c->graph_key[3] != (double)terms ||
-                       c->graph_key[4] != ca;
-    if (stale) MDK_TRY(graph_build_langevin(c, dt, ca, cb, tg, seed, terms));
-    unsigned long long h_step = c->langevin_step;
-    MDK_CUDA(c, cudaMemcpyAsync(c->step_dev.p, &h_step, sizeof(h_step), cudaMemcpyHostToDevice, c->stream));
-    int h_before[16];
-    MDK_CUDA(c, cudaMemcpyAsync(h_before, c->counters.p, sizeof(h_before), cudaMemcpyDeviceToHost, c->stream));
-    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int s = 0; s < nsteps; ++s) {
-        MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
-        MDK_CUDA(c, cudaGraphLaunch(c->step_exec, c->stream));
+    const bool stale = c->graph_epoch_built != c->graph_epoch || c->graph_key[0] != dt || c->graph_key[1] != tg ||
+                       c->graph_key[2] != (double)seed || c->graph_key[3] != (double)terms || c->graph_key[4] != ca;
+    if (stale) {
+        graph_destroy(c);
+        if (terms & MDK_TERM_PME_RECIP) MDK_TRY(pme_prepare(c));
+        MDK_CUDA(c, c->step_dev.reserve(2));
+        c->in_capture = true;
+        int rc = graph_build_upkeep(c);
+        c->in_capture = false;
+        if (rc != MDK_OK) { graph_destroy(c); c->graph_epoch_built = -1; return rc; }
+        c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_key[2] = (double)seed; c->graph_key[3] = (double)terms;
+        c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
     }
-    int h_after[16], h_flags[4];
-    MDK_CUDA(c, cudaMemcpyAsync(h_after, c->counters.p, sizeof(h_after), cudaMemcpyDeviceToHost, c->stream));
-    MDK_CUDA(c, cudaMemcpyAsync(h_flags, c->flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
-    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->langevin_step += (uint64_t)nsteps;
-    const int rebuilt = h_after[12] - h_before[12];
+    for (int v = 0; v < 2; ++v) {
+        const bool need = v == 1 || nsteps > 1;
+        if (need && !c->step_exec[v]) {
+            int rc = graph_build_step(c, v, dt, ca, cb, tg, seed, terms);
+            if (rc != MDK_OK) { graph_destroy(c); c->graph_epoch_built = -1; return rc; }
+        }
+    }
+    unsigned long long h_words[2] = {c->langevin_step, nsteps == 1 ? 1ull : 3ull};
+    MDK_CUDA(c, cudaMemcpyAsync(c->step_dev.p, h_words, sizeof(h_words), cudaMemcpyHostToDevice, c->stream));
+    for (int s = 0; s < nsteps; ++s) {
+        const bool last = s + 1 == nsteps;
+        if (last && nsteps > 1) { k_set_word<<<1, 1, 0, c->stream>>>(c->step_dev.p + 1, 1ull); ++c->n_launches; }
+        MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
+        MDK_CUDA(c, cudaGraphLaunch(c->step_exec[last ? 1 : 0], c->stream));
+    }
+    c->graph_pending = nsteps;   // counters / flags come back with the energies (energies_enqueue)
+    return MDK_OK;
+}
+
+// bookkeeping of a graph run once the stream has been synchronised
+int graph_finish(mdk_ctx *c) {
+    const int nsteps = c->graph_pending;
+    if (nsteps <= 0) return MDK_OK;
+    c->graph_pending = 0;
+    const int *h_after = reinterpret_cast<const int *>(c->pin_words + 16);
+    const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
+    c->langevin_step += (uint64_t)(nsteps - 1);
+    const int rebuilt = h_after[12] - c->rebuilds_seen;
+    c->rebuilds_seen = h_after[12];
     c->n_rebuilds += rebuilt;
     if (rebuilt > 0) { c->stat_units = h_after[13]; c->stat_chunks = h_after[14]; c->stat_masks = h_after[15]; }
     c->n_launches += (int64_t)nsteps * c->graph_launches_per_step + (int64_t)rebuilt * 9;
@@ -695,7 +736,8 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
     return MDK_OK;
 }
 
-int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms) {
+int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
+                       int graph_min_steps, bool defer_energies) {
     if (nsteps <= 0) return MDK_OK;
     const int n = c->n, T = 256, B = (n + T - 1) / T;
     StepGeom g = make_geom(c);
@@ -705,35 +747,44 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
 #define LANGEVIN(mode)                                                                                          \
     do {                                                                                                        \
         PhaseTimer pt(c, PH_INTEGRATE);                                                                         \
-        k_langevin<<<B, T, 0, c->stream>>>(n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, c->order.p, \
-                                           c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p, \
-                                           c->xs_ref.p, c->flags.p);                                            \
+        k_langevin<<<B, T, 0, c->stream>>>(n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, nullptr, \
+                                           c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, \
+                                           c->xs.p, c->xs_ref.p, c->flags.p);                                   \
         ++c->n_launches;                                                                                        \
     } while (0)
+    const bool use_graph = c->use_graph && c->profiling < 2 && (c->nranks == 1 || c->graph_nccl) && nsteps >= graph_min_steps;
     if (!c->langevin_cached) {
         MDK_TRY(compute_terms(c, terms, false));  // f(x_0)
         LANGEVIN(2);
         c->langevin_cached = true;
     } else {
-        MDK_TRY(nlist_refresh_sorted(c));
-        MDK_TRY(nlist_ensure(c));
+        // the cached force is f(x_n): no list needed to advance; the position update publishes the
+        // tile-order copy itself when a list exists
+        if (!c->nlist_valid || !use_graph) {
+            MDK_TRY(nlist_refresh_sorted(c));
+            MDK_TRY(nlist_ensure(c));
+        }
         LANGEVIN(2 | 4);
+        c->xs_current = c->nlist_valid;
     }
     ++c->langevin_step;
-    int s0 = 0;
-    if (c->use_graph && c->profiling < 2 && (c->nranks == 1 || c->graph_nccl) && nsteps > 4) {
-        MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps - 1));
-        s0 = nsteps - 1;
-    }
-    for (int s = s0; s < nsteps; ++s) {
-        MDK_TRY(compute_terms(c, terms, false));  // f(x_n+1)
-        const bool more = s + 1 < nsteps;
-        LANGEVIN(more ? 3 : 1);
-        if (more) ++c->langevin_step;
+    if (use_graph) {
+        MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps));
+    } else {
+        for (int s = 0; s < nsteps; ++s) {
+            MDK_TRY(compute_terms(c, terms, false));  // f(x_n+1)
+            const bool more = s + 1 < nsteps;
+            LANGEVIN(more ? 3 : 1);
+            if (more) ++c->langevin_step;
+        }
     }
 #undef LANGEVIN
     MDK_CUDA(c, cudaGetLastError());
-    return fetch_energies(c, terms);
+    MDK_TRY(energies_enqueue(c));
+    if (defer_energies) return MDK_OK;     // the caller synchronises once, after queueing its downloads
+    MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+    energies_finish(c, terms);
+    return graph_finish(c);
 }
 
 }  // namespace mdk

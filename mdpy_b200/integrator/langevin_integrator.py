@@ -24,7 +24,14 @@ class LangevinIntegrator(Integrator):
         self._seed = int(seed)
 
     def integrate(self, ensemble, num_steps: int = 1):
-        ctx, terms = self._prepare(ensemble)
-        ctx.dev.step_langevin(float(self._time_step), float(self._kbt), float(self._gamma), self._seed,
-                              int(num_steps), terms)
-        self._publish(ensemble, ctx, terms)
+        """One call = the host State goes in, num_steps steps run on the device, the new host State comes
+        out (mdk_step_langevin_host).  The State is uploaded on every call — in-place edits of its arrays
+        are honoured — and the device keeps its float64 trajectory wherever the host value still equals
+        what the previous call handed out."""
+        ctx, terms = self._bind(ensemble)
+        state = ensemble.state
+        x_out, v_out = ctx.state_buffers()
+        e = ctx.dev.step_langevin_host(self._host_f32(state.positions), self._host_f32(state.velocities), x_out, v_out,
+                                       float(self._time_step), float(self._kbt), float(self._gamma), self._seed,
+                                       int(num_steps), terms)
+        self._publish_state(ensemble, ctx, x_out, v_out, e)

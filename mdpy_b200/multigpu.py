@@ -7,8 +7,8 @@ The reference is single-process, single-device; this is new design
 * the i-blocks of the tile list are dealt to ranks by `block % modulus in [lo, hi)` — tile order is
   spatial, so this is a fine spatial interleave that also balances the half-shell list lengths;
   each rank builds and evaluates only its own blocks' work units;
-* the PME mesh runs on the last rank, bonded and excluded-pair terms on rank 0; the range widths
-  are weighted so that those ranks get fewer pair units;
+* the PME mesh runs on the last rank (its pair range is narrowed by the weights so that it still
+  finishes with the others); bonded and excluded-pair terms are dealt evenly, in contiguous ranges;
 * every force evaluation ends with ONE `ncclAllReduce(sum)` of the int64 fixed-point force
   accumulator, issued by libmdpyb200 on its own stream (mdk_comm.cu).  Integer sums are exact and
   order independent: the N-GPU forces equal the 1-GPU forces bit for bit.

@@ -344,6 +344,51 @@ def test_langevin_equipartition():
     assert 270 < np.mean(temps) < 330
 
 
+def _small_water(seed=5):
+    s = synthetic.water_box(2000, seed, box=np.full(3, 39.2))
+    ens = s.ensemble(cutoff=9.0, pme=True, grid=(40, 40, 40))
+    LangevinIntegrator(0.25, 300, 0.05, seed=3).integrate(ens, 300)   # off the lattice clashes
+    return s, ens
+
+
+def test_langevin_host_state_calls_continue_the_trajectory():
+    """integrate(ens, 1) x 12 (host State in and out at every call, mdk_step_langevin_host) walks the same
+    trajectory as integrate(ens, 12): the device keeps its float64 state while the host copy is unchanged."""
+    _, ens_a = _small_water()
+    _, ens_b = _small_water()
+    assert np.array_equal(ens_a.state.positions, ens_b.state.positions)
+    ia, ib = LangevinIntegrator(1.0, 300, 0.001, seed=7), LangevinIntegrator(1.0, 300, 0.001, seed=7)
+    ia.integrate(ens_a, 12)
+    for _ in range(12):
+        ib.integrate(ens_b, 1)
+    assert np.abs(ens_a.state.positions - ens_b.state.positions).max() < 1e-4
+    assert np.abs(ens_a.state.velocities - ens_b.state.velocities).max() < 1e-5
+    assert ens_a.potential_energy == pytest.approx(ens_b.potential_energy, rel=1e-6)
+    assert ens_b.state.positions.dtype == np.float32 and ens_b.state.positions.shape == (6000, 3)
+    # the energies the step call reports are those of a fresh evaluation at the returned positions
+    e_step = ens_b.potential_energy
+    ens_b.update()
+    assert ens_b.potential_energy == pytest.approx(e_step, rel=1e-6)
+
+
+def test_langevin_host_state_edits_are_honoured():
+    """In-place edits of ensemble.state arrays (no set_positions call, so no revision bump) reach the device."""
+    s, ens = _small_water()
+    integ = LangevinIntegrator(0.5, 300, 0.001, seed=9)
+    integ.integrate(ens, 3)
+    x = ens.state.positions
+    moved = x[0].copy() + np.float32([0.4, 0.0, 0.0])
+    x[0] = moved
+    ens.state.velocities[...] = 0
+    integ.integrate(ens, 1)
+    assert np.abs(ens.state.positions[0] - moved).max() < 0.2
+    assert np.abs(ens.state.velocities).max() < 0.05          # one 0.5 fs step from rest
+    # an atom two box lengths away is lost, as in utils/pbc.py:29-34
+    ens.state.positions[5, 1] = 2.5 * 39.2
+    with pytest.raises(ParticleLossError):
+        integ.integrate(ens, 1)
+
+
 # ---------------------------------------------------------------------------------------------
 # benchmark sizes: size-independent properties + sub-sampled oracle
 def test_92k_box_subsample_parity_and_momentum():

@@ -619,7 +619,7 @@ int mdk_step_langevin_host(mdk_ctx *c, const float *x_in, const float *v_in, flo
     const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
     const uint64_t step0 = c->langevin_step;
     bool ahead = (x_in || v_in) && nsteps > 0 && c->have_pos && c->langevin_cached && c->nlist_valid && c->use_graph &&
-                 c->profiling < 2 && c->nranks == 1;
+                 c->profiling < 2;
     float *px = nullptr, *pv = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         if ((x_in || v_in) && pass == 0) MDK_TRY(host_state_in(c, x_in, v_in, m));

@@ -155,6 +155,7 @@ struct mdk_ctx {
     bool use_graph = true, in_capture = false;
     bool capture_energy = false;              // the step graph being captured carries the pair-kernel energy sums
     int graph_pending = 0;                    // graph steps queued whose bookkeeping (graph_finish) is still due
+    bool graph_pending_hosted = false;        // ... with host-launched force / update kernels (multi-GPU)
     bool graph_nccl = false;                  // capture the per-step ncclAllReduce into the step graph (N > 1): hung at N = 2 in round 1, off
     bool graph_energy = false;                // energies in every graph step (the energy-less k_pair variant measured 18 % slower at 92k atoms: ptxas schedules it worse)
     bool xs_current = false;                  // tile-order positions already match x_cur (integrator just published them)

@@ -674,8 +674,12 @@ __global__ void k_set_word(unsigned long long *p, unsigned long long v) { *p = v
 
 // nsteps force evaluations as graph launches: nsteps - 1 steady-state steps (finish v of the pending
 // step, advance x) and a last one that only finishes v and carries the energies.
+//
+// hosted = true (multi-GPU): only the list upkeep (k_decide -> IF { rebuild }) is a graph; the force
+// kernels, the NCCL all-reduce and the Langevin update are launched from the host, still without a
+// single host synchronisation inside the run (the rebuild decision stays on the device).
 static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, double tg, uint64_t seed, unsigned terms,
-                              int nsteps) {
+                              int nsteps, bool hosted) {
     if (!c->graph_pools) {           // first use: re-plan the pools with graph slack, on the host
         c->graph_pools = true;
         c->nlist_valid = false;
@@ -698,6 +702,23 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
         c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_key[2] = (double)seed; c->graph_key[3] = (double)terms;
         c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
     }
+    if (hosted) {
+        const int n = c->n, T = 256, B = (n + T - 1) / T;
+        StepGeom g = make_geom(c);
+        for (int s = 0; s < nsteps; ++s) {
+            const bool last = s + 1 == nsteps;
+            MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
+            MDK_TRY(forces_enqueue(c, terms));
+            k_langevin<<<B, T, 0, c->stream>>>(n, last ? 1 : 3, dt, ca, cb, tg, seed, c->langevin_step + (uint64_t)s, nullptr,
+                                               nullptr, c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p,
+                                               c->f_prev.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
+            c->n_launches += 2;
+        }
+        c->n_pair_launches += nsteps;
+        c->graph_pending = nsteps;
+        c->graph_pending_hosted = true;
+        return MDK_OK;
+    }
     for (int v = 0; v < 2; ++v) {
         const bool need = v == 1 || nsteps > 1;
         if (need && !c->step_exec[v]) {
@@ -714,6 +735,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
         MDK_CUDA(c, cudaGraphLaunch(c->step_exec[last ? 1 : 0], c->stream));
     }
     c->graph_pending = nsteps;   // counters / flags come back with the energies (energies_enqueue)
+    c->graph_pending_hosted = false;
     return MDK_OK;
 }
 
@@ -729,8 +751,11 @@ int graph_finish(mdk_ctx *c) {
     c->rebuilds_seen = h_after[12];
     c->n_rebuilds += rebuilt;
     if (rebuilt > 0) { c->stat_units = h_after[13]; c->stat_chunks = h_after[14]; c->stat_masks = h_after[15]; }
-    c->n_launches += (int64_t)nsteps * c->graph_launches_per_step + (int64_t)rebuilt * 9;
-    c->n_pair_launches += nsteps;
+    c->n_launches += (int64_t)rebuilt * 9;
+    if (!c->graph_pending_hosted) {
+        c->n_launches += (int64_t)nsteps * c->graph_launches_per_step;
+        c->n_pair_launches += nsteps;
+    }
     if (h_flags[3] & 1) return fail(c, MDK_ERR_OOM, "tile-list pool overflow inside a graph step (raise the pools: more atoms per box than planned)");
     if (h_flags[3] & 2) return fail(c, MDK_ERR_NLIST_STALE, "an i-block outgrew the hoisted-minimum-image bound inside a graph step");
     return MDK_OK;
@@ -752,7 +777,8 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
                                            c->xs.p, c->xs_ref.p, c->flags.p);                                   \
         ++c->n_launches;                                                                                        \
     } while (0)
-    const bool use_graph = c->use_graph && c->profiling < 2 && (c->nranks == 1 || c->graph_nccl) && nsteps >= graph_min_steps;
+    const bool use_graph = c->use_graph && c->profiling < 2 && nsteps >= graph_min_steps;
+    const bool hosted = c->nranks > 1 && !c->graph_nccl;   // NCCL stays out of the captured step (it hung there)
     if (!c->langevin_cached) {
         MDK_TRY(compute_terms(c, terms, false));  // f(x_0)
         LANGEVIN(2);
@@ -769,7 +795,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
     }
     ++c->langevin_step;
     if (use_graph) {
-        MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps));
+        MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps, hosted));
     } else {
         for (int s = 0; s < nsteps; ++s) {
             MDK_TRY(compute_terms(c, terms, false));  // f(x_n+1)

@@ -186,8 +186,11 @@ int mdk_create(int device, mdk_ctx **out) {
         return fail(nullptr, MDK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
-    cudaStreamCreateWithFlags(&c->s_pme, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking);
+    // the short side-stream kernels (PME mesh chain, bonded terms) go ahead of queued k_pair blocks
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&c->s_pme, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, prio_hi);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_pme, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
@@ -709,6 +712,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 1: c->concurrent = value != 0; break;         // PME / bonded on side streams
         case 2: c->force_canonical = value != 0; break;
         case 3: c->graph_energy = value != 0; break;       // energies in every graph step
+        case 5: c->pair_blocks_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value); break;
         case 4: c->graph_nccl = value != 0; break;         // graph steps with the NCCL all-reduce inside (N > 1)    // per-pair canonical minimum image even in large boxes
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }

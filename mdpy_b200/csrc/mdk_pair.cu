@@ -259,7 +259,7 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     const bool sw = do_lj && c->r_switch < c->rc_lj;
     const bool shift = c->shift_ok && !c->force_canonical;
     const bool onecut = !(do_lj && do_coul) || c->rc_lj == c->rc_coul;
-    int grid = c->sm_count * 4;
+    int grid = c->sm_count * c->pair_blocks_per_sm;
     long long max_blocks = (c->stat_units + PAIR_WARPS - 1) / PAIR_WARPS;
     if (max_blocks < 1) max_blocks = 1;
     if (grid > max_blocks && !c->in_capture) grid = (int)max_blocks;   // a captured launch must fit any later list

@@ -232,6 +232,7 @@ def run_b200(args, cfg):
     terms = 0
     for c in ens.constraints:
         terms |= c.terms
+    terms &= int(os.environ.get('MDK_TERMS_MASK', '0xffff'), 0)   # experiments: drop force terms from the direct step calls
 
     # ---- per-phase profile (separate untimed pass; per-phase events add syncs) ----
     prof_steps = 50 if n > 200000 else 200
@@ -319,6 +320,11 @@ def run_b200(args, cfg):
         return
 
     peaks = measured_peaks()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json'))).get(args.config)
+    except (OSError, ValueError):
+        pass
     fp32_peak = 148 * 128 * 2 * peaks['sm_max_mhz'] * 1e6 / 1e12
     pair_ms_n = ph_n['pair_ms'] / prof_steps
     # this rank evaluates its share of the pair slots; at N=1 that is everything
@@ -356,7 +362,9 @@ def run_b200(args, cfg):
                  gpu_launches_per_step=e2e_launches, potential_energy_last_step=e2e_energy,
                  path='LangevinIntegrator.integrate(ensemble, 1) per step: host State (float32 positions + velocities, '
                       'page-locked) -> mdk_step_langevin_host -> host State + energies; wall clock, max over ranks'),
-        roofline=dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak, traffic=None,
+        roofline=dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak,
+                      traffic=None if traffic is None or world > 1 else traffic['bytes'],
+                      traffic_source=None if traffic is None or world > 1 else traffic['source'] + ' (ncu dram bytes read + written per launch)',
                       kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=pair_ms_n,
                       peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source'],
                       note='rank 0 share of the pair work at N > 1' if world > 1 else 'whole pair kernel'),

@@ -224,7 +224,7 @@ void mdk_destroy(mdk_ctx *c) {
     c->cell_key.release(); c->cell_key_sorted.release(); c->idx_tmp.release(); c->cell_start.release();
     c->sort_tmp.release(); c->sort_buf.release(); c->bb_center.release(); c->bb_half.release();
     c->units.release(); c->chunk_j.release(); c->chunk_mask.release(); c->mask_excl.release(); c->mask_14.release();
-    c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release();
+    c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release(); c->fft_tw.release();
     c->io_dev.release();
     if (c->io_host) cudaFreeHost(c->io_host);
     if (c->pin_words) cudaFreeHost(c->pin_words);
@@ -712,6 +712,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 1: c->concurrent = value != 0; break;         // PME / bonded on side streams
         case 2: c->force_canonical = value != 0; break;
         case 3: c->graph_energy = value != 0; break;       // energies in every graph step
+        case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;
         case 5: c->pair_blocks_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value); break;
         case 4: c->graph_nccl = value != 0; break;         // graph steps with the NCCL all-reduce inside (N > 1)    // per-pair canonical minimum image even in large boxes
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);

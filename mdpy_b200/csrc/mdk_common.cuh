@@ -148,6 +148,9 @@ struct mdk_ctx {
     mdk::DevBuf<float> grid_r;                // real mesh
     mdk::DevBuf<float2> grid_c;               // half spectrum
     mdk::DevBuf<float> influence;             // G(m) on the half spectrum
+    mdk::DevBuf<float2> fft_tw;               // twiddles of the small-mesh FFT kernels
+    bool pme_fast = false;                    // every mesh axis a power of two in 8..64: own fused FFT kernels instead of cuFFT
+    bool pme_force_cufft = false;             // test hook: cuFFT also for small power-of-two meshes
     cufftHandle plan_r2c = 0, plan_c2r = 0;
     bool have_plans = false;
     double e_self_bg = 0.0;
@@ -242,7 +245,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
 int energies_enqueue(mdk_ctx *c);                    // kinetic energy + all-reduce + D2H into pin_words (no sync)
 void energies_finish(mdk_ctx *c, unsigned terms);    // after the stream was synchronised
 int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);
-int forces_enqueue(mdk_ctx *c, unsigned terms);
+int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry);
 void graph_destroy(mdk_ctx *c);
 int graph_finish(mdk_ctx *c);                        // counters / sticky errors of a queued graph run, after a sync
 int comm_allreduce_forces(mdk_ctx *c);

@@ -15,6 +15,8 @@
 // Spreading accumulates in int64 fixed point (scale 2^40) with `red.global.add.u64`, so the
 // mesh — and with it the whole force evaluation — is bitwise reproducible run to run; the
 // conversion kernel turns the mesh into fp32 for cuFFT and clears it for the next step.
+#include <algorithm>
+
 #include "mdk_common.cuh"
 
 namespace mdk {
@@ -162,6 +164,183 @@ __global__ void k_gather(PmeParams p, const float4 *__restrict__ xs, const float
     atomic_add_fix(&f_acc[3 * (size_t)i + 2], to_fix(-a.w * p.scale[2] * fz));
 }
 
+
+// ---------------------------------------------------------------------------
+// Small power-of-two meshes (every axis 8..64): the whole mesh chain between spreading and gathering
+// in three launches instead of cuFFT's six plus two of ours — at 64^3 those eight kernels are 3-5 us
+// each, pure launch latency, and sit on the critical path of the 23k-atom step.
+//   k_mesh_fwd_yz   one block per x-plane: int64 mesh -> float (and clear), 2-D FFT over (y, z)
+//   k_mesh_x_conv   one block per y: FFT over x, influence function + energy, inverse FFT over x
+//   k_mesh_inv_yz   one block per x-plane: inverse 2-D FFT over (y, z), real part -> potential mesh
+// Complex-to-complex on the full spectrum (the mesh is 2 MB: redundancy is cheaper than a launch).
+// The FFTs run in shared memory without any reordering pass: forward transforms are decimation in
+// frequency (natural order in, bit-reversed out), inverse transforms decimation in time (bit-reversed in,
+// natural out), so the spectrum simply lives in bit-reversed order between the kernels and only the
+// influence-function lookup has to un-reverse its indices.  Two radix-2 stages are fused per pass over
+// the tile (four points per thread in registers).  tw[k] = exp(-+ 2 pi i k / 64), k < 32.
+constexpr int FFT_NMAX = 64;
+constexpr int MESH_T = 1024;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// element (b, k) of sequence b lives at s[b * sb + k * sk]; nb = 1 << lognb sequences of length 1 << logn.
+// over_batch: consecutive threads walk the batch index (the unit-stride direction of a strided axis).
+template <bool INVERSE>
+__device__ __forceinline__ void smem_fft(float2 *s, int logn, int lognb, int sb, int sk, const float2 *tw, bool over_batch) {
+    const int n = 1 << logn, nb = 1 << lognb;
+    if (!INVERSE) {
+        int h = n >> 1;   // half size of the next stage
+        for (; h >= 2; h >>= 2) {          // fused stages (h, h / 2)
+            const int Q = h >> 1, logQ = 31 - __clz(Q);
+            for (int t = threadIdx.x; t < (nb << (logn - 2)); t += blockDim.x) {
+                int b, q;
+                if (over_batch) { b = t & (nb - 1); q = t >> lognb; } else { q = t & ((n >> 2) - 1); b = t >> (logn - 2); }
+                const int pos = q & (Q - 1), i0 = ((q >> logQ) << (logQ + 2)) + pos;
+                float2 *p = s + b * sb + i0 * sk;
+                const int st = Q * sk;
+                float2 e0 = p[0], e1 = p[st], e2 = p[2 * st], e3 = p[3 * st];
+                const float2 wa = tw[pos * (16 >> logQ)], wb = tw[pos * (16 >> logQ) + 16], wc = tw[pos * (32 >> logQ)];
+                const float2 a0 = cadd(e0, e2), a2 = cmul(csub(e0, e2), wa), a1 = cadd(e1, e3), a3 = cmul(csub(e1, e3), wb);
+                p[0] = cadd(a0, a1); p[st] = cmul(csub(a0, a1), wc);
+                p[2 * st] = cadd(a2, a3); p[3 * st] = cmul(csub(a2, a3), wc);
+            }
+            __syncthreads();
+        }
+        if (h == 1) {                      // odd number of stages: last one is a plain butterfly
+            for (int t = threadIdx.x; t < (nb << (logn - 1)); t += blockDim.x) {
+                int b, j;
+                if (over_batch) { b = t & (nb - 1); j = t >> lognb; } else { j = t & ((n >> 1) - 1); b = t >> (logn - 1); }
+                float2 *p = s + b * sb + 2 * j * sk;
+                const float2 a = p[0], c = p[sk];
+                p[0] = cadd(a, c); p[sk] = csub(a, c);
+            }
+            __syncthreads();
+        }
+    } else {
+        int Q = 1;
+        if (logn & 1) {
+            for (int t = threadIdx.x; t < (nb << (logn - 1)); t += blockDim.x) {
+                int b, j;
+                if (over_batch) { b = t & (nb - 1); j = t >> lognb; } else { j = t & ((n >> 1) - 1); b = t >> (logn - 1); }
+                float2 *p = s + b * sb + 2 * j * sk;
+                const float2 a = p[0], c = p[sk];
+                p[0] = cadd(a, c); p[sk] = csub(a, c);
+            }
+            __syncthreads();
+            Q = 2;
+        }
+        for (; 4 * Q <= n; Q <<= 2) {      // fused stages (Q, 2 Q)
+            const int logQ = 31 - __clz(Q);
+            for (int t = threadIdx.x; t < (nb << (logn - 2)); t += blockDim.x) {
+                int b, q;
+                if (over_batch) { b = t & (nb - 1); q = t >> lognb; } else { q = t & ((n >> 2) - 1); b = t >> (logn - 2); }
+                const int pos = q & (Q - 1), i0 = ((q >> logQ) << (logQ + 2)) + pos;
+                float2 *p = s + b * sb + i0 * sk;
+                const int st = Q * sk;
+                float2 e0 = p[0], e1 = p[st], e2 = p[2 * st], e3 = p[3 * st];
+                const float2 wc = tw[pos * (32 >> logQ)], wa = tw[pos * (16 >> logQ)], wb = tw[pos * (16 >> logQ) + 16];
+                const float2 t1 = cmul(e1, wc), t3 = cmul(e3, wc);
+                const float2 a0 = cadd(e0, t1), a1 = csub(e0, t1), a2 = cadd(e2, t3), a3 = csub(e2, t3);
+                const float2 u2 = cmul(a2, wa), u3 = cmul(a3, wb);
+                p[0] = cadd(a0, u2); p[2 * st] = csub(a0, u2);
+                p[st] = cadd(a1, u3); p[3 * st] = csub(a1, u3);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct MeshDims { int nx, ny, nz, lx, ly, lz; };
+
+__global__ void __launch_bounds__(MESH_T)
+k_mesh_fwd_yz(MeshDims d, long long *__restrict__ fix, float2 *__restrict__ spec, const float2 *__restrict__ tw_g) {
+    extern __shared__ float2 sm[];
+    float2 *tw = sm, *tile = sm + 32;
+    if (threadIdx.x < 32) tw[threadIdx.x] = tw_g[threadIdx.x];
+    const int plane = d.ny * d.nz;
+    long long *src = fix + (size_t)blockIdx.x * plane;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < plane; i += MESH_T) {
+        const long long v = src[i];
+        tile[i] = make_float2((float)((double)v * (1.0 / FIX_SCALE)), 0.f);
+        if (v != 0) src[i] = 0;
+    }
+    __syncthreads();
+    smem_fft<false>(tile, d.lz, d.ly, d.nz, 1, tw, false);
+    smem_fft<false>(tile, d.ly, d.lz, 1, d.nz, tw, true);
+    float2 *dst = spec + (size_t)blockIdx.x * plane;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < plane; i += MESH_T) dst[i] = tile[i];
+}
+
+__global__ void __launch_bounds__(MESH_T)
+k_mesh_x_conv(MeshDims d, float2 *__restrict__ spec, const float *__restrict__ G, const float2 *__restrict__ tw_g,
+              long long *__restrict__ e_acc) {
+    extern __shared__ float2 sm[];
+    float2 *twf = sm, *twi = sm + 32, *tile = sm + 64;   // tile[x][z] for this block's y position
+    if (threadIdx.x < 64) sm[threadIdx.x] = tw_g[threadIdx.x];
+    const int yp = blockIdx.x, nzc = d.nz / 2 + 1, cnt = d.nx * d.nz;
+    const int ky = (int)(__brev((unsigned)yp) >> (32 - d.ly));          // the spectrum sits in bit-reversed order
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt; i += MESH_T) {
+        const int x = i >> d.lz, z = i & (d.nz - 1);
+        tile[i] = spec[(((size_t)x << d.ly) + yp) * d.nz + z];
+    }
+    __syncthreads();
+    smem_fft<false>(tile, d.lx, d.lz, 1, d.nz, twf, true);
+    double e = 0.0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt; i += MESH_T) {
+        const int xp = i >> d.lz, zp = i & (d.nz - 1);
+        const int kx = (int)(__brev((unsigned)xp) >> (32 - d.lx)), kz = (int)(__brev((unsigned)zp) >> (32 - d.lz));
+        const float g = G[((size_t)kx * d.ny + ky) * nzc + (2 * kz <= d.nz ? kz : d.nz - kz)];
+        const float2 c = tile[i];
+        e += 0.5 * (double)(g * (c.x * c.x + c.y * c.y));
+        tile[i] = make_float2(c.x * g, c.y * g);
+    }
+    __syncthreads();
+    smem_fft<true>(tile, d.lx, d.lz, 1, d.nz, twi, true);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt; i += MESH_T) {
+        const int x = i >> d.lz, z = i & (d.nz - 1);
+        spec[(((size_t)x << d.ly) + yp) * d.nz + z] = tile[i];
+    }
+    // per-thread fixed point, integer sums: the energy does not depend on the reduction order
+    long long v = warp_sum_ll(to_fix(e));
+    if ((threadIdx.x & 31) == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_PME_RECIP], v);
+}
+
+__global__ void __launch_bounds__(MESH_T)
+k_mesh_inv_yz(MeshDims d, const float2 *__restrict__ spec, float *__restrict__ phi, const float2 *__restrict__ tw_g) {
+    extern __shared__ float2 sm[];
+    float2 *tw = sm, *tile = sm + 32;
+    if (threadIdx.x < 32) tw[threadIdx.x] = tw_g[32 + threadIdx.x];
+    const int plane = d.ny * d.nz;
+    const float2 *src = spec + (size_t)blockIdx.x * plane;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < plane; i += MESH_T) tile[i] = src[i];
+    __syncthreads();
+    smem_fft<true>(tile, d.ly, d.lz, 1, d.nz, tw, true);
+    smem_fft<true>(tile, d.lz, d.ly, d.nz, 1, tw, false);
+    float *dst = phi + (size_t)blockIdx.x * plane;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < plane; i += MESH_T) dst[i] = tile[i].x;
+}
+
+static int ilog2_exact(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return (1 << l) == n ? l : -1;
+}
+static bool mesh_fast_ok(const mdk_ctx *c) {
+    if (c->pme_force_cufft) return false;
+    for (int a = 0; a < 3; ++a)
+        if (c->pme_n[a] < 8 || c->pme_n[a] > FFT_NMAX || ilog2_exact(c->pme_n[a]) < 0) return false;
+    return true;
+}
+
 // ---------------------------------------------------------------------------
 // host: influence function.  M_P at the integers by the cardinal B-spline recursion.
 static void bspline_moduli(int n, int P, std::vector<double> &mod) {
@@ -226,10 +405,29 @@ int pme_prepare(mdk_ctx *c) {
     MDK_CUDA(c, cudaMemcpyAsync(c->influence.p, G.data(), totc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); c->have_plans = false; }
-    if (cufftPlan3d(&c->plan_r2c, nx, ny, nz, CUFFT_R2C) != CUFFT_SUCCESS ||
-        cufftPlan3d(&c->plan_c2r, nx, ny, nz, CUFFT_C2R) != CUFFT_SUCCESS)
-        return fail(c, MDK_ERR_CUDA, "cufftPlan3d(%d,%d,%d) failed", nx, ny, nz);
-    c->have_plans = true;
+    c->pme_fast = mesh_fast_ok(c);
+    if (c->pme_fast) {
+        // full complex spectrum in grid_c, twiddles exp(-+ 2 pi i k / 64)
+        MDK_CUDA(c, c->grid_c.reserve(total));
+        MDK_CUDA(c, c->fft_tw.reserve(64));
+        float2 tw[64];
+        for (int k = 0; k < 32; ++k) {
+            const double a = 2.0 * M_PI * k / FFT_NMAX;
+            tw[k] = make_float2((float)cos(a), (float)-sin(a));
+            tw[32 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        MDK_CUDA(c, cudaMemcpyAsync(c->fft_tw.p, tw, sizeof(tw), cudaMemcpyHostToDevice, c->stream));
+        MDK_CUDA(c, cudaStreamSynchronize(c->stream));
+        const int smem = (64 + std::max(ny * nz, nx * nz)) * (int)sizeof(float2);
+        MDK_CUDA(c, cudaFuncSetAttribute(k_mesh_fwd_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MDK_CUDA(c, cudaFuncSetAttribute(k_mesh_x_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MDK_CUDA(c, cudaFuncSetAttribute(k_mesh_inv_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    } else {
+        if (cufftPlan3d(&c->plan_r2c, nx, ny, nz, CUFFT_R2C) != CUFFT_SUCCESS ||
+            cufftPlan3d(&c->plan_c2r, nx, ny, nz, CUFFT_C2R) != CUFFT_SUCCESS)
+            return fail(c, MDK_ERR_CUDA, "cufftPlan3d(%d,%d,%d) failed", nx, ny, nz);
+        c->have_plans = true;
+    }
     c->pme_dirty = false;
     return MDK_OK;
 }
@@ -244,6 +442,30 @@ static int pme_run(mdk_ctx *c) {
         p.scale[a] = (float)(c->pme_n[a] / c->box.Ld[a]);
     }
     size_t total = (size_t)p.nx * p.ny * p.nz, totc = (size_t)p.nx * p.ny * p.nzc;
+    if (c->pme_fast) {
+        {
+            PhaseTimer pt(c, PH_SPREAD);
+            k_spread<P><<<(c->n + 127) / 128, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p);
+            c->n_launches += 1;
+        }
+        {
+            PhaseTimer pt(c, PH_FFT);
+            MeshDims d{p.nx, p.ny, p.nz, ilog2_exact(p.nx), ilog2_exact(p.ny), ilog2_exact(p.nz)};
+            const size_t smem = (64 + (size_t)std::max(p.ny * p.nz, p.nx * p.nz)) * sizeof(float2);
+            k_mesh_fwd_yz<<<p.nx, MESH_T, smem, c->stream>>>(d, c->grid_fix.p, c->grid_c.p, c->fft_tw.p);
+            k_mesh_x_conv<<<p.ny, MESH_T, smem, c->stream>>>(d, c->grid_c.p, c->influence.p, c->fft_tw.p,
+                                                         reinterpret_cast<long long *>(c->e_acc.p));
+            k_mesh_inv_yz<<<p.nx, MESH_T, smem, c->stream>>>(d, c->grid_c.p, c->grid_r.p, c->fft_tw.p);
+            c->n_launches += 3;
+        }
+        {
+            PhaseTimer pt(c, PH_GATHER);
+            k_gather<P><<<(c->n + 127) / 128, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p);
+            c->n_launches += 1;
+        }
+        MDK_CUDA(c, cudaGetLastError());
+        return MDK_OK;
+    }
     cufftSetStream(c->plan_r2c, c->stream);
     cufftSetStream(c->plan_c2r, c->stream);
     {

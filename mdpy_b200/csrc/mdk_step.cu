@@ -287,9 +287,13 @@ int bonded_compute(mdk_ctx *c, unsigned terms) {
 // term dispatcher
 // Device work of one force evaluation on a valid tile list: enqueue only, no host synchronisation,
 // fixed launch shapes (this is what a CUDA-graph step captures).
-int forces_enqueue(mdk_ctx *c, unsigned terms) {
-    MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
-    MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
+// clean_on_entry: the accumulators are already zero (steps of a graph run: k_decide clears the energies,
+// the Langevin update clears each force after consuming it), so the two memset nodes are left out.
+int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry) {
+    if (!clean_on_entry) {
+        MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
+        MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
+    }
     // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units and its range of
     // the bonded / excluded-pair terms; bare Coulomb runs on rank 0, the PME mesh on the last rank
     const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
@@ -330,7 +334,7 @@ int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
     if (!c->xs_current) MDK_TRY(nlist_refresh_sorted(c));
     MDK_TRY(nlist_ensure(c));
     c->xs_current = true;
-    MDK_TRY(forces_enqueue(c, terms));
+    MDK_TRY(forces_enqueue(c, terms, false));
     if (sync_energies) {
         MDK_TRY(comm_allreduce_energies(c));
         long long h[MDK_NUM_ENERGIES];
@@ -446,7 +450,7 @@ __global__ void k_verlet_velocity(int n, int quirks, double dt, const int *__res
 __global__ void k_langevin(int n, int mode, double dt, double ca, double cb, double two_g_kT_dt,
                            uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_dev,
                            const unsigned long long *__restrict__ mode_dev, const int *__restrict__ order,
-                           const float *__restrict__ mass, const long long *__restrict__ f_acc,
+                           const float *__restrict__ mass, long long *__restrict__ f_acc,
                            double *__restrict__ x_cur, double *__restrict__ vel, double *__restrict__ f_prev,
                            StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
                            int *__restrict__ flags) {
@@ -478,6 +482,12 @@ __global__ void k_langevin(int n, int mode, double dt, double ca, double cb, dou
     if (!(mode & 4)) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) f_prev[3 * a + d] = f_new[d];
+    }
+    // another step follows (finish + advance): leave the accumulator clean for it; after the last step of
+    // a call the forces stay readable (mdk_download_forces)
+    if (mode == 3) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f_acc[3 * (size_t)k + d] = 0;
     }
     if (mode & 2) {
         double xi[3], xn[3];
@@ -563,10 +573,15 @@ int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quir
 // them.  The steady-state Langevin step is therefore captured once into a graph whose rebuild
 // branch is a conditional (IF) node driven from the device: k_decide reads the skin/2 flag the
 // previous step's position update raised and arms the branch; its body is the whole list rebuild.
-__global__ void k_decide(cudaGraphConditionalHandle handle, const int *__restrict__ flags) {
+// ... and does the per-step housekeeping that would otherwise be graph nodes of their own: advance the
+// device-side noise counter, clear the energy accumulators for the step that follows.
+__global__ void k_decide(cudaGraphConditionalHandle handle, const int *__restrict__ flags,
+                         unsigned long long *__restrict__ step_dev, long long *__restrict__ e_acc) {
     cudaGraphSetConditional(handle, flags[1] != 0 ? 1u : 0u);
+    *step_dev += 1ull;
+#pragma unroll
+    for (int k = 0; k < MDK_NUM_ENERGIES; ++k) e_acc[k] = 0;
 }
-__global__ void k_tick(unsigned long long *step_dev) { *step_dev += 1ull; }
 
 void graph_destroy(mdk_ctx *c) {
     for (int v = 0; v < 2; ++v) {
@@ -603,7 +618,7 @@ static int graph_build_upkeep(mdk_ctx *c) {
     CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
     cudaGraphConditionalHandle handle;
     CAP(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
-    k_decide<<<1, 1, 0, s>>>(handle, c->flags.p);
+    k_decide<<<1, 1, 0, s>>>(handle, c->flags.p, c->step_dev.p, reinterpret_cast<long long *>(c->e_acc.p));
     CAP(cudaStreamGetCaptureInfo_v2(s, &status, &id, &graph, &deps, &ndeps));
     cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
     cp.conditional.handle = handle;
@@ -650,20 +665,18 @@ static int graph_build_step(mdk_ctx *c, int variant, double dt, double ca, doubl
     cudaGraph_t graph = nullptr;
     CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
     if (rc == MDK_OK) {
-        rc = forces_enqueue(c, terms);
-        if (rc == MDK_OK) {
+        rc = forces_enqueue(c, terms, true);
+        if (rc == MDK_OK)
             k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->step_dev.p + 1, c->order.p,
                                        c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p,
                                        c->xs_ref.p, c->flags.p);
-            k_tick<<<1, 1, 0, s>>>(c->step_dev.p);
-        }
         cudaError_t e = cudaStreamEndCapture(s, &graph);
         if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
     }
     c->in_capture = false;
     c->capture_energy = false;
     c->stream = s;
-    c->graph_launches_per_step = (int)(c->n_launches - launches_before) + 3;   // + decide, langevin, tick
+    c->graph_launches_per_step = (int)(c->n_launches - launches_before) + 2;   // + decide, langevin
     c->n_launches = launches_before; c->n_pair_launches = pair_before;         // capturing is not launching
     if (rc != MDK_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
     c->step_graph[variant] = graph;
@@ -705,13 +718,16 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
         c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_key[2] = (double)seed; c->graph_key[3] = (double)terms;
         c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
     }
+    // the steps of a run find the force accumulator clean: zeroed here once, then by every Langevin update
+    // that is followed by another step
+    MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
     if (hosted) {
         const int n = c->n, T = 256, B = (n + T - 1) / T;
         StepGeom g = make_geom(c);
         for (int s = 0; s < nsteps; ++s) {
             const bool last = s + 1 == nsteps;
             MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
-            MDK_TRY(forces_enqueue(c, terms));
+            MDK_TRY(forces_enqueue(c, terms, true));
             k_langevin<<<B, T, 0, c->stream>>>(n, last ? 1 : 3, dt, ca, cb, tg, seed, c->langevin_step + (uint64_t)s, nullptr,
                                                nullptr, c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p,
                                                c->f_prev.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
@@ -729,7 +745,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
             if (rc != MDK_OK) { graph_destroy(c); c->graph_epoch_built = -1; return rc; }
         }
     }
-    unsigned long long h_words[2] = {c->langevin_step, nsteps == 1 ? 1ull : 3ull};
+    unsigned long long h_words[2] = {c->langevin_step - 1ull, nsteps == 1 ? 1ull : 3ull};   // k_decide ticks before each step
     MDK_CUDA(c, cudaMemcpyAsync(c->step_dev.p, h_words, sizeof(h_words), cudaMemcpyHostToDevice, c->stream));
     for (int s = 0; s < nsteps; ++s) {
         const bool last = s + 1 == nsteps;

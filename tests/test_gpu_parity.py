@@ -286,6 +286,24 @@ def test_pme_converges_to_exact_ewald():
     assert abs(pme.potential_energy - e_ex) < ENERGY_TOL * np.abs(e[1:5]).sum()
 
 
+def test_small_mesh_fft_kernels_match_cufft():
+    """Power-of-two meshes up to 64 per axis run the fused mesh kernels (mdk_pme.cu: k_mesh_*); the cuFFT
+    chain on the same mesh is the check (option pme_cufft), on a non-cubic mesh so that every axis has its
+    own length."""
+    g = load_golden('mix_small_f64')
+    res = []
+    for use_cufft in (0, 1):
+        ens = ensemble_from_golden(g)
+        pme = ElectrostaticPMEConstraint(cutoff_radius=9.0, alpha=0.32, grid=(32, 64, 16), order=4)
+        ens.add_constraints(pme)
+        pme._ctx.dev.set_option('pme_cufft', use_cufft)
+        pme.update()
+        res.append((pme.forces.astype(np.float64), pme.potential_energy, pme._ctx.dev.last_energies()[2]))
+    assert rel_rms(res[0][0], res[1][0]) < 2e-6
+    assert res[0][2] == pytest.approx(res[1][2], rel=1e-6)
+    assert res[0][1] == pytest.approx(res[1][1], rel=1e-6, abs=1e-6 * abs(res[1][2]))
+
+
 def test_results_are_bitwise_reproducible():
     g = load_golden('mix_small_f64')
     out = []

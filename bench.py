@@ -379,6 +379,14 @@ def run_b200(args, cfg):
     )
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    try:   # recorded, not live: the reference's own numba.cuda path on one B200 (baseline/ref_numba_cuda.py)
+        rec = json.load(open(os.path.join(ROOT, 'profiles', 'r01_reference_numba_cuda.json'))).get(args.config)
+        if rec:
+            line['reference_numba_cuda_recorded'] = dict(
+                atom_steps_per_s=rec['atom_steps_per_s'], ns_per_day=rec['ns_per_day_at_2fs'], seconds_per_step=rec['seconds_per_step'],
+                source='profiles/r01_reference_numba_cuda.json (unmodified reference, one B200, plain-cutoff LJ + bare Coulomb, no PME)')
+    except (OSError, ValueError):
+        pass
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

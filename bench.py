@@ -107,53 +107,67 @@ def build_system(cfg):
 
 
 # ---------------------------------------------------------------------------------------------
+class ReferenceSampler:
+    """One step of the reference's CPU path (LJ over its 27-cell list + all-pairs Coulomb, both restated
+    in C in oracle/), timed on a bounded slice of the outer atom loop and scaled to all N atoms."""
+
+    def __init__(self, system, cfg, threads):
+        from oracle import cpu_oracle as ora
+        self.ora, self.cfg, self.threads = ora, cfg, threads
+        self.n = system.num_particles
+        self.topo = system.topology()
+        self.pos = system.positions.astype(np.float32)
+        self.pbc = np.diag(system.box).astype(np.float32)
+        self.table = system.lj_table()
+        self.k = 4 * np.pi * float(np.float32(0.5727653))
+        self.per_atom = None
+
+    def _run(self, m):
+        """(t_lj, t_coulomb) for atoms [0, m) of the outer loops."""
+        o, t = self.ora, self.topo
+        t0 = time.perf_counter()
+        o.lj_cell(self.pos, self.table, self.pbc, self.cfg['cutoff'], t.bonded_particles, t.scaling_particles,
+                  cell_cutoff=12.0, i_range=(0, m), threads=self.threads)
+        t1 = time.perf_counter()
+        o.coulomb_allpairs(self.pos, t.charges, self.pbc, t.bonded_particles, self.k, i_range=(0, m), threads=self.threads)
+        return t1 - t0, time.perf_counter() - t1
+
+    def step(self, budget_s):
+        """Seconds per full step estimated from a sample sized to budget_s, and the sample description."""
+        n = self.n
+        floor = max(self.threads * 8, min(n, 64))
+        if self.per_atom is None:   # calibrate once on a small slice
+            probe = max(floor, min(n, 256))
+            self.per_atom = sum(self._run(probe)) / probe
+        m = int(min(n, max(floor, budget_s / max(self.per_atom, 1e-9))))
+        t_lj, t_c = self._run(m)
+        # LJ is linear in the slice; the all-pairs loop is triangular: slice [0, m) covers
+        # m n - m(m+1)/2 of the n(n-1)/2 pairs
+        frac_c = (m * n - m * (m + 1) / 2.0) / (n * (n - 1) / 2.0)
+        full = t_lj * n / m + t_c / frac_c
+        sample = ('atoms [0,%d) of %d of the outer loops of LJ (27-cell list, rc %.0f A) and all-pairs Coulomb, fp32, '
+                  'scaled to N (LJ linear, Coulomb by pair count); reference semantics: no PME' % (m, n, self.cfg['cutoff']))
+        return full, sample
+
+
 def reference_step_seconds(system, cfg, threads, budget_s=12.0):
-    """One step of the reference's CPU path (LJ over its 27-cell list + all-pairs Coulomb, both
-    restated in C in oracle/), timed on a bounded slice of the outer atom loop and scaled to all N
-    atoms.  Returns (seconds per full step, sample description)."""
-    from oracle import cpu_oracle as ora
-    n = system.num_particles
-    topo = system.topology()
-    pos = system.positions.astype(np.float32)
-    pbc = np.diag(system.box).astype(np.float32)
-    table = system.lj_table()
-    k = 4 * np.pi * float(np.float32(0.5727653))
-    # calibrate on a small slice, then size the sample to the budget
-    probe = max(threads * 8, min(n, 256))
-    t0 = time.perf_counter()
-    ora.lj_cell(pos, table, pbc, cfg['cutoff'], topo.bonded_particles, topo.scaling_particles, cell_cutoff=12.0,
-                i_range=(0, probe), threads=threads)
-    ora.coulomb_allpairs(pos, topo.charges, pbc, topo.bonded_particles, k, i_range=(0, probe), threads=threads)
-    per_atom = (time.perf_counter() - t0) / probe
-    m = int(min(n, max(probe, budget_s / max(per_atom, 1e-9))))
-    t0 = time.perf_counter()
-    ora.lj_cell(pos, table, pbc, cfg['cutoff'], topo.bonded_particles, topo.scaling_particles, cell_cutoff=12.0,
-                i_range=(0, m), threads=threads)
-    t_lj = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ora.coulomb_allpairs(pos, topo.charges, pbc, topo.bonded_particles, k, i_range=(0, m), threads=threads)
-    t_c = time.perf_counter() - t0
-    # LJ is linear in the slice; the all-pairs loop is triangular: slice [0, m) covers
-    # m n - m(m+1)/2 of the n(n-1)/2 pairs
-    frac_c = (m * n - m * (m + 1) / 2.0) / (n * (n - 1) / 2.0)
-    full = t_lj * n / m + t_c / frac_c
-    sample = ('atoms [0,%d) of %d of the outer loops of LJ (27-cell list, rc %.0f A) and all-pairs Coulomb, fp32, '
-              'scaled to N (LJ linear, Coulomb by pair count); reference semantics: no PME' % (m, n, cfg['cutoff']))
-    return full, sample
+    return ReferenceSampler(system, cfg, threads).step(budget_s)
 
 
 def run_reference(args, cfg):
-    """--impl reference: the reference's own CPU algorithm for the path on the host cores."""
+    """--impl reference: the reference's own CPU algorithm for the path on the host cores; every step is a
+    bounded sample of the workload, sized so that the whole run stays within ~150 s of CPU work."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     system = build_system(cfg)
     threads = os.cpu_count() or 1
-    per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    sampler = ReferenceSampler(system, cfg, threads)
+    per_step = min(12.0, 150.0 / max(1, args.steps + args.warmup))
     times = []
     sample = ''
     for it in range(args.warmup + args.steps):
-        t, sample = reference_step_seconds(system, cfg, threads, budget_s=per_step)
+        t, sample = sampler.step(per_step)
         if it >= args.warmup:
             times.append(t)
     sec = float(np.mean(times))

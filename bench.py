@@ -260,13 +260,15 @@ def run_b200(args, cfg):
     lj = ens.constraints[0]
     ens.state._positions = dev.download_positions()
     ctx._pos_rev = None
-    n_pairs = len(lj.neighbor_pairs())      # in-cutoff pair count of the current configuration (flop model)
+    lj._configure(); ctx.sync_positions()
+    n_pairs = dev.pair_count()               # in-cutoff pair count of the current configuration (flop model)
     slots_single = dev.timing()['j_chunks'] * 1024.0
 
     # ---- multi-GPU: join the communicator, deal i-blocks to ranks weighted by the extra roles ----
     weights = None
     if world > 1:
         weights = multigpu.role_weights(world, pair_ms + ph['nlist_ms'] / prof_steps, pme_ms, 0.0)   # bonded terms are split evenly
+        weights = multigpu.broadcast_array(dist, weights, rank)   # one set of shard ranges for all ranks
         multigpu.attach(ctx, dist, rank, world, weights)
     integ.integrate(ens, max(args.warmup, 3))
 

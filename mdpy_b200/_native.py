@@ -304,6 +304,12 @@ class Device:
                 return np.stack([oi[:cnt.value], oj[:cnt.value]], axis=1)
             cap = int(cnt.value)
 
+    def pair_count(self):
+        """Number of in-cutoff, non-excluded pairs of the current configuration (no pair arrays)."""
+        cnt = C.c_int64(0)
+        self._ck(self._lib.mdk_get_pairs(self._h, None, None, 0, C.byref(cnt)))
+        return int(cnt.value)
+
     def timing(self):
         t = np.zeros(24, dtype=np.float64)
         self._ck(self._lib.mdk_get_timing(self._h, _ptr(t)))

@@ -96,7 +96,21 @@ def attach(ctx, dist, rank, world, weights=None):
     finally:
         os.dup2(saved, 1)
         os.close(saved)
-    set_weights(ctx, rank, world, np.ones(world) if weights is None else weights)
+    # The shard ranges MUST be identical on every rank (a block owned twice is counted twice, a block owned
+    # by nobody is lost): weights derived from per-rank timings differ in their last digits, so rank 0's
+    # copy is the one everybody uses.
+    w = np.ones(world) if weights is None else np.asarray(weights, dtype=np.float64)
+    set_weights(ctx, rank, world, broadcast_array(dist, w, rank))
+
+
+def broadcast_array(dist, values, rank, src=0):
+    """float64 array from rank `src` to everybody (torch.distributed, either backend)."""
+    import torch
+    t = torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64).copy())
+    if dist.get_backend() == 'nccl':
+        t = t.cuda()
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()
 
 
 def set_weights(ctx, rank, world, weights):

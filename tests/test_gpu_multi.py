@@ -25,12 +25,12 @@ os.environ['MDPY_B200_DEVICE'] = str(local)
 from mdpy_b200 import synthetic, _native, multigpu
 from mdpy_b200.integrator import LangevinIntegrator
 s = synthetic.solvated_protein_box(20002, (60.0, 60.0, 60.0), protein_fraction=0.1, seed=3)
-def run(shard, canonical):
+def run(shard, canonical, pme_ms=40.0):
     ens = s.ensemble(cutoff=10.0, switch=8.0, pme=True, grid=(60, 60, 60))
     ctx = _native.context_of(ens)
     ctx.dev.set_option('canonical_min_image', 1 if canonical else 0)
     if shard:
-        multigpu.attach(ctx, dist, rank, world, multigpu.role_weights(world, 100.0, 40.0, 10.0))
+        multigpu.attach(ctx, dist, rank, world, multigpu.role_weights(world, 100.0, pme_ms, 10.0))
     ens.update()
     f0, e0 = ens.forces.copy(), ens.potential_energy
     LangevinIntegrator(1.0, 300, 0.01, seed=5).integrate(ens, 25)
@@ -42,9 +42,13 @@ c = run(False, False)
 d = run(True, False)
 dx = c[2] - d[2]; dx -= 60.0 * np.round(dx / 60.0)
 ok2 = (np.array_equal(c[0], d[0]), c[1] == d[1], bool(np.abs(dx).max() < 1e-3), bool(abs(c[3] - d[3]) < 1e-5 * abs(c[3])))
+# a PME rank so loaded that it gets no pair work at all (what an 8-GPU run of the 1M box does)
+z = run(True, True, pme_ms=4000.0)
+ok3 = (np.array_equal(a[0], z[0]), a[1] == z[1], np.array_equal(a[2], z[2]), a[3] == z[3])
 if rank == 0:
     print('MULTI', ok, float(np.abs(a[0] - b[0]).max()), a[1], b[1])
     print('HOIST', ok2, float(np.abs(dx).max()), c[3], d[3])
+    print('ZEROW', ok3, float(np.abs(a[2] - z[2]).max()), a[3], z[3])
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -65,4 +69,6 @@ def test_sharded_forces_and_trajectory_equal_single_gpu(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith('MULTI')][0]
     assert '(True, True, True, True)' in line, line
     line = [l for l in out.stdout.splitlines() if l.startswith('HOIST')][0]
+    assert '(True, True, True, True)' in line, line
+    line = [l for l in out.stdout.splitlines() if l.startswith('ZEROW')][0]
     assert '(True, True, True, True)' in line, line

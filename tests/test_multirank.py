@@ -49,7 +49,22 @@ def _worker(rank, world, port, q):
                 return bytes(range(128))
         uid = multigpu.broadcast_unique_id(dist, FakeDev(), rank)
         ok_uid = uid == bytes(range(128))
-        # 2. sharded partial forces -> fixed point -> all_reduce == single-rank result, bit for bit
+        # 2. per-rank timings differ in their last digits: the weights every rank uses must be rank 0's
+        #    (weights that differ between ranks give overlapping or missing shard ranges)
+        class FakeCtxDev:
+            def comm_init(self, *a): pass
+            def set_shard(self, lo, hi, mod): self.shard = (lo, hi, mod)
+            comm_unique_id = FakeDev.comm_unique_id
+        class FakeCtx:
+            dev = FakeCtxDev()
+        noisy = multigpu.role_weights(world, 70.0 + 3.0 * rank, 30.0 - 2.0 * rank, 0.0)
+        fc = FakeCtx()
+        multigpu.attach(fc, dist, rank, world, noisy)
+        mine_t = torch.tensor([fc.shard[0], fc.shard[1]]); both = [torch.zeros(2, dtype=mine_t.dtype) for _ in range(world)]
+        dist.all_gather(both, mine_t)
+        ranges = [tuple(int(v) for v in t) for t in both]
+        ok_uid = ok_uid and ranges == multigpu.shard_ranges(multigpu.role_weights(world, 70.0, 30.0, 0.0))
+        # 3. sharded partial forces -> fixed point -> all_reduce == single-rank result, bit for bit
         g = load_golden('mix_small_f64')
         n = g['positions'].shape[0]
         n_blocks = (n + 31) // 32

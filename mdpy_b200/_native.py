@@ -324,7 +324,7 @@ class Device:
 
     def set_option(self, key, value):
         """key: 'graph' | 'concurrent' | 'canonical_min_image'."""
-        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6}[key]
+        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6, 'graph_hosted': 7}[key]
         self._ck(self._lib.mdk_set_option(self._h, k, float(value)))
 
     def flush_l2(self):

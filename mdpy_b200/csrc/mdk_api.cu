@@ -622,7 +622,7 @@ int mdk_step_langevin_host(mdk_ctx *c, const float *x_in, const float *v_in, flo
     const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
     const uint64_t step0 = c->langevin_step;
     bool ahead = (x_in || v_in) && nsteps > 0 && c->have_pos && c->langevin_cached && c->nlist_valid && c->use_graph &&
-                 c->profiling < 2;
+                 c->profiling < 2 && (c->nranks == 1 || c->graph_nccl || c->graph_hosted);
     float *px = nullptr, *pv = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         if ((x_in || v_in) && pass == 0) MDK_TRY(host_state_in(c, x_in, v_in, m));
@@ -712,6 +712,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 1: c->concurrent = value != 0; break;         // PME / bonded on side streams
         case 2: c->force_canonical = value != 0; break;
         case 3: c->graph_energy = value != 0; break;       // energies in every graph step
+        case 7: c->graph_hosted = value != 0; break;
         case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;
         case 5: c->pair_blocks_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value); break;
         case 4: c->graph_nccl = value != 0; break;         // graph steps with the NCCL all-reduce inside (N > 1)    // per-pair canonical minimum image even in large boxes

@@ -68,6 +68,7 @@ void comm_destroy(mdk_ctx *c) {
     if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
     c->nccl_comm = nullptr;
     c->nranks = 1; c->rank = 0;
+    ++c->graph_epoch;
 }
 
 }  // namespace mdk
@@ -104,6 +105,7 @@ int mdk_comm_init(mdk_ctx *c, int rank, int nranks, const void *unique_id128) {
     c->nccl_comm = comm;
     c->rank = rank; c->nranks = nranks;
     c->nlist_valid = false;
+    ++c->graph_epoch;   // rank / nranks are baked into captured launches (term ranges, PME role)
     return MDK_OK;
 }
 
@@ -112,6 +114,10 @@ int mdk_set_shard(mdk_ctx *c, int lo, int hi, int modulus) {
     if (modulus < 1 || lo < 0 || hi > modulus || lo > hi) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_shard(%d, %d, %d)", lo, hi, modulus);
     c->shard_lo = lo; c->shard_hi = hi; c->shard_mod = modulus;
     c->nlist_valid = false;
+    // the shard range is a kernel argument of the list builder captured inside the upkeep graph: a graph
+    // captured before this call would keep building EVERY block's units on this rank (forces counted
+    // nranks times after the first in-graph rebuild)
+    ++c->graph_epoch;
     return MDK_OK;
 }
 

@@ -161,6 +161,9 @@ struct mdk_ctx {
     int graph_pending = 0;                    // graph steps queued whose bookkeeping (graph_finish) is still due
     bool graph_pending_hosted = false;        // ... with host-launched force / update kernels (multi-GPU)
     bool graph_nccl = false;                  // capture the per-step ncclAllReduce into the step graph (N > 1): hung at N = 2 in round 1, off
+    bool graph_hosted = false;                // N > 1: upkeep graph + host-launched step kernels (no host sync inside a run).  Off by
+                                              // default: its round-1 runs were made with upkeep graphs captured before the shard was set
+                                              // (fixed since, mdk_set_shard), and the fixed path has not been re-measured on > 1 GPU yet
     bool graph_energy = false;                // energies in every graph step (the energy-less k_pair variant measured 18 % slower at 92k atoms: ptxas schedules it worse)
     bool xs_current = false;                  // tile-order positions already match x_cur (integrator just published them)
     // two instantiations of the step graph: [0] inner steps (pair kernel without energy sums where that

@@ -796,8 +796,12 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
                                            c->xs.p, c->xs_ref.p, c->flags.p);                                   \
         ++c->n_launches;                                                                                        \
     } while (0)
-    const bool use_graph = c->use_graph && c->profiling < 2 && nsteps >= graph_min_steps;
-    const bool hosted = c->nranks > 1 && !c->graph_nccl;   // NCCL stays out of the captured step (it hung there)
+    // multi-GPU: plain host-launched steps unless one of the two graph flavours is switched on — `hosted`
+    // (upkeep graph + host-launched forces / NCCL / update, no host sync inside a run) or `graph_nccl`
+    // (NCCL inside the captured step; hung in round 1)
+    const bool use_graph = c->use_graph && c->profiling < 2 && nsteps >= graph_min_steps &&
+                           (c->nranks == 1 || c->graph_nccl || c->graph_hosted);
+    const bool hosted = c->nranks > 1 && !c->graph_nccl;
     if (!c->langevin_cached) {
         MDK_TRY(compute_terms(c, terms, false));  // f(x_0)
         LANGEVIN(2);

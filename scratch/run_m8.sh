@@ -2,7 +2,7 @@
 N=${1:-8}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 900 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus $N --steps 300 --warmup 30 > gpurun_out/bench_protein_1m_g${N}_s9.json 2> gpurun_out/bench_protein_1m_g${N}_s9.err
+timeout 900 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus $N --steps 200 --warmup 20 --relax 0.3 > gpurun_out/bench_protein_1m_g${N}_s9.json 2> gpurun_out/bench_protein_1m_g${N}_s9.err
 echo "1m g$N rc=$?"; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/bench_protein_1m_g${N}_s9.err | tail -c 800
 python - <<PY
 import json

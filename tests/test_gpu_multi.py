@@ -25,30 +25,53 @@ os.environ['MDPY_B200_DEVICE'] = str(local)
 from mdpy_b200 import synthetic, _native, multigpu
 from mdpy_b200.integrator import LangevinIntegrator
 s = synthetic.solvated_protein_box(20002, (60.0, 60.0, 60.0), protein_fraction=0.1, seed=3)
-def run(shard, canonical, pme_ms=40.0):
+def run(shard, canonical, pme_ms=40.0, pre_steps=0, steps=25, hosted=False):
     ens = s.ensemble(cutoff=10.0, switch=8.0, pme=True, grid=(60, 60, 60))
     ctx = _native.context_of(ens)
     ctx.dev.set_option('canonical_min_image', 1 if canonical else 0)
+    ctx.dev.set_option('graph_hosted', 1 if hosted else 0)
+    integ = LangevinIntegrator(1.0, 300, 0.01, seed=5)
+    if pre_steps:
+        # steps BEFORE the job is sharded (as bench.py relaxes the box on every rank first): the CUDA graphs
+        # captured here must not survive the attach — the shard range is one of their kernel arguments
+        integ.integrate(ens, pre_steps)
     if shard:
         multigpu.attach(ctx, dist, rank, world, multigpu.role_weights(world, 100.0, pme_ms, 10.0))
     ens.update()
     f0, e0 = ens.forces.copy(), ens.potential_energy
-    LangevinIntegrator(1.0, 300, 0.01, seed=5).integrate(ens, 25)
+    integ.integrate(ens, steps)
     return f0, e0, ens.state.positions.copy(), ens.total_energy
+def exact(p, q):
+    return (bool(np.array_equal(p[0], q[0])), bool(p[1] == q[1]), bool(np.array_equal(p[2], q[2])), bool(p[3] == q[3]))
+def close(p, q, first_exact, tol_x=1e-3):
+    dx = p[2] - q[2]; dx -= 60.0 * np.round(dx / 60.0)
+    df = np.sqrt(((p[0] - q[0]) ** 2).sum() / (q[0] ** 2).sum())
+    scale = max(abs(q[1]), abs(q[3]), 1.0)
+    first = (bool(np.array_equal(p[0], q[0])), bool(p[1] == q[1])) if first_exact else \
+            (bool(df < 1e-6), bool(abs(p[1] - q[1]) < 1e-6 * scale))
+    return first + (bool(np.abs(dx).max() < tol_x), bool(abs(p[3] - q[3]) < 1e-4 * scale)), float(np.abs(dx).max())
+res = {}
 a = run(False, True)
-b = run(True, True)
-ok = (np.array_equal(a[0], b[0]), a[1] == b[1], np.array_equal(a[2], b[2]), a[3] == b[3])
+# 1. device-driven upkeep on both sides (the sharded side with host-launched step kernels): the same lists
+#    are rebuilt at the same steps, so with the canonical minimum image everything is bit for bit
+res['MULTI'] = (exact(a, run(True, True, hosted=True)), 0.0)
+# 2. hoisted minimum image: first evaluation bit for bit, trajectory to rounding
 c = run(False, False)
-d = run(True, False)
-dx = c[2] - d[2]; dx -= 60.0 * np.round(dx / 60.0)
-ok2 = (np.array_equal(c[0], d[0]), c[1] == d[1], bool(np.abs(dx).max() < 1e-3), bool(abs(c[3] - d[3]) < 1e-5 * abs(c[3])))
-# a PME rank so loaded that it gets no pair work at all (what an 8-GPU run of the 1M box does)
-z = run(True, True, pme_ms=4000.0)
-ok3 = (np.array_equal(a[0], z[0]), a[1] == z[1], np.array_equal(a[2], z[2]), a[3] == z[3])
+res['HOIST'] = close(run(True, False, hosted=True), c, True)
+# 3. a PME rank so loaded that it gets no pair work at all (what an 8-GPU run of the 1M box does)
+res['ZEROW'] = (exact(a, run(True, True, pme_ms=4000.0, hosted=True)), 0.0)
+# 4. the default multi-GPU path (plain host-launched steps, list rebuilt from the host): same list at the
+#    first evaluation -> bit for bit; afterwards the two sides rebuild at different moments, so float32
+#    partial sums differ in their last bits
+res['PLAIN'] = close(run(True, True), a, True)
+# 5. sharding a context that has already stepped (graphs captured unsharded), long enough for list
+#    rebuilds after the attach; both flavours
+e = run(False, False, pre_steps=12, steps=150)
+res['LATE'] = close(run(True, False, pre_steps=12, steps=150), e, False)
+res['LATEH'] = close(run(True, False, pre_steps=12, steps=150, hosted=True), e, False)
 if rank == 0:
-    print('MULTI', ok, float(np.abs(a[0] - b[0]).max()), a[1], b[1])
-    print('HOIST', ok2, float(np.abs(dx).max()), c[3], d[3])
-    print('ZEROW', ok3, float(np.abs(a[2] - z[2]).max()), a[3], z[3])
+    for k, (flags, dmax) in res.items():
+        print(k, tuple(flags), dmax)
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -66,9 +89,6 @@ def test_sharded_forces_and_trajectory_equal_single_gpu(tmp_path):
                           '--master-addr', '127.0.0.1', '--master-port', '29631', str(script)],
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    line = [l for l in out.stdout.splitlines() if l.startswith('MULTI')][0]
-    assert '(True, True, True, True)' in line, line
-    line = [l for l in out.stdout.splitlines() if l.startswith('HOIST')][0]
-    assert '(True, True, True, True)' in line, line
-    line = [l for l in out.stdout.splitlines() if l.startswith('ZEROW')][0]
-    assert '(True, True, True, True)' in line, line
+    for key in ('MULTI', 'HOIST', 'ZEROW', 'PLAIN', 'LATE', 'LATEH'):
+        line = [l for l in out.stdout.splitlines() if l.startswith(key + ' ')][0]
+        assert '(True, True, True, True)' in line, line

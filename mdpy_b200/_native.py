@@ -323,7 +323,8 @@ class Device:
         self._ck(self._lib.mdk_set_profiling(self._h, int(level)))
 
     def set_option(self, key, value):
-        """key: 'graph' | 'concurrent' | 'canonical_min_image'."""
+        """Execution options of mdk_set_option (include/mdpy_b200.h): 'graph', 'concurrent',
+        'canonical_min_image', 'graph_energy', 'graph_nccl', 'pair_blocks_per_sm', 'pme_cufft', 'graph_hosted'."""
         k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6, 'graph_hosted': 7}[key]
         self._ck(self._lib.mdk_set_option(self._h, k, float(value)))
 

@@ -710,12 +710,12 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
     switch (key) {
         case 0: c->use_graph = value != 0; break;          // CUDA-graph steps in the integrators
         case 1: c->concurrent = value != 0; break;         // PME / bonded on side streams
-        case 2: c->force_canonical = value != 0; break;
-        case 3: c->graph_energy = value != 0; break;       // energies in every graph step
-        case 7: c->graph_hosted = value != 0; break;
-        case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;
+        case 2: c->force_canonical = value != 0; break;    // per-pair canonical minimum image even in large boxes
+        case 3: c->graph_energy = value != 0; break;       // energy sums in every graph step
+        case 4: c->graph_nccl = value != 0; break;         // N > 1: NCCL all-reduce inside the captured step (hung in round 1)
         case 5: c->pair_blocks_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value); break;
-        case 4: c->graph_nccl = value != 0; break;         // graph steps with the NCCL all-reduce inside (N > 1)    // per-pair canonical minimum image even in large boxes
+        case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;   // cuFFT also for small power-of-two meshes
+        case 7: c->graph_hosted = value != 0; break;       // N > 1: upkeep graph + host-launched step kernels
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

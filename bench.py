@@ -362,6 +362,9 @@ def run_b200(args, cfg):
         metric='atom_steps_per_s', value=n * args.steps / (dev_ms * 1e-3), unit='atom-steps/s', n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong',
         vs_baseline=None, dtype='f32', data='synthetic', ns_per_day=value, wall_ms_per_step=wall * 1e3 / args.steps,
+        scaling_note='default workloads follow BASELINE.json: --gpus 1 = configs[1] (23 556-atom water box), --gpus > 1 = configs[3] '
+                     '(1 066 628-atom box, strong scaling of that box); atom-steps/s is the size-normalised metric that makes the '
+                     'two comparable (one GPU: 2.25e8 at 23k, 2.20e8 at 92k atoms)',
         config=dict(workload=args.config, atoms=n, cutoff_A=cfg['cutoff'], switch_A=cfg['switch'], pme_grid=list(cfg['grid']),
                     pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=2.0,
                     terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_in_timed=rebuilds,

@@ -254,3 +254,48 @@ if want('config1'):
             out[name + '_idx'] = np.array(c._int_parameters)
             out[name + '_par'] = np.array(c._float_parameters)
     save('config1', **out)
+
+# ---------------------------------------------------------------------------------------------
+# config 1, trajectory: the example system advanced by the reference's own VerletIntegrator
+# (example/charmm/charmm.py:45: dt = 0.05 fs; zero start velocities) with every constraint of the
+# force field EXCEPT the dihedral one, whose force is not the gradient of its energy (DESIGN Q12), so a
+# drop-in with the analytic gradient cannot follow it.  ~10 s per step on one core: run with
+#   --only config1_verlet [--verlet-steps 100]
+if want('config1_verlet') and args.only == 'config1_verlet':
+    from mdpy.constraint import CharmmDihedralConstraint as _Dih
+    g = np.load(os.path.join(GOLDEN, 'config1' + SUFFIX + '.npz'))
+    base = os.path.join(REF, 'example', 'charmm', 'str')
+    atoms, bonds, angles, dihedrals, impropers = parse_psf(os.path.join(base, '6PO6_ionized.psf'))
+    t = Topology()
+    t.add_particles([Particle(particle_id=i, particle_type=a[5], particle_name=a[4], molecule_id=int(a[2]),
+                              molecule_type=a[3], chain_id=a[1], mass=float(a[7]), charge=float(a[6]))
+                     for i, a in enumerate(atoms)])
+    for b in bonds: t.add_bond([int(x) for x in b])
+    for a in angles: t.add_angle([int(x) for x in a])
+    for d in dihedrals: t.add_dihedral([int(x) for x in d])
+    for d in impropers: t.add_improper([int(x) for x in d])
+    t.join()
+    ff = CharmmForcefield(t, np.diag(g['box']))
+    ff.set_param_files(os.path.join(REF, 'data', 'charmm', 'par_all36_prot.prm'),
+                       os.path.join(REF, 'data', 'charmm', 'toppar_water_ions_namd.str'))
+    full = ff.create_ensemble()
+    ens = Ensemble(t, np.diag(g['box']))
+    kept = [c for c in full.constraints if not isinstance(c, _Dih)]
+    for c in kept:
+        c._parent_ensemble = None
+    ens.add_constraints(*kept)
+    ens.state.set_positions(np.array(g['positions'], dtype=F))
+    nsteps = int(os.environ.get('VERLET_STEPS', '100'))
+    dt = 0.05
+    integ = VerletIntegrator(dt)
+    t0 = time.time()
+    snaps = {}
+    for s in range(nsteps):
+        integ.integrate(ens, 1)
+        if (s + 1) in (1, 5, 10, 25, 50, 100, nsteps):
+            snaps[s + 1] = np.array(integ.cur_positions)
+            print('  config1 verlet step %d (%.0fs)' % (s + 1, time.time() - t0), flush=True)
+    save('config1_verlet', box=g['box'], positions0=np.array(g['positions']), dt=dt, steps=nsteps,
+         constraints=np.array([type(c).__name__ for c in kept]),
+         snapshot_steps=np.array(sorted(snaps)), snapshots=np.stack([snaps[k] for k in sorted(snaps)]),
+         final_positions=np.array(ens.state.positions), final_velocities=np.array(ens.state.velocities))

@@ -37,6 +37,9 @@ CONFIGS = {
     'water_23k': dict(gen='water_23k', cutoff=9.0, switch=None, grid=(64, 64, 64), dt=2.0),
     'protein_92k': dict(gen='protein_92k', cutoff=12.0, switch=10.0, grid=(108, 108, 80), dt=2.0),
     'protein_1m': dict(gen='protein_1m', cutoff=12.0, switch=10.0, grid=(216, 216, 216), dt=2.0),
+    # BASELINE configs[4]: 10 000 002-atom water box, 1 A skin (rebuild stress), PME 480^3.  Generates in ~25 s
+    # on the host; NOT run on a GPU in round 1 (the multi-GPU budget went into the 1M box).
+    'water_10m': dict(gen='water_10m', cutoff=9.0, switch=None, grid=(480, 480, 480), dt=2.0, skin=1.0),
 }
 FLOP_PER_PAIR = 70.0
 TEMPERATURE, GAMMA = 300.0, 1e-3   # K, 1/fs (= 1/ps)
@@ -213,6 +216,9 @@ def run_b200(args, cfg):
     dev = ctx.dev
     kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
     dt = cfg['dt']
+    skin = float(cfg.get('skin', 2.0))
+    if skin != 2.0:
+        dev.set_nlist(skin)
     if args.no_graph:
         dev.set_option('graph', 0)
     for kv in filter(None, os.environ.get('MDK_OPTS', '').split(',')):   # experiments: MDK_OPTS=concurrent=0,graph=1
@@ -366,7 +372,7 @@ def run_b200(args, cfg):
                      '(1 066 628-atom box, strong scaling of that box); atom-steps/s is the size-normalised metric that makes the '
                      'two comparable (one GPU: 2.25e8 at 23k, 2.20e8 at 92k atoms)',
         config=dict(workload=args.config, atoms=n, cutoff_A=cfg['cutoff'], switch_A=cfg['switch'], pme_grid=list(cfg['grid']),
-                    pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=2.0,
+                    pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=skin,
                     terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_in_timed=rebuilds,
                     parallelism='single GPU' if world == 1 else
                     'replicated positions, i-block sharded pair forces (weights %s), bonded terms split evenly, PME on last rank, int64 all-reduce per step'

@@ -216,3 +216,24 @@ def test_spme_restatement_converges_to_exact_ewald(order, grid, alpha, tol):
     f, en = spme.pme_total(pos, q, box, bonded, grid, order, alpha, 11.5, K_E)
     assert rel_rms(f, f_ex) < tol
     assert abs(en['total'] - e_ex) / abs(e_ex) < tol
+
+
+def test_config1_verlet_fixture_is_the_reference_trajectory_without_the_dihedral_term():
+    """tests/golden/config1_verlet_f64.npz (oracle/make_golden.py --only config1_verlet): 100 steps of the
+    reference's own VerletIntegrator on the example system, dt 0.05 fs from rest, every force-field term but
+    the dihedral one (whose reference force is not the gradient of its energy, DESIGN Q12).  The GPU parity
+    test on it belongs to the next round; here the fixture is checked for what it claims to be."""
+    g = load_golden('config1_verlet_f64')
+    c1 = load_golden('config1_f64')
+    assert np.array_equal(g['positions0'], c1['positions']) and np.array_equal(g['box'], c1['box'])
+    assert int(g['steps']) == 100 and float(g['dt']) == 0.05
+    names = [str(x) for x in g['constraints']]
+    assert 'CharmmDihedralConstraint' not in names and 'CharmmNonbondedConstraint' in names and 'ElectrostaticConstraint' in names
+    steps = [int(k) for k in g['snapshot_steps']]
+    assert steps == sorted(steps) and steps[-1] == 100 and g['snapshots'].shape == (len(steps), 2423, 3)
+    # from rest, x(t) - x(0) = a t^2 / 2 to leading order (the reference's first step uses a dt^2, Q4): the
+    # early snapshots must grow quadratically with the step count
+    d1 = np.abs(g['snapshots'][steps.index(5)] - g['positions0']).max()
+    d2 = np.abs(g['snapshots'][steps.index(10)] - g['positions0']).max()
+    assert 3.0 < d2 / d1 < 4.6
+    assert np.isfinite(g['final_velocities']).all() and np.abs(g['snapshots'][-1] - g['positions0']).max() < 2.0

@@ -299,3 +299,30 @@ if want('config1_verlet') and args.only == 'config1_verlet':
          constraints=np.array([type(c).__name__ for c in kept]),
          snapshot_steps=np.array(sorted(snaps)), snapshots=np.stack([snaps[k] for k in sorted(snaps)]),
          final_positions=np.array(ens.state.positions), final_velocities=np.array(ens.state.velocities))
+
+# ---------------------------------------------------------------------------------------------
+# config 2 at full size: the reference's own LJ (27-cell list, rc 9 A — 5 cells per edge, so its pair
+# loss Q1 is in the numbers) and bare all-pairs Coulomb on the 23 556-atom water box of the benchmark.
+# The box is regenerated from its seed (mdpy_b200.synthetic.water_box(7852, 20260001)), so only a
+# strided subset of the per-atom forces, the energies and a position checksum are stored.  ~6 min on one
+# core:  --only config2_full
+if want('config2_full') and args.only == 'config2_full':
+    s = synthetic.CONFIGS['water_23k']()
+    t = ref_topology(s.types, s.masses, s.charges, s.bonds, s.angles, s.dihedrals, s.impropers)
+    ens = Ensemble(t, np.diag(s.box))
+    lj = CharmmNonbondedConstraint(s.lj_parameters, cutoff_radius=9.0)
+    el = ElectrostaticConstraint()
+    ens.add_constraints(lj, el)
+    ens.state.set_positions(s.positions.astype(F))
+    f_lj, e_lj, t_lj = eval_constraint(lj)
+    print('config2_full LJ %.9f (%.1fs)' % (e_lj, t_lj), flush=True)
+    f_el, e_el, t_el = eval_constraint(el)
+    print('config2_full Coulomb %.9f (%.1fs)' % (e_el, t_el), flush=True)
+    stride = 16
+    cl = ens.state.cell_list
+    save('config2_full', box=s.box, n=t.num_particles, rc=9.0, stride=stride,
+         position_checksum=np.array([np.asarray(ens.state.positions, dtype=np.float64).sum(),
+                                     (np.asarray(ens.state.positions, dtype=np.float64) ** 2).sum()]),
+         lj_forces_strided=f_lj[::stride], lj_energy=e_lj, lj_force_sumsq=float((f_lj.astype(np.float64) ** 2).sum()),
+         coul_forces_strided=f_el[::stride], coul_energy=e_el, coul_force_sumsq=float((f_el.astype(np.float64) ** 2).sum()),
+         cell_num=np.array(cl.num_cell_vec), ref_seconds=np.array([t_lj, t_el]))

@@ -25,6 +25,30 @@ def test_shard_ranges_partition_the_residues():
         multigpu.shard_ranges([0, 0])
 
 
+def test_shard_ranges_cover_every_residue_exactly_once_for_any_weights():
+    """Property test: whatever the (non-negative) weights — zeros for ranks that get no pair work included —
+    the ranges tile [0, 32 N) without gap or overlap, which is what makes every i-block owned exactly once."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.one_of(st.just(0.0), st.floats(min_value=1e-6, max_value=1e3)), min_size=1, max_size=8))
+    def check(weights):
+        if sum(weights) <= 0:
+            with pytest.raises(ValueError):
+                multigpu.shard_ranges(weights)
+            return
+        r = multigpu.shard_ranges(weights)
+        m = multigpu.RESIDUES_PER_RANK * len(weights)
+        owner = np.zeros(m, dtype=int)
+        for lo, hi in r:
+            assert 0 <= lo <= hi <= m
+            owner[lo:hi] += 1
+        assert (owner == 1).all()
+        assert all((hi > lo) == (w > 0) or (w > 0 and hi > lo) for (lo, hi), w in zip(r, weights) if w > 0)
+        assert all(hi == lo for (lo, hi), w in zip(r, weights) if w == 0)
+    check()
+
+
 def test_role_weights_equalise_rank_times():
     for n, pair, pme, bonded in ((2, 70.0, 54.0, 16.0), (8, 3000.0, 350.0, 40.0), (4, 50.0, 80.0, 5.0)):
         x = multigpu.role_weights(n, pair, pme, bonded)

@@ -1,17 +1,31 @@
-"""Ensemble — binds constraints to a (topology, state) pair and sums their forces/energies:
-the caller of the drop-in boundary (mdpy/ensemble.py:16-102).
+"""Ensemble: a topology, its State and the constraints acting on it — the caller of the drop-in
+boundary.  Interface of mdpy/ensemble.py:16-102 (add_constraints, update, forces / energies,
+constraints / num_constraints), kept so that reference code driving an Ensemble keeps working.
 
-`update()` keeps the reference's contract (every constraint's update(), float64 sums,
-ensemble.py:53-61).  When all bound constraints are native and share one device context
-the per-constraint passes are fused into a single mdk_compute; the
-per-constraint `.forces` then come from the one shared accumulator and only their *sum* is
-meaningful, which is exactly what Ensemble exposes.
+What differs from the reference is where the sum over constraints happens.  The reference loops over
+its constraints and adds their float arrays on the host (ensemble.py:53-61).  Here, when every bound
+constraint is native and they share one device context, `update()` issues ONE force evaluation for the
+union of their terms: the per-constraint `.forces` then all refer to the one shared
+accumulator and only their sum — which is what Ensemble exposes — is meaningful.  Foreign constraints
+(anything without `is_native`) fall back to the reference's per-constraint protocol.
 """
 import numpy as np
 
 from .core import State, Topology
 from .error import ConstraintConflictError
 from .unit import Quantity, default_energy_unit, default_mass_unit, default_velocity_unit
+
+_KE_TO_ENERGY = None  # conversion factor Da (A/fs)^2 -> internal energy unit, resolved on first use
+
+
+def _kinetic_energy_of(velocities, masses):
+    """sum m v^2 / 2 in the internal energy unit, accumulated in float64."""
+    global _KE_TO_ENERGY
+    if _KE_TO_ENERGY is None:
+        _KE_TO_ENERGY = Quantity(1.0, default_velocity_unit ** 2 * default_mass_unit).convert_to(default_energy_unit).value
+    v = np.asarray(velocities, dtype=np.float64)
+    m = np.asarray(masses, dtype=np.float64).reshape(-1)
+    return 0.5 * float(np.einsum('i,ij,ij->', m, v, v)) * float(_KE_TO_ENERGY)
 
 
 class Ensemble:
@@ -21,50 +35,79 @@ class Ensemble:
         self._topology = topology
         self._state = State(topology, pbc_matrix)
         self._matrix_shape = self._state.matrix_shape
-        self._forces = np.zeros(self._matrix_shape)
-        self._total_energy = self._potential_energy = self._kinetic_energy = 0
         self._constraints = []
-        self._native = None  # shared device context, created by the first native constraint
+        self._native = None   # device context shared by the native constraints, created by the first one bound
+        self._forces = np.zeros(self._matrix_shape)
+        self._potential_energy = self._kinetic_energy = self._total_energy = 0
 
     def __repr__(self):
-        return '<mdpy_b200.Ensemble object: %d constraints at %x>' % (self.num_constraints, id(self))
+        return '<mdpy_b200.Ensemble object: %d constraints at %x>' % (len(self._constraints), id(self))
 
+    # ---- constraints ----------------------------------------------------------------------------------
     def add_constraints(self, *constraints):
-        for constraint in constraints:
-            if any(constraint is c for c in self._constraints):
-                raise ConstraintConflictError('%s has added twice to %s' % (constraint, self))
-            self._constraints.append(constraint)
-            constraint.bind_ensemble(self)
-            if constraint.cutoff_radius > self._state.cell_list.cutoff_radius:
-                self._state.cell_list.set_cutoff_radius(constraint.cutoff_radius)
+        """Bind constraints in order; the same object twice is a ConstraintConflictError (ensemble.py:40-46)
+        and the State's cutoff guard follows the largest cutoff bound so far (ensemble.py:49-50)."""
+        guard = self._state.cell_list
+        for new in constraints:
+            for bound in self._constraints:
+                if bound is new:
+                    raise ConstraintConflictError('%s has added twice to %s' % (new, self))
+            self._constraints.append(new)
+            new.bind_ensemble(self)
+            if new.cutoff_radius > guard.cutoff_radius:
+                guard.set_cutoff_radius(new.cutoff_radius)
 
+    def _all_native(self):
+        return self._native is not None and all(getattr(c, 'is_native', False) for c in self._constraints)
+
+    # ---- one force / energy evaluation ----------------------------------------------------------------
     def update(self, fused=True):
-        self._forces = np.zeros(self._matrix_shape)
-        self._potential_energy = 0
-        native = [c for c in self._constraints if getattr(c, 'is_native', False)]
-        if fused and self._native is not None and len(native) == len(self._constraints) and len(native) > 1:
-            forces, energy = self._native.compute_fused(native)
-            self._forces += forces
-            self._potential_energy += energy
+        """Forces (float64 [N,3]) and potential energy summed over the constraints, kinetic energy from the
+        State's velocities, total = potential + kinetic."""
+        if fused and len(self._constraints) > 1 and self._all_native():
+            forces, potential = self._native.compute_fused(self._constraints)
+            total_force = np.array(forces, dtype=np.float64)
         else:
-            for constraint in self._constraints:
-                constraint.update()
-                self._forces += constraint.forces
-                self._potential_energy += constraint.potential_energy
-        self._update_kinetic_energy()
+            total_force = np.zeros(self._matrix_shape)
+            potential = 0
+            for c in self._constraints:
+                c.update()
+                total_force += c.forces
+                potential += c.potential_energy
+        self._forces = total_force
+        self._potential_energy = potential
+        self._kinetic_energy = _kinetic_energy_of(self._state.velocities, self._topology.masses)
         self._total_energy = self._potential_energy + self._kinetic_energy
 
-    def _update_kinetic_energy(self):
-        v = np.asarray(self._state.velocities, dtype=np.float64)
-        m = np.asarray(self._topology.masses, dtype=np.float64).reshape(-1)
-        ke = 0.5 * float(((v ** 2).sum(1) * m).sum())
-        self._kinetic_energy = Quantity(ke, default_velocity_unit ** 2 * default_mass_unit).convert_to(default_energy_unit).value
+    # ---- read-only views ------------------------------------------------------------------------------
+    @property
+    def topology(self):
+        return self._topology
 
-    topology = property(lambda self: self._topology)
-    state = property(lambda self: self._state)
-    forces = property(lambda self: self._forces)
-    total_energy = property(lambda self: self._total_energy)
-    potential_energy = property(lambda self: self._potential_energy)
-    kinetic_energy = property(lambda self: self._kinetic_energy)
-    constraints = property(lambda self: self._constraints)
-    num_constraints = property(lambda self: len(self._constraints))
+    @property
+    def state(self):
+        return self._state
+
+    @property
+    def constraints(self):
+        return self._constraints
+
+    @property
+    def num_constraints(self):
+        return len(self._constraints)
+
+    @property
+    def forces(self):
+        return self._forces
+
+    @property
+    def potential_energy(self):
+        return self._potential_energy
+
+    @property
+    def kinetic_energy(self):
+        return self._kinetic_energy
+
+    @property
+    def total_energy(self):
+        return self._total_energy

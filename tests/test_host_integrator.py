@@ -125,3 +125,43 @@ def test_double_precision_state_is_converted_at_the_boundary(monkeypatch):
     LangevinIntegrator(2.0, 300, 1e-3).integrate(ens, 2)
     assert ens.state.positions.dtype == np.float64 and ens.state.velocities.dtype == np.float64
     assert np.allclose(ens.state.positions, x0 + 0.02, atol=1e-5)
+
+
+def test_ensemble_update_fuses_native_constraints_into_one_evaluation(monkeypatch):
+    """Ensemble.update (mdpy/ensemble.py:53-61): with every constraint native, one device evaluation of the
+    union of the terms; fused=False keeps the reference's per-constraint protocol.  Energies are split by
+    each constraint's slots either way."""
+    class Dev(StubDevice):
+        def compute(self, terms):
+            self.calls.append(('compute', terms))
+            e = np.zeros(_native.NUM_ENERGIES)
+            e[_native.E_LJ], e[_native.E_BOND], e[_native.E_ANGLE] = -1.0, 0.25, 0.125
+            return e
+
+        def forces(self, dtype=np.float32):
+            return np.full((self.n, 3), 0.5, dtype=dtype)
+
+        def upload_positions(self, x):
+            self.calls.append('upload')
+
+    monkeypatch.setattr(_native, 'Device', Dev)
+    s = synthetic.water_box(300, 4, box=np.full(3, 30.0))
+    ens = s.ensemble(cutoff=9.0, pme=True, grid=(32, 32, 32))
+    dev = _native.context_of(ens).dev
+    ens.state.set_velocities(np.full((900, 3), 0.01, dtype=np.float32))
+    ens.update()
+    computes = [c for c in dev.calls if isinstance(c, tuple) and c[0] == 'compute']
+    union = 0
+    for c in ens.constraints:
+        union |= c.terms
+    assert computes == [('compute', union)]
+    assert ens.forces.dtype == np.float64 and ens.forces.shape == (900, 3) and np.all(ens.forces == 0.5)
+    assert ens.potential_energy == pytest.approx(-1.0 + 0.25 + 0.125)
+    m = np.asarray(ens.topology.masses, dtype=np.float64).reshape(-1)
+    assert ens.kinetic_energy > 0 and ens.total_energy == pytest.approx(ens.potential_energy + ens.kinetic_energy)
+    n_before = len(computes)
+    ens.update(fused=False)
+    computes = [c for c in dev.calls if isinstance(c, tuple) and c[0] == 'compute']
+    assert len(computes) - n_before == ens.num_constraints          # one evaluation per constraint
+    assert np.all(ens.forces == 0.5 * ens.num_constraints)
+    assert ens.potential_energy == pytest.approx(-1.0 + 0.25 + 0.125)

@@ -412,6 +412,16 @@ def run_b200(args, cfg):
                 source='profiles/r01_reference_numba_cuda.json (unmodified reference, one B200, plain-cutoff LJ + bare Coulomb, no PME)')
     except (OSError, ValueError):
         pass
+    if args.config == 'water_23k':   # recorded, not live: the unmodified reference's CPU path on this very box (1 core, DOUBLE mode)
+        try:
+            g = np.load(os.path.join(ROOT, 'tests', 'golden', 'config2_full_f64.npz'))
+            sec = float(np.sum(g['ref_seconds']))
+            line['reference_cpu_recorded'] = dict(
+                seconds_per_step=sec, atom_steps_per_s=n / sec, ns_per_day=ns_per_day(1, sec, dt),
+                source='tests/golden/config2_full_f64.npz:ref_seconds (oracle/make_golden.py --only config2_full: one LJ + one '
+                       'Coulomb evaluation of the unmodified reference, numba CPU kernels, 1 core of the build container)')
+        except (OSError, KeyError, ValueError):
+            pass
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -89,6 +89,7 @@ def test_bench_line_has_every_key_of_the_contract(monkeypatch, capsys):
     assert line['gpu_launches'] == 13 * 20
     assert line['value'] == pytest.approx(23556 * 20 / (0.1 * 20 * 1e-3))
     assert 'reference_numba_cuda_recorded' in line
+    assert line['reference_cpu_recorded']['seconds_per_step'] == pytest.approx(419.5, rel=0.01)   # the reference itself, 1 core
 
 
 def test_default_workload_follows_the_gpu_count(monkeypatch):

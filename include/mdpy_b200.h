@@ -172,6 +172,12 @@ MDK_API int mdk_last_energies(mdk_ctx *ctx, double *energies);
 /* The in-cutoff (rc of mdk_set_lj), non-excluded pair set the tile list yields, as
  * matrix_id pairs i<j (unsorted).  *n_out = count; at most cap are written. */
 MDK_API int mdk_get_pairs(mdk_ctx *ctx, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out);
+/* The same set as the PRODUCTION pair kernel decides it: a debug instantiation of k_pair (same template
+ * arguments as the launch mdk_compute / the step graphs make for the current system: hoisted minimum
+ * image where the box allows it, CHARMM switch, shared cutoff) writes out every slot that passes its own
+ * cutoff / exclusion test, on the tile list and tile-order positions exactly as the last force evaluation
+ * left them (no refresh, no rebuild: after a step call this is the list the last in-graph rebuild made). */
+MDK_API int mdk_get_pairs_production(mdk_ctx *ctx, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out);
 /* Device time (ms, CUDA events on the ctx stream) of the last mdk_compute / step call,
  * per phase: [0]=nlist rebuild [1]=pair kernel [2]=pme spread [3]=fft+convolve
  * [4]=pme gather [5]=bonded+special pairs [6]=integrate [7]=bare coulomb
@@ -199,8 +205,8 @@ MDK_API int mdk_set_shard(mdk_ctx *ctx, int lo, int hi, int modulus);
 /* Multi-GPU: one process per GPU.  mdk_comm_unique_id wraps ncclGetUniqueId (rank 0 calls it and
  * ships the 128 bytes to the other ranks by any means, e.g. torch.distributed.broadcast);
  * mdk_comm_init joins the communicator.  Afterwards every force evaluation ends with one
- * ncclAllReduce(sum) of the int64 force accumulator; bonded / excluded-pair terms run on rank 0
- * only, the PME mesh on the last rank. */
+ * ncclAllReduce(sum) of the int64 force accumulator; bonded / excluded-pair terms are dealt to the
+ * ranks in contiguous ranges, the PME mesh runs on the last rank. */
 MDK_API int mdk_comm_unique_id(void *out128);
 MDK_API int mdk_comm_init(mdk_ctx *ctx, int rank, int nranks, const void *unique_id128);
 

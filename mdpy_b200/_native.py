@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_set_shard', 'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free',
+    'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
 _lib = None
@@ -86,6 +86,7 @@ def load_library():
         'mdk_step_langevin': (i32, [vp, f64, f64, f64, u64, i32, C.c_uint]),
         'mdk_last_energies': (i32, [vp, vp]),
         'mdk_get_pairs': (i32, [vp, vp, vp, i64, C.POINTER(i64)]),
+        'mdk_get_pairs_production': (i32, [vp, vp, vp, i64, C.POINTER(i64)]),
         'mdk_get_timing': (i32, [vp, vp]),
         'mdk_set_profiling': (i32, [vp, i32]),
         'mdk_force_accumulator': (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
@@ -294,12 +295,15 @@ class Device:
         return e
 
     # -- hooks
-    def pairs(self):
+    def pairs(self, production=False):
+        """In-cutoff, non-excluded pairs [m,2] (matrix ids, i<j, unsorted).  production=True: emitted by the
+        production pair kernel itself on the list as the last force evaluation left it (mdk_get_pairs_production)."""
         cap = max(4096, self.n * 400)
+        fn = self._lib.mdk_get_pairs_production if production else self._lib.mdk_get_pairs
         while True:
             oi = np.empty(cap, dtype=np.int32); oj = np.empty(cap, dtype=np.int32)
             cnt = C.c_int64(0)
-            self._ck(self._lib.mdk_get_pairs(self._h, _ptr(oi), _ptr(oj), cap, C.byref(cnt)))
+            self._ck(fn(self._h, _ptr(oi), _ptr(oj), cap, C.byref(cnt)))
             if cnt.value <= cap:
                 return np.stack([oi[:cnt.value], oj[:cnt.value]], axis=1)
             cap = int(cnt.value)
@@ -356,18 +360,38 @@ class EnsembleContext:
         self.dev.set_exclusions(topo.bonded_particles, topo.scaling_particles)
         self.integrator_owner = None
 
+    MAX_STATE_BUFFERS = 8
+
     def state_buffers(self):
         """(positions, velocities) float32 [n,3] arrays in page-locked memory for the next host-state step
-        call to fill.  Two pairs alternate, so the arrays handed out by the previous call (which are the
-        current State, and the next call's input) are never the ones being written."""
-        bufs = getattr(self, '_state_bufs', None)
-        if bufs is None or bufs[0][0].shape[0] != self.dev.n:
-            # positions and velocities share one block, so each direction is a single DMA
-            blocks = [self.dev.pinned_empty((2, self.dev.n, 3)) for _ in range(2)]
-            bufs = self._state_bufs = [(b[0], b[1]) for b in blocks]
-            self._state_turn = 0
-        self._state_turn ^= 1
-        return bufs[self._state_turn]
+        call to fill, or (None, None) when every pooled block is still referenced by somebody.
+
+        The arrays handed out become `ensemble.state.positions / velocities`.  A block is reused only when
+        nobody outside the pool holds a reference to it (or to a view of it) any more — code that keeps
+        `frames.append(ens.state.positions)` therefore keeps its frames intact, like with the reference, which
+        allocates a fresh array on every set_positions (state.py:58-60).  The pool grows on demand up to
+        MAX_STATE_BUFFERS blocks; beyond that the integrator falls back to plain numpy copies.
+        Explicitly closing the Device frees the page-locked memory: State arrays must not be used after that."""
+        import sys
+        pool = getattr(self, '_state_pool', None)
+        if pool is None or pool[0][1].shape[1] != self.dev.n:
+            pool = self._state_pool = []
+        for entry in pool:
+            owner, block, x, v, base = entry
+            if (sys.getrefcount(owner), sys.getrefcount(block), sys.getrefcount(x), sys.getrefcount(v)) == base:
+                return x, v
+        if len(pool) >= self.MAX_STATE_BUFFERS:
+            return None, None
+        # positions and velocities share one block, so each direction is a single DMA
+        block = self.dev.pinned_empty((2, self.dev.n, 3))
+        owner = block.base if block.base is not None else block
+        while getattr(owner, 'base', None) is not None and isinstance(owner.base, np.ndarray):
+            owner = owner.base
+        x, v = block[0], block[1]
+        entry = [owner, block, x, v, None]
+        pool.append(entry)
+        entry[4] = (sys.getrefcount(owner), sys.getrefcount(block), sys.getrefcount(x), sys.getrefcount(v))
+        return x, v
 
     def check_box(self):
         m = self.ensemble.state.pbc_matrix
@@ -413,14 +437,11 @@ class EnsembleContext:
         e = self.compute(terms)
         forces = self.dev.forces(np.float64)
         total = 0.0
-        zeros = getattr(self, '_zeros', None)
-        if zeros is None or zeros.shape != forces.shape:
-            zeros = self._zeros = np.zeros(forces.shape, dtype=env.NUMPY_FLOAT)
-            zeros.setflags(write=False)
-        for k, c in enumerate(constraints):
+        stamp = self._revision(self.ensemble.state)
+        for c in constraints:
             c._potential_energy = c._energy_from(e)
-            # one shared accumulator: the sum lives on the first constraint, the others report zero
-            c._forces = forces if k == 0 else zeros
+            # the sum came out of one evaluation; each constraint's own forces are evaluated when read
+            c._defer_forces(stamp)
             total += c._potential_energy
         return forces, total
 

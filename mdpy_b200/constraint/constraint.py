@@ -23,6 +23,7 @@ class Constraint:
         self._potential_energy = None
         self._cutoff_radius = env.NUMPY_FLOAT(0)
         self._ctx = None
+        self._lazy_stamp = None   # set by a fused Ensemble.update: own forces are evaluated on first access
 
     def __repr__(self):
         return '<mdpy_b200.constraint.Constraint class>'
@@ -66,6 +67,26 @@ class Constraint:
         self._forces = np.ascontiguousarray(self._ctx.dev.forces(np.float64 if env.NUMPY_FLOAT == np.float64 else np.float32),
                                             dtype=env.NUMPY_FLOAT)
         self._potential_energy = self._energy_from(e)
+        self._lazy_stamp = None
+
+    def _defer_forces(self, stamp):
+        """Called by the fused Ensemble.update: the sum over all constraints came out of ONE device evaluation;
+        this constraint's own forces (ensemble.py:56-59 leaves each constraint with its own) are evaluated when
+        somebody reads `.forces`, against the same positions (`stamp` = the State revision they belong to)."""
+        self._forces = None
+        self._lazy_stamp = stamp
+
+    @property
+    def forces(self):
+        if self._forces is None and self._lazy_stamp is not None:
+            ctx = self._ctx
+            if ctx._revision(ctx.ensemble.state) != self._lazy_stamp:
+                raise RuntimeError('%s: the State changed since Ensemble.update(); call update() on the constraint '
+                                   'for forces at the new positions' % self)
+            energy = self._potential_energy
+            self.update()
+            self._potential_energy = energy   # the value of the fused evaluation (same positions, same term)
+        return self._forces
 
     def set_cutoff_radius(self, val):
         self._cutoff_radius = check_quantity_value(val, default_length_unit)
@@ -73,6 +94,5 @@ class Constraint:
     force_id = property(lambda self: self._force_id)
     force_group = property(lambda self: self._force_group)
     parent_ensemble = property(lambda self: self._parent_ensemble)
-    forces = property(lambda self: self._forces)
     potential_energy = property(lambda self: self._potential_energy)
     cutoff_radius = property(lambda self: self._cutoff_radius)

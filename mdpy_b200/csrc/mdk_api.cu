@@ -19,7 +19,13 @@ int fail(mdk_ctx *c, int code, const char *fmt, ...) {
     return code;
 }
 
-static void invalidate(mdk_ctx *c) { c->nlist_valid = false; c->xs_current = false; ++c->graph_epoch; }
+// A changed box / cutoff / parameter table / exclusion set: the tile list, the captured graphs and the
+// integrators' cached forces (f_prev of the Langevin step, x_prev of the Verlet step) all belong to the old system.
+static void invalidate(mdk_ctx *c) {
+    c->nlist_valid = false; c->xs_current = false;
+    c->verlet_cached = false; c->langevin_cached = false;
+    ++c->graph_epoch;
+}
 
 __global__ void k_f32_to_f64(size_t n, const float *__restrict__ in, double *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,8 +346,11 @@ int mdk_set_pme(mdk_ctx *c, int nx, int ny, int nz, int order) {
     if (nx < 4 || ny < 4 || nz < 4) return fail(c, MDK_ERR_BAD_ARG, "PME mesh %dx%dx%d too small", nx, ny, nz);
     if (order != 4 && order != 5 && order != 6 && order != 8) return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", order);
     if (nx < order || ny < order || nz < order) return fail(c, MDK_ERR_BAD_ARG, "PME mesh smaller than the spline order");
+    if (c->have_pme && c->pme_n[0] == nx && c->pme_n[1] == ny && c->pme_n[2] == nz && c->pme_order == order) return MDK_OK;
     c->pme_n[0] = nx; c->pme_n[1] = ny; c->pme_n[2] = nz; c->pme_order = order;
     c->have_pme = true; c->pme_dirty = true;
+    c->verlet_cached = false; c->langevin_cached = false;
+    ++c->graph_epoch;   // mesh sizes and buffers are baked into captured launches
     return MDK_OK;
 }
 
@@ -368,6 +377,8 @@ int mdk_set_bonded(mdk_ctx *c, int kind, int n, const int32_t *idx, const float 
         MDK_CUDA(c, cudaMemcpyAsync(b.par.p, par, (size_t)n * np[kind] * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    c->verlet_cached = false; c->langevin_cached = false;
+    ++c->graph_epoch;   // term counts and table addresses are baked into captured launches
     return MDK_OK;
 }
 
@@ -514,7 +525,9 @@ int mdk_step_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int refer
     return MDK_OK;
 }
 
-void mdk_verlet_reset(mdk_ctx *c) { if (c) { c->verlet_cached = false; c->langevin_cached = false; } }
+// A new integrator object (or erase_cache) starts from scratch: no cached force / previous position, and the
+// Langevin noise counter (atom, step) restarts at step 0.
+void mdk_verlet_reset(mdk_ctx *c) { if (c) { c->verlet_cached = false; c->langevin_cached = false; c->langevin_step = 0; } }
 
 int mdk_step_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms) {
     NEED_CTX(c);
@@ -680,7 +693,15 @@ int mdk_get_pairs(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64
     cudaSetDevice(c->device);
     if (!n_out || cap < 0 || (cap > 0 && (!out_i || !out_j))) return fail(c, MDK_ERR_BAD_ARG, "mdk_get_pairs: bad arguments");
     if (!c->have_box || c->n <= 0 || !c->have_pos) return fail(c, MDK_ERR_NOT_BOUND, "mdk_get_pairs before box/atoms/positions");
-    return pair_enumerate(c, out_i, out_j, cap, n_out);
+    return pair_enumerate(c, out_i, out_j, cap, n_out, 0);
+}
+
+int mdk_get_pairs_production(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!n_out || cap < 0 || (cap > 0 && (!out_i || !out_j))) return fail(c, MDK_ERR_BAD_ARG, "mdk_get_pairs_production: bad arguments");
+    if (!c->have_box || c->n <= 0 || !c->have_pos) return fail(c, MDK_ERR_NOT_BOUND, "mdk_get_pairs_production before box/atoms/positions");
+    return pair_enumerate(c, out_i, out_j, cap, n_out, 1);
 }
 
 int mdk_get_timing(mdk_ctx *c, double *out24) {

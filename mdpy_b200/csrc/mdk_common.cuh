@@ -174,6 +174,8 @@ struct mdk_ctx {
     cudaGraphExec_t upkeep_exec = nullptr;
     mdk::DevBuf<unsigned long long> step_dev;  // [0] Langevin noise counter, [1] k_langevin mode of the next graph step
     double graph_key[8] = {0};
+    uint64_t graph_seed = 0;                  // Philox key baked into the captured k_langevin (kept as an integer: all 64 bits count)
+    unsigned cached_terms = 0;                // term set the integrators' cached forces (f_prev / x_prev) were computed with
     long long graph_epoch = 0, graph_epoch_built = -1;
     int graph_launches_per_step = 0;
 
@@ -237,7 +239,7 @@ int nlist_ensure(mdk_ctx *c);                  // rebuild if flagged / invalid
 NlistView nlist_view(mdk_ctx *c);
 int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul);
 int pair_special(mdk_ctx *c, bool pme_excl);   // excluded-pair erf correction
-int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out);
+int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out, int production);
 int coulomb_bare(mdk_ctx *c);
 int pme_prepare(mdk_ctx *c);
 int pme_compute(mdk_ctx *c);
@@ -251,6 +253,7 @@ int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);
 int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry);
 void graph_destroy(mdk_ctx *c);
 int graph_finish(mdk_ctx *c);                        // counters / sticky errors of a queued graph run, after a sync
+int check_lost_flag(mdk_ctx *c);                     // flags[0] in the last read-back block -> MDK_ERR_PARTICLE_LOST
 int comm_allreduce_forces(mdk_ctx *c);
 int comm_allreduce_energies(mdk_ctx *c);
 void comm_destroy(mdk_ctx *c);

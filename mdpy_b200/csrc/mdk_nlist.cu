@@ -581,12 +581,16 @@ int nlist_rebuild(mdk_ctx *c) {
             // the centre, so R + h_max <= L/2 on every axis is enough (pairs farther apart than R may then
             // see a non-minimal image, but both distances exceed the cutoff).  1 A spare when later
             // rebuilds will run inside a graph and cannot switch kernels.
+            const bool shift_before = c->shift_ok;
             c->shift_ok = true;
             for (int a = 0; a < 3; ++a) {
                 float hmax;
                 memcpy(&hmax, &h_cnt[8 + a], sizeof(float));
                 if (g.R + hmax + (c->graph_pools ? 1.0f : 0.f) + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
             }
+            // the SHIFT / canonical choice is a template argument of the k_pair launch captured in the step
+            // graphs (and the in-graph bound check is armed only for SHIFT): a flip makes them stale
+            if (c->shift_ok != shift_before) ++c->graph_epoch;
             c->nlist_valid = true;
             ++c->n_rebuilds;
             return MDK_OK;

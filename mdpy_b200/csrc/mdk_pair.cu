@@ -22,7 +22,20 @@ struct PairParams {
     float rc2_c, alpha, two_alpha_over_sqrtpi;
     float sw_c0, sw_12inv;      // rc^2 - 3 ron^2, 12 (rc^2 - ron^2)^-3
     float alpha2_log2e;         // alpha^2 log2(e): exp(-alpha^2 r^2) = ex2(-alpha2_log2e r^2)
+    // SHIFT kernels: r^2 computed on hoisted images differs from the canonical r^2 by a few ulp of the box
+    // length; slots whose r^2 falls inside [lo, hi] around a cutoff are re-decided on the canonical
+    // expression (a handful per step), so the pair set is the canonical one bit for bit
+    float lj_lo, lj_hi, c_lo, c_hi, max_lo, max_hi;
     int n;
+};
+
+// debug instantiation of k_pair: every slot that passes the kernel's own cutoff / exclusion decision is
+// written out (mdk_get_pairs with production != 0)
+struct EmitOut {
+    int *out_i, *out_j;
+    const int *order;
+    unsigned long long cap;
+    unsigned long long *count;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -65,12 +78,21 @@ constexpr int PAIR_WARPS = 8;
 
 // One chunk = 32 j-atoms against the warp's 32 i-atoms, 32 rotation steps.  MASKED chunks carry
 // exclusion / 1-4 bits (a few per i-block); the rest skip the bit tests entirely.
-template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool MASKED>
+// r^2 of one pair by the canonical criterion (oracle/mdpy_oracle.c:ora_pair_set_f32) from the stored
+// wrapped coordinates — the rare slow path of the SHIFT kernels
+__device__ __noinline__ float canonical_r2(float Lx, float Ly, float Lz, float ix, float iy, float iz,
+                                           const float4 *__restrict__ xs, int ia, int ja) {
+    const float4 a = xs[ia], b = xs[ja];
+    return dist2(min_image(b.x - a.x, Lx, ix), min_image(b.y - a.y, Ly, iy), min_image(b.z - a.z, Lz, iz));
+}
+
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool MASKED, bool EMIT>
 __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__restrict__ sx,
                                            const float4 *__restrict__ slj, const int lane, const float4 xi,
                                            const float4 li, const unsigned excl, const unsigned m14, float &fix,
                                            float &fiy, float &fiz, float &fjx, float &fjy, float &fjz, float &e_lj,
-                                           float &e_c) {
+                                           float &e_c, const float4 *__restrict__ xs, const int *__restrict__ cj,
+                                           const int ia, const EmitOut &em) {
     // the chunk is staged twice back to back (64 entries), so slot (lane + k) & 31 is entry lane + k: one
     // base address per lane, the rotation step is an immediate offset of the LDS
     sx += lane; slj += lane;
@@ -84,14 +106,31 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
             dz = min_image(dz, P.L[2], P.invL[2]);
         }
         const float r2 = dist2(dx, dy, dz);
-        bool in = r2 <= P.rc2_max;
+        bool in = r2 <= (SHIFT ? P.max_hi : P.rc2_max);
         if (MASKED) in = in && !((excl >> k) & 1u);
+        float r2d = r2;   // the value the cutoff decisions are taken on
+        if (SHIFT && in) {
+            bool near = r2 > P.max_lo;
+            if (!ONECUT) near = near || (r2 > P.lj_lo && r2 <= P.lj_hi) || (r2 > P.c_lo && r2 <= P.c_hi);
+            if (near) {
+                r2d = canonical_r2(P.L[0], P.L[1], P.L[2], P.invL[0], P.invL[1], P.invL[2], xs, ia, cj[(lane + k) & 31]);
+                in = r2d <= P.rc2_max;
+            }
+        }
         if (in) {
+            if (EMIT) {
+                const unsigned long long pos = atomicAdd(em.count, 1ull);
+                if (pos < em.cap) {
+                    const int a = em.order[ia], b = em.order[cj[(lane + k) & 31]];
+                    em.out_i[pos] = a < b ? a : b;
+                    em.out_j[pos] = a < b ? b : a;
+                }
+            }
             const float rinv = rsqrt_approx(r2);
             const float r2inv = rinv * rinv;
             float g = 0.f;  // dE/dr / r : F_i = g d, F_j = -g d  (d = x_j - x_i)
             if (DO_LJ) {
-                if (ONECUT || r2 <= P.rc2_lj) {
+                if (ONECUT || r2d <= P.rc2_lj) {
                     const float4 lj = slj[k];
                     float a = li.x * lj.x, s = li.y + lj.y;             // 4 eps_ij, sigma_ij
                     if (MASKED) {
@@ -116,7 +155,7 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
                 }
             }
             if (DO_COUL) {
-                if (ONECUT || r2 <= P.rc2_c) {
+                if (ONECUT || r2d <= P.rc2_c) {
                     // erfc(x) = P(t) exp(-x^2):  E = qq P ex / r,  dE/dr / r = -qq ex (P / r + 2 alpha / sqrt(pi)) / r^2
                     const float u = xi.w * xj.w * ex2_approx(-P.alpha2_log2e * r2);
                     const float v = erfcx_poly(P.alpha * (r2 * rinv)) * rinv;
@@ -143,11 +182,11 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
 // the same criterion is evaluated on d rounded once more (pairs within an ulp of rc may differ).
 // ONECUT: LJ and Coulomb share one cutoff.  ENERGY: off for the steps of a graph run whose energies
 // nobody reads.
-template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY>
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool EMIT = false>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
        const float4 *__restrict__ bbc, long long *__restrict__ f_acc, long long *__restrict__ e_acc,
-       int *__restrict__ cursor) {
+       int *__restrict__ cursor, EmitOut em) {
     __shared__ float4 s_x[PAIR_WARPS][64];
     __shared__ float4 s_lj[PAIR_WARPS][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -194,11 +233,13 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
             if (mslot >= 0) {
                 const unsigned excl = nl.mask_excl[(size_t)mslot * 32 + lane];
                 const unsigned m14 = DO_LJ ? nl.mask_14[(size_t)mslot * 32 + lane] : 0u;
-                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, true>(P, s_x[wid], s_lj[wid], lane, xi, li, excl, m14,
-                                                                               fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c);
+                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, true, EMIT>(
+                    P, s_x[wid], s_lj[wid], lane, xi, li, excl, m14, fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c, xs,
+                    nl.chunk_j + (size_t)chunk * 32, ia, em);
             } else {
-                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, false>(P, s_x[wid], s_lj[wid], lane, xi, li, 0u, 0u,
-                                                                                fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c);
+                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, false, EMIT>(
+                    P, s_x[wid], s_lj[wid], lane, xi, li, 0u, 0u, fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c, xs,
+                    nl.chunk_j + (size_t)chunk * 32, ia, em);
             }
             // after 32 rotations lane l holds the sum for slot l again
             if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {
@@ -245,6 +286,19 @@ static PairParams make_pair_params(mdk_ctx *c, bool do_lj, bool do_coul) {
     P.sw_c0 = P.rc2_lj - 3.f * P.ron2;
     P.sw_12inv = 12.f * P.inv_ab3;
     P.n = c->n;
+    // decision band of the SHIFT kernels.  Hoisted coordinates carry <= 1.5 ulp(L) of rounding per atom and axis,
+    // the canonical difference 0.5 ulp(L): |d' - d| <= 2 L 2^-23 per axis; delta takes 4x that.
+    // |r'^2 - r^2| <= 2 sqrt(3) r delta (+ the roundings of the sum of squares).
+    const float Lmax = fmaxf(c->box.L[0], fmaxf(c->box.L[1], c->box.L[2]));
+    const float delta = 8.f * Lmax * 1.1920929e-07f;
+    auto band = [&](float rc2, float &lo, float &hi) {
+        if (rc2 <= 0.f) { lo = hi = -1.f; return; }
+        const float b = 1.5f * 3.4641016f * sqrtf(rc2) * delta + 4e-7f * rc2;
+        lo = rc2 - b; hi = rc2 + b;
+    };
+    band(P.rc2_lj, P.lj_lo, P.lj_hi);
+    band(P.rc2_c, P.c_lo, P.c_hi);
+    band(P.rc2_max, P.max_lo, P.max_hi);
     return P;
 }
 
@@ -271,7 +325,7 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     const bool energy = !c->in_capture || c->graph_energy || c->capture_energy || sw;   // the inner steps of a graph run never report energies
 #define LAUNCH(LJ, CO, SW, SH, OC, EN)                                                                          \
     k_pair<LJ, CO, SW, SH, OC, EN><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
-                                                             c->e_acc.p, cursor)
+                                                             c->e_acc.p, cursor, EmitOut{})
 #define PICK_EN(LJ, CO, SW, SH, OC) do { if (energy) LAUNCH(LJ, CO, SW, SH, OC, true); else LAUNCH(LJ, CO, SW, SH, OC, false); } while (0)
 #define PICK_OC(LJ, CO, SW, SH) do { if (onecut) PICK_EN(LJ, CO, SW, SH, true); else PICK_EN(LJ, CO, SW, SH, false); } while (0)
 #define PICK_SH(LJ, CO, SW) do { if (shift) PICK_OC(LJ, CO, SW, true); else PICK_OC(LJ, CO, SW, false); } while (0)
@@ -381,11 +435,23 @@ __global__ void k_enumerate(PairParams P, NlistView nl, const float4 *__restrict
     }
 }
 
-int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out) {
+// production != 0: the pairs come out of k_pair itself (EMIT instantiation of the variant pair_compute would
+// launch: same SHIFT / switch / cutoff decision code), on the tile list and tile-order positions exactly as the
+// last force evaluation left them — no refresh, no rebuild — so a list that was rebuilt inside a CUDA graph
+// is the one that gets tested.  Forces / energies go to scratch accumulators.
+int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out, int production) {
     if (!c->have_lj) return fail(c, MDK_ERR_NOT_BOUND, "mdk_get_pairs needs mdk_set_lj");
-    MDK_TRY(nlist_refresh_sorted(c));
-    MDK_TRY(nlist_ensure(c));
-    PairParams P = make_pair_params(c, true, false);
+    if (production) {
+        if (!c->nlist_valid || !c->xs_current)
+            return fail(c, MDK_ERR_NOT_BOUND, "mdk_get_pairs(production): no current tile list (run mdk_compute or a step call first)");
+        const bool do_coul = c->have_coul && c->rc_coul > 0.f;
+        if (do_coul && c->rc_coul != c->rc_lj)
+            return fail(c, MDK_ERR_BAD_ARG, "mdk_get_pairs(production) needs one cutoff for LJ and Coulomb");
+    } else {
+        MDK_TRY(nlist_refresh_sorted(c));
+        MDK_TRY(nlist_ensure(c));
+    }
+    PairParams P = make_pair_params(c, true, production && c->have_coul && c->rc_coul > 0.f);
     int *d_i = nullptr, *d_j = nullptr;
     unsigned long long *d_cnt = nullptr;
     size_t capn = cap > 0 ? (size_t)cap : 1;
@@ -393,8 +459,33 @@ int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int6
     MDK_CUDA(c, cudaMalloc(&d_j, capn * sizeof(int)));
     MDK_CUDA(c, cudaMalloc(&d_cnt, sizeof(unsigned long long)));
     MDK_CUDA(c, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
-    k_enumerate<<<c->sm_count * 4, 256, 0, c->stream>>>(P, nlist_view(c), c->xs.p, c->order.p, d_i, d_j,
-                                                       (unsigned long long)cap, d_cnt);
+    if (!production) {
+        k_enumerate<<<c->sm_count * 4, 256, 0, c->stream>>>(P, nlist_view(c), c->xs.p, c->order.p, d_i, d_j,
+                                                           (unsigned long long)cap, d_cnt);
+    } else {
+        long long *scratch = nullptr;   // forces + energies of the emitting launch are thrown away
+        const size_t words = (size_t)c->n_pad * 3 + MDK_NUM_ENERGIES;
+        cudaError_t e0 = cudaMalloc(&scratch, words * sizeof(long long));
+        if (e0 != cudaSuccess) { cudaFree(d_i); cudaFree(d_j); cudaFree(d_cnt); MDK_CUDA(c, e0); }
+        cudaMemsetAsync(scratch, 0, words * sizeof(long long), c->stream);
+        cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream);
+        EmitOut em{d_i, d_j, c->order.p, (unsigned long long)cap, d_cnt};
+        const bool do_coul = P.rc2_c > 0.f;
+        const bool sw = c->r_switch < c->rc_lj, shift = c->shift_ok && !c->force_canonical;
+        dim3 g(c->sm_count * c->pair_blocks_per_sm), b(PAIR_WARPS * 32);
+        NlistView nl = nlist_view(c);
+#define EMIT_LAUNCH(CO, SW, SH)                                                                                    \
+        k_pair<true, CO, SW, SH, true, true, true><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, \
+                                                                           scratch, scratch + (size_t)c->n_pad * 3, \
+                                                                           c->counters.p + 3, em)
+#define EMIT_SH(CO, SW) do { if (shift) EMIT_LAUNCH(CO, SW, true); else EMIT_LAUNCH(CO, SW, false); } while (0)
+        if (do_coul) { if (sw) EMIT_SH(true, true); else EMIT_SH(true, false); }
+        else         { if (sw) EMIT_SH(false, true); else EMIT_SH(false, false); }
+#undef EMIT_SH
+#undef EMIT_LAUNCH
+        cudaStreamSynchronize(c->stream);
+        cudaFree(scratch);
+    }
     ++c->n_launches;
     unsigned long long h = 0;
     cudaError_t e = cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream);

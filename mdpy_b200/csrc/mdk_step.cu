@@ -101,19 +101,20 @@ int coulomb_bare(mdk_ctx *c) {
 }
 
 // ===========================================================================
-// CHARMM bonded terms.  One thread per term, fp32 geometry on the wrapped
-// tile-order positions, minimum image per bond vector, fixed-point force atomics.
-struct V3 { float x, y, z; };
+// CHARMM bonded terms.  One thread per term, float64 geometry on the wrapped
+// tile-order positions (O(N) terms: the arithmetic is free, and acos / atan2 near their singular points lose
+// digits in fp32), minimum image per bond vector, fixed-point force atomics.
+struct V3 { double x, y, z; };
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 
-struct BoxF { float L[3], invL[3]; };
+struct BoxF { double L[3]; };
 __device__ __forceinline__ V3 mi_vec(float4 a, float4 b, const BoxF &bx) {  // b - a, minimum image
-    return {min_image(b.x - a.x, bx.L[0], bx.invL[0]), min_image(b.y - a.y, bx.L[1], bx.invL[1]),
-            min_image(b.z - a.z, bx.L[2], bx.invL[2])};
+    double dx = (double)b.x - (double)a.x, dy = (double)b.y - (double)a.y, dz = (double)b.z - (double)a.z;
+    return {dx - bx.L[0] * rint(dx / bx.L[0]), dy - bx.L[1] * rint(dy / bx.L[1]), dz - bx.L[2] * rint(dz / bx.L[2])};
 }
 __device__ __forceinline__ void add_force(long long *f_acc, int slot, V3 f) {
     atomic_add_fix(&f_acc[3 * (size_t)slot + 0], to_fix(f.x));
@@ -135,14 +136,14 @@ __global__ void k_bonds(int first, int nb, const int *__restrict__ idx, const fl
     double e = 0.0;
     if (t < nb) {
         int s1 = inv_order[idx[2 * t]], s2 = inv_order[idx[2 * t + 1]];
-        float k = par[2 * t], r0 = par[2 * t + 1];
+        double k = par[2 * t], r0 = par[2 * t + 1];
         V3 d = mi_vec(xs[s1], xs[s2], bx);
-        float r = sqrtf(dot(d, d));
-        float dr = r - r0;
-        e = (double)(k * dr * dr);
-        V3 f = (2.f * k * dr / r) * d;  // force on atom 1 (toward 2 when stretched)
+        double r = sqrt(dot(d, d));
+        double dr = r - r0;
+        e = (k * dr * dr);
+        V3 f = (2. * k * dr / r) * d;  // force on atom 1 (toward 2 when stretched)
         add_force(f_acc, s1, f);
-        add_force(f_acc, s2, -1.f * f);
+        add_force(f_acc, s2, -1. * f);
     }
     block_energy(e, e_acc, MDK_E_BOND);
 }
@@ -155,27 +156,27 @@ __global__ void k_angles(int first, int na, const int *__restrict__ idx, const f
     double e = 0.0;
     if (t < na) {
         int s1 = inv_order[idx[3 * t]], s2 = inv_order[idx[3 * t + 1]], s3 = inv_order[idx[3 * t + 2]];
-        float k = par[4 * t], th0 = par[4 * t + 1], ku = par[4 * t + 2], u0 = par[4 * t + 3];
+        double k = par[4 * t], th0 = par[4 * t + 1], ku = par[4 * t + 2], u0 = par[4 * t + 3];
         float4 p1 = xs[s1], p2 = xs[s2], p3 = xs[s3];
         V3 r21 = mi_vec(p2, p1, bx), r23 = mi_vec(p2, p3, bx);
-        float l21 = sqrtf(dot(r21, r21)), l23 = sqrtf(dot(r23, r23));
-        float ct = dot(r21, r23) / (l21 * l23);
-        ct = fminf(1.f, fmaxf(-1.f, ct));
-        float th = acosf(ct);
-        float st = sqrtf(fmaxf(1.f - ct * ct, 1e-12f));
-        float dEdth = 2.f * k * (th - th0);
+        double l21 = sqrt(dot(r21, r21)), l23 = sqrt(dot(r23, r23));
+        double ct = dot(r21, r23) / (l21 * l23);
+        ct = fmin(1., fmax(-1., ct));
+        double th = acos(ct);
+        double st = sqrt(fmax(1. - ct * ct, 1e-24));
+        double dEdth = 2. * k * (th - th0);
         // d theta / d r1 = -(r23/l23 - ct r21/l21) / (l21 st)
-        V3 e21 = (1.f / l21) * r21, e23 = (1.f / l23) * r23;
+        V3 e21 = (1. / l21) * r21, e23 = (1. / l23) * r23;
         V3 f1 = (dEdth / (l21 * st)) * (e23 - ct * e21);
         V3 f3 = (dEdth / (l23 * st)) * (e21 - ct * e23);
-        e = (double)(k * (th - th0) * (th - th0));
-        add_force(f_acc, s2, -1.f * (f1 + f3));
-        if (ku != 0.f) {  // Urey-Bradley 1-3 spring acts on the end atoms only
+        e = (k * (th - th0) * (th - th0));
+        add_force(f_acc, s2, -1. * (f1 + f3));
+        if (ku != 0.) {  // Urey-Bradley 1-3 spring acts on the end atoms only
             V3 r13 = mi_vec(p1, p3, bx);
-            float l13 = sqrtf(dot(r13, r13));
-            float du = l13 - u0;
-            e += (double)(ku * du * du);
-            V3 fu = (2.f * ku * du / l13) * r13;
+            double l13 = sqrt(dot(r13, r13));
+            double du = l13 - u0;
+            e += (ku * du * du);
+            V3 fu = (2. * ku * du / l13) * r13;
             f1 = f1 + fu;
             f3 = f3 - fu;
         }
@@ -187,20 +188,20 @@ __global__ void k_angles(int first, int na, const int *__restrict__ idx, const f
 
 // Torsion geometry shared by dihedrals and impropers: phi by the reference's atan2
 // convention (utils/geometry.py:84-96), analytic gradient (Blondel & Karplus form).
-__device__ __forceinline__ float torsion(float4 p1, float4 p2, float4 p3, float4 p4, const BoxF &bx, V3 &g1,
+__device__ __forceinline__ double torsion(float4 p1, float4 p2, float4 p3, float4 p4, const BoxF &bx, V3 &g1,
                                          V3 &g2, V3 &g3, V3 &g4) {
     V3 r1 = mi_vec(p1, p2, bx), r2 = mi_vec(p2, p3, bx), r3 = mi_vec(p3, p4, bx);
     V3 n1 = cross(r1, r2), n2 = cross(r2, r3);
-    float l2 = sqrtf(dot(r2, r2));
-    float x = l2 * dot(r1, n2), y = dot(n1, n2);
-    float phi = atan2f(x, y);
-    float n1sq = fmaxf(dot(n1, n1), 1e-20f), n2sq = fmaxf(dot(n2, n2), 1e-20f);
+    double l2 = sqrt(dot(r2, r2));
+    double x = l2 * dot(r1, n2), y = dot(n1, n2);
+    double phi = atan2(x, y);
+    double n1sq = fmax(dot(n1, n1), 1e-30), n2sq = fmax(dot(n2, n2), 1e-30);
     // d phi / d r_a, d phi / d r_d
     g1 = (-l2 / n1sq) * n1;
     g4 = (l2 / n2sq) * n2;
-    const float a = -dot(r1, r2) / (l2 * l2), b = -dot(r3, r2) / (l2 * l2);
-    g2 = (a - 1.f) * g1 + (-b) * g4;
-    g3 = (b - 1.f) * g4 + (-a) * g1;
+    const double a = -dot(r1, r2) / (l2 * l2), b = -dot(r3, r2) / (l2 * l2);
+    g2 = (a - 1.) * g1 + (-b) * g4;
+    g3 = (b - 1.) * g4 + (-a) * g1;
     return phi;
 }
 
@@ -214,12 +215,12 @@ __global__ void k_dihedrals(int first, int nd, const int *__restrict__ idx, cons
     if (t < nd) {
         int s[4];
         for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
-        float k = par[3 * t], nn = par[3 * t + 1], delta = par[3 * t + 2];
+        double k = par[3 * t], nn = par[3 * t + 1], delta = par[3 * t + 2];
         V3 g1, g2, g3, g4;
-        float phi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
-        float arg = nn * phi - delta;
-        e = (double)(k * (1.f + cosf(arg)));
-        float dEdphi = -k * nn * sinf(arg);
+        double phi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
+        double arg = nn * phi - delta;
+        e = (k * (1. + cos(arg)));
+        double dEdphi = -k * nn * sin(arg);
         add_force(f_acc, s[0], (-dEdphi) * g1);
         add_force(f_acc, s[1], (-dEdphi) * g2);
         add_force(f_acc, s[2], (-dEdphi) * g3);
@@ -237,12 +238,12 @@ __global__ void k_impropers(int first, int ni, const int *__restrict__ idx, cons
     if (t < ni) {
         int s[4];
         for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
-        float k = par[2 * t], psi0 = par[2 * t + 1];
+        double k = par[2 * t], psi0 = par[2 * t + 1];
         V3 g1, g2, g3, g4;
-        float psi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
-        float d = psi - psi0;
-        e = (double)(k * d * d);
-        float dE = 2.f * k * d;
+        double psi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
+        double d = psi - psi0;
+        e = (k * d * d);
+        double dE = 2. * k * d;
         add_force(f_acc, s[0], (-dE) * g1);
         add_force(f_acc, s[1], (-dE) * g2);
         add_force(f_acc, s[2], (-dE) * g3);
@@ -260,7 +261,7 @@ static inline void rank_range(const mdk_ctx *c, int n, int &first, int &end) {
 
 int bonded_compute(mdk_ctx *c, unsigned terms) {
     BoxF bx;
-    for (int a = 0; a < 3; ++a) { bx.L[a] = c->box.L[a]; bx.invL[a] = c->box.invL[a]; }
+    for (int a = 0; a < 3; ++a) bx.L[a] = c->box.Ld[a];
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
     PhaseTimer pt(c, PH_BONDED);
     const int T = 128;
@@ -379,11 +380,20 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint32_t atom, uint64_t s
 
 struct StepGeom { double L[3]; float Lf[3], invLf[3]; float skin_half2; };
 
-__device__ __forceinline__ void publish_position(int k, const double x[3], const StepGeom &g, float4 *xs,
-                                                 const float4 *xs_ref, int *flags) {
+__device__ __forceinline__ void publish_position(int k, const double x[3], const double x_old[3], const StepGeom &g,
+                                                 float4 *xs, const float4 *xs_ref, int *flags) {
     float w[3];
+    bool lost = false;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) w[d] = (float)(x[d] - g.L[d] * rint(x[d] / g.L[d]));
+    for (int d = 0; d < 3; ++d) {
+        const double img = rint(x[d] / g.L[d]);
+        w[d] = (float)(x[d] - g.L[d] * img);
+        // a diverging trajectory: the reference wraps after every step and raises ParticleLossError when the new
+        // coordinate is 2 or more images away, |round(x / L)| >= 2 (utils/pbc.py:29-34), i.e. when one step moved
+        // the atom by 1.5 L or more; non-finite coordinates fail the same test
+        if (!(fabs(x[d] - x_old[d]) < 1.5 * g.L[d])) lost = true;
+    }
+    if (lost) flags[0] = 1;
     float4 r = xs_ref[k];
     float dx = min_image(w[0] - r.x, g.Lf[0], g.invLf[0]);
     float dy = min_image(w[1] - r.y, g.Lf[1], g.invLf[1]);
@@ -404,17 +414,18 @@ __global__ void k_verlet(int n, int mode, int quirks, double dt, const int *__re
     if (k >= n) return;
     int a = order[k];
     double inv_m = 1.0 / (double)mass[a];
-    double xn[3];
+    double xn[3], xo[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         double acc = (double)f_acc[3 * (size_t)k + d] * (1.0 / FIX_SCALE) * inv_m;
         double xc = x_cur[3 * a + d];
         double xp = mode == 0 ? xc - vel[3 * a + d] * dt + (quirks ? 1.0 : 0.5) * acc * dt * dt : x_prev[3 * a + d];
         xn[d] = 2.0 * xc - xp + acc * dt * dt;
+        xo[d] = xc;
         x_prev[3 * a + d] = xc;
         x_cur[3 * a + d] = xn[d];
     }
-    publish_position(k, xn, g, xs, xs_ref, flags);
+    publish_position(k, xn, xo, g, xs, xs_ref, flags);
 }
 
 // velocities at the end of VerletIntegrator.integrate (verlet_integrator.py:47-50).
@@ -490,15 +501,16 @@ __global__ void k_langevin(int n, int mode, double dt, double ca, double cb, dou
         for (int d = 0; d < 3; ++d) f_acc[3 * (size_t)k + d] = 0;
     }
     if (mode & 2) {
-        double xi[3], xn[3];
+        double xi[3], xn[3], xo[3];
         normal3(seed, (uint32_t)a, step, xi);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            xn[d] = x_cur[3 * a + d] + cb * dt * v[d] + 0.5 * cb * dt * dt * inv_m * f_new[d] +
+            xo[d] = x_cur[3 * a + d];
+            xn[d] = xo[d] + cb * dt * v[d] + 0.5 * cb * dt * dt * inv_m * f_new[d] +
                     0.5 * cb * dt * inv_m * bs * xi[d];
             x_cur[3 * a + d] = xn[d];
         }
-        publish_position(k, xn, g, xs, xs_ref, flags);
+        publish_position(k, xn, xo, g, xs, xs_ref, flags);
     }
 }
 
@@ -538,15 +550,27 @@ void energies_finish(mdk_ctx *c, unsigned terms) {
     if (terms & MDK_TERM_PME_RECIP) c->last_e[MDK_E_PME_SELF] = c->e_self_bg;
 }
 
+// flags[0] raised by an integrator kernel: the state is unusable from here on
+int check_lost_flag(mdk_ctx *c) {
+    const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
+    if (!h_flags[0]) return MDK_OK;
+    cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream);
+    c->have_pos = false;
+    c->verlet_cached = false; c->langevin_cached = false;
+    c->nlist_valid = false; c->xs_current = false;
+    return fail(c, MDK_ERR_PARTICLE_LOST, "Atom(s) moved beyond 2 PBC image.");
+}
+
 static int fetch_energies(mdk_ctx *c, unsigned terms) {
     MDK_TRY(energies_enqueue(c));
     MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     energies_finish(c, terms);
-    return MDK_OK;
+    return check_lost_flag(c);
 }
 
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks) {
     if (nsteps <= 0) return MDK_OK;
+    if (terms != c->cached_terms) { c->verlet_cached = false; c->langevin_cached = false; c->cached_terms = terms; }
     const int n = c->n, T = 256, B = (n + T - 1) / T;
     StepGeom g = make_geom(c);
     MDK_CUDA(c, c->x_prev.reserve((size_t)3 * n));
@@ -706,7 +730,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
     if (!c->nlist_valid) MDK_TRY(nlist_ensure(c));
     c->xs_current = true;
     const bool stale = c->graph_epoch_built != c->graph_epoch || c->graph_key[0] != dt || c->graph_key[1] != tg ||
-                       c->graph_key[2] != (double)seed || c->graph_key[3] != (double)terms || c->graph_key[4] != ca;
+                       c->graph_seed != seed || c->graph_key[3] != (double)terms || c->graph_key[4] != ca;
     if (stale) {
         graph_destroy(c);
         if (terms & MDK_TERM_PME_RECIP) MDK_TRY(pme_prepare(c));
@@ -715,7 +739,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
         int rc = graph_build_upkeep(c);
         c->in_capture = false;
         if (rc != MDK_OK) { graph_destroy(c); c->graph_epoch_built = -1; return rc; }
-        c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_key[2] = (double)seed; c->graph_key[3] = (double)terms;
+        c->graph_key[0] = dt; c->graph_key[1] = tg; c->graph_seed = seed; c->graph_key[3] = (double)terms;
         c->graph_key[4] = ca; c->graph_epoch_built = c->graph_epoch;
     }
     // the steps of a run find the force accumulator clean: zeroed here once, then by every Langevin update
@@ -761,7 +785,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
 // bookkeeping of a graph run once the stream has been synchronised
 int graph_finish(mdk_ctx *c) {
     const int nsteps = c->graph_pending;
-    if (nsteps <= 0) return MDK_OK;
+    if (nsteps <= 0) return check_lost_flag(c);
     c->graph_pending = 0;
     const int *h_after = reinterpret_cast<const int *>(c->pin_words + 16);
     const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
@@ -775,6 +799,7 @@ int graph_finish(mdk_ctx *c) {
         c->n_launches += (int64_t)nsteps * c->graph_launches_per_step;
         c->n_pair_launches += nsteps;
     }
+    MDK_TRY(check_lost_flag(c));
     if (h_flags[3] & 1) return fail(c, MDK_ERR_OOM, "tile-list pool overflow inside a graph step (raise the pools: more atoms per box than planned)");
     if (h_flags[3] & 2) return fail(c, MDK_ERR_NLIST_STALE, "an i-block outgrew the hoisted-minimum-image bound inside a graph step");
     return MDK_OK;
@@ -783,6 +808,7 @@ int graph_finish(mdk_ctx *c) {
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
                        int graph_min_steps, bool defer_energies) {
     if (nsteps <= 0) return MDK_OK;
+    if (terms != c->cached_terms) { c->verlet_cached = false; c->langevin_cached = false; c->cached_terms = terms; }  // f_prev belongs to another term set
     const int n = c->n, T = 256, B = (n + T - 1) / T;
     StepGeom g = make_geom(c);
     MDK_CUDA(c, c->f_prev.reserve((size_t)3 * n));

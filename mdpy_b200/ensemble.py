@@ -5,9 +5,10 @@ constraints / num_constraints), kept so that reference code driving an Ensemble 
 What differs from the reference is where the sum over constraints happens.  The reference loops over
 its constraints and adds their float arrays on the host (ensemble.py:53-61).  Here, when every bound
 constraint is native and they share one device context, `update()` issues ONE force evaluation for the
-union of their terms: the per-constraint `.forces` then all refer to the one shared
-accumulator and only their sum — which is what Ensemble exposes — is meaningful.  Foreign constraints
-(anything without `is_native`) fall back to the reference's per-constraint protocol.
+union of their terms; each constraint keeps its own energy, and its own `.forces`
+(ensemble.py:56-59 leaves every constraint with its own array) are evaluated lazily, on first access,
+for the same positions.  Foreign constraints (anything without `is_native`) fall back to the reference's
+per-constraint protocol.
 """
 import numpy as np
 

@@ -27,10 +27,15 @@ class LangevinIntegrator(Integrator):
         """One call = the host State goes in, num_steps steps run on the device, the new host State comes
         out (mdk_step_langevin_host).  The State is uploaded on every call — in-place edits of its arrays
         are honoured — and the device keeps its float64 trajectory wherever the host value still equals
-        what the previous call handed out."""
+        what the previous call handed out.  The arrays published as the new State are never written again
+        while anybody holds a reference to them (EnsembleContext.state_buffers)."""
         ctx, terms = self._bind(ensemble)
         state = ensemble.state
         x_out, v_out = ctx.state_buffers()
+        pooled = x_out is not None
+        if not pooled:   # every page-locked block is still referenced (kept frames): plain arrays
+            x_out = np.empty((ctx.dev.n, 3), dtype=np.float32)
+            v_out = np.empty((ctx.dev.n, 3), dtype=np.float32)
         e = ctx.dev.step_langevin_host(self._host_f32(state.positions), self._host_f32(state.velocities), x_out, v_out,
                                        float(self._time_step), float(self._kbt), float(self._gamma), self._seed,
                                        int(num_steps), terms)

@@ -42,6 +42,7 @@ def lib():
         _lib.ora_lj_cell_f32.restype = C.c_longlong
         _lib.ora_lj_cell_f64.restype = C.c_longlong
         _lib.ora_pair_set_f32.restype = C.c_longlong
+        _lib.ora_pair_set_f32_range.restype = C.c_longlong
     return _lib
 
 
@@ -207,11 +208,12 @@ def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn):
 # ----------------------------------------------------------------------------
 
 def nonbonded_bruteforce(positions, box, params, charges, bonded, scaling, rc_lj=12.0, r_on=None,
-                         coul_mode=0, k_e=0.0, alpha=0.0, rc_coul=None, i_range=None):
+                         coul_mode=0, k_e=0.0, alpha=0.0, rc_coul=None, i_range=None, threads=1):
     """All-pairs float64 LJ (+switch) and Coulomb (mode 1: erfc + excluded-pair erf
     correction; mode 2: the reference's bare minimum-image sum).  See mdpy_oracle.c.
     Returns dict(f_lj, f_coul, e_lj, e_coul, e_excl, n_lj, n_coul); forces are only
-    filled for atoms in i_range (default all)."""
+    filled for atoms in i_range (default all).  threads > 1: the rows of i_range are split over host
+    threads (rows are independent; partial energies / counts add up)."""
     pos = np.ascontiguousarray(positions, dtype=np.float64)
     n = pos.shape[0]
     box = np.ascontiguousarray(box, dtype=np.float64).reshape(3)
@@ -220,31 +222,48 @@ def nonbonded_bruteforce(positions, box, params, charges, bonded, scaling, rc_lj
     bonded, scaling = _pad_rows(bonded), _pad_rows(scaling)
     i0, i1 = (0, n) if i_range is None else i_range
     f_lj = np.zeros((n, 3)); f_c = np.zeros((n, 3))
-    en = np.zeros(5); cnt = np.zeros(2, dtype=np.int64)
-    lib().ora_nonbonded_bruteforce(
-        n, _p(pos), _p(box), _p(params), _p(q), _p(bonded), bonded.shape[1], _p(scaling),
-        scaling.shape[1], C.c_double(rc_lj), C.c_double(rc_lj if r_on is None else r_on),
-        int(coul_mode), C.c_double(k_e), C.c_double(alpha),
-        C.c_double(rc_lj if rc_coul is None else rc_coul), int(i0), int(i1), _p(f_lj), _p(f_c),
-        _p(en), _p(cnt))
+
+    def piece(rng):
+        en = np.zeros(5); cnt = np.zeros(2, dtype=np.int64)
+        lib().ora_nonbonded_bruteforce(
+            n, _p(pos), _p(box), _p(params), _p(q), _p(bonded), bonded.shape[1], _p(scaling),
+            scaling.shape[1], C.c_double(rc_lj), C.c_double(rc_lj if r_on is None else r_on),
+            int(coul_mode), C.c_double(k_e), C.c_double(alpha),
+            C.c_double(rc_lj if rc_coul is None else rc_coul), int(rng[0]), int(rng[1]), _p(f_lj), _p(f_c),
+            _p(en), _p(cnt))     # each slice writes its own rows of the shared force arrays
+        return en, cnt
+    if threads <= 1 or i1 - i0 < 2 * threads:
+        parts = [piece((i0, i1))]
+    else:
+        cuts = np.linspace(i0, i1, int(threads) + 1).round().astype(int)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(int(threads)) as ex:
+            parts = list(ex.map(piece, list(zip(cuts[:-1], cuts[1:]))))
+    en = sum(p[0] for p in parts); cnt = sum(p[1] for p in parts)
     return dict(f_lj=f_lj, f_coul=f_c, e_lj=en[0], e_coul=en[1], e_excl=en[2], e_lj_abs=en[3], e_coul_abs=en[4],
                 n_lj=int(cnt[0]), n_coul=int(cnt[1]))
 
 
-def pair_set_f32(positions, box, rc, bonded):
-    """The canonical fp32 in-cutoff pair set, i<j, lexicographic (mdpy_oracle.c:ora_pair_set_f32)."""
+def pair_set_f32(positions, box, rc, bonded, threads=1):
+    """The canonical fp32 in-cutoff pair set, i<j, lexicographic (mdpy_oracle.c:ora_pair_set_f32).
+    threads > 1: rows split over host threads (sqrt-spaced cuts: row i has n-i-1 candidates), results
+    concatenated in row order."""
     pos = np.ascontiguousarray(positions, dtype=np.float32)
     n = pos.shape[0]
     box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
     bonded = _pad_rows(bonded)
-    cap = max(1024, int(n * 700))
-    while True:
-        oi = np.empty(cap, dtype=np.int32); oj = np.empty(cap, dtype=np.int32)
-        cnt = lib().ora_pair_set_f32(n, _p(pos), _p(box), C.c_float(rc), _p(bonded),
-                                     bonded.shape[1], _p(oi), _p(oj), C.c_longlong(cap))
-        if cnt <= cap:
-            return np.stack([oi[:cnt], oj[:cnt]], axis=1)
-        cap = int(cnt)
+
+    def piece(rng):
+        cap = max(1024, int((rng[1] - rng[0]) * 500))
+        while True:
+            oi = np.empty(cap, dtype=np.int32); oj = np.empty(cap, dtype=np.int32)
+            cnt = lib().ora_pair_set_f32_range(n, _p(pos), _p(box), C.c_float(rc), _p(bonded), bonded.shape[1],
+                                               int(rng[0]), int(rng[1]), _p(oi), _p(oj), C.c_longlong(cap))
+            if cnt <= cap:
+                return np.stack([oi[:cnt], oj[:cnt]], axis=1)
+            cap = int(cnt)
+    parts = _run_slices(piece, (0, n), threads)
+    return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
 
 def ewald_recip(positions, charges, box, alpha, kmax, k_e):
@@ -274,3 +293,55 @@ def ewald_exact(positions, charges, box, bonded, k_e, tol_exp=36.0):
                              alpha=alpha, rc_coul=0.5 * box.min())
     f_rec, e_rec, e_self, e_bg = ewald_recip(positions, charges, box, alpha, kmax, k_e)
     return d['f_coul'] + f_rec, d['e_coul'] + d['e_excl'] + e_rec + e_self + e_bg
+
+
+# ----------------------------------------------------------------------------
+# Langevin (G-JF) step restated on the host
+# ----------------------------------------------------------------------------
+# The reference's own LangevinIntegrator is not a usable oracle (force sign, state carry-over);
+# what IS taken from it are the coefficients a, b, sigma (mdpy/integrator/langevin_integrator.py:23-31).
+# The update is the published G-JF scheme (Gronbech-Jensen & Farago, Mol. Phys. 111, 983 (2013)); the noise
+# is Philox4x32-10 (Salmon et al., SC'11: multipliers 0xD2511F53 / 0xCD9E8D57, Weyl keys 0x9E3779B9 /
+# 0xBB67AE85) with counter (atom, step_lo, step_hi, 'MDPY') and key = seed, then Box-Muller on 24-bit uniforms.
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10; all arguments uint32 arrays / scalars.  Returns 4 uint32 arrays."""
+    c = [np.asarray(x, dtype=np.uint64) for x in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0 = np.uint64(k0); k1 = np.uint64(k1)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[0]; p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return [x.astype(np.uint32) for x in c]
+
+
+def langevin_noise(seed, n_atoms, step):
+    """[n,3] standard normal variates of (atom, step): the float32 Box-Muller of the device kernel
+    (uniform = (bits >> 8 + 0.5) 2^-24), evaluated with float64 log / sin / cos."""
+    atom = np.arange(n_atoms, dtype=np.uint32)
+    r = philox4x32_10(atom, np.uint32(step & 0xFFFFFFFF), np.uint32(step >> 32), np.uint32(0x4d445059),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u = [((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24) for x in r]
+    u = [x.astype(np.float64) for x in u]
+    m0, m1 = np.sqrt(-2.0 * np.log(u[0])), np.sqrt(-2.0 * np.log(u[2]))
+    two_pi = float(np.float32(6.283185307179586))
+    return np.stack([m0 * np.cos(two_pi * u[1]), m0 * np.sin(two_pi * u[1]), m1 * np.cos(two_pi * u[3])], axis=1)
+
+
+def gjf_step(x, v, f_old, force_fn, masses, dt, gamma, kT, seed, step):
+    """One G-JF step with a = (1 - g dt/2)/(1 + g dt/2), b = 1/(1 + g dt/2) (langevin_integrator.py:23-31):
+        x' = x + b dt v + b dt^2/(2m) f + b dt/(2m) beta,      beta = sqrt(2 g m kT dt) xi(atom, step)
+        v' = a v + dt/(2m) (a f + f') + b/m beta,              f' = force_fn(x')
+    Returns (x', v', f')."""
+    m = np.asarray(masses, dtype=np.float64).reshape(-1, 1)
+    half = 0.5 * gamma * dt
+    a, b = (1.0 - half) / (1.0 + half), 1.0 / (1.0 + half)
+    beta = np.sqrt(2.0 * gamma * kT * dt * m) * langevin_noise(seed, x.shape[0], step)
+    x_new = x + b * dt * v + 0.5 * b * dt * dt / m * f_old + 0.5 * b * dt / m * beta
+    f_new = force_fn(x_new)
+    v_new = a * v + 0.5 * dt / m * (a * f_old + f_new) + b / m * beta
+    return x_new, v_new, f_new

@@ -163,13 +163,22 @@ void ora_nonbonded_bruteforce(int n, const double *pos, const double *box, const
  * rounding (charmm_nonbonded_constraint.py:85-90); the two differ only for pairs within
  * an ulp of the cutoff.  Pairs are emitted i<j, row-major, excluded (bonded) pairs
  * skipped.  Returns the pair count (and writes at most `cap`). */
+long long ora_pair_set_f32_range(int n, const float *pos, const float *box, float rc, const int *bonded,
+                                 int wb, int i0, int i1, int *out_i, int *out_j, long long cap);
+
 long long ora_pair_set_f32(int n, const float *pos, const float *box, float rc, const int *bonded,
                            int wb, int *out_i, int *out_j, long long cap) {
+    return ora_pair_set_f32_range(n, pos, box, rc, bonded, wb, 0, n, out_i, out_j, cap);
+}
+
+/* rows i in [i0, i1) of the same set (the rows are independent: host threads take slices) */
+long long ora_pair_set_f32_range(int n, const float *pos, const float *box, float rc, const int *bonded,
+                                 int wb, int i0, int i1, int *out_i, int *out_j, long long cap) {
     const float MAGIC = 12582912.0f;
     const float rc2 = rc * rc;
     float invL[3] = {1.0f / box[0], 1.0f / box[1], 1.0f / box[2]};
     long long cnt = 0;
-    for (int i = 0; i < n; ++i) {
+    for (int i = i0; i < i1; ++i) {
         const int *bi = bonded + (size_t)i * wb;
         for (int j = i + 1; j < n; ++j) {
             float d[3];

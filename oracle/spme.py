@@ -60,14 +60,7 @@ def influence_function(box, grid, order, alpha, k_e):
     return G
 
 
-def spme_reciprocal(positions, charges, box, grid, order, alpha, k_e):
-    """Returns (forces [N,3], E_rec).  positions may be anywhere (wrapped internally)."""
-    pos = np.asarray(positions, dtype=np.float64)
-    q = np.asarray(charges, dtype=np.float64).reshape(-1)
-    box = np.asarray(box, dtype=np.float64).reshape(3)
-    grid = tuple(int(g) for g in grid)
-    n = pos.shape[0]
-    pos = pos - box * np.round(pos / box)
+def _spline_terms(pos, box, grid, order):
     th, dth, idx = [], [], []
     for a in range(3):
         u = (pos[:, a] / box[a] + 0.5) * grid[a]
@@ -75,31 +68,55 @@ def spme_reciprocal(positions, charges, box, grid, order, alpha, k_e):
         t, d = bspline_weights(u - k0, order)
         th.append(t); dth.append(d)
         idx.append((k0.astype(np.int64)[:, None] - order + 1 + np.arange(order)[None, :]) % grid[a])
-    Q = np.zeros(grid)
-    ix = idx[0][:, :, None, None]; iy = idx[1][:, None, :, None]; iz = idx[2][:, None, None, :]
-    wgt = q[:, None, None, None] * th[0][:, :, None, None] * th[1][:, None, :, None] * th[2][:, None, None, :]
-    np.add.at(Q, (np.broadcast_to(ix, wgt.shape), np.broadcast_to(iy, wgt.shape), np.broadcast_to(iz, wgt.shape)), wgt)
+    return th, dth, idx
+
+
+def spme_reciprocal(positions, charges, box, grid, order, alpha, k_e, atoms=None, chunk=65536):
+    """Returns (forces [N,3], E_rec).  positions may be anywhere (wrapped internally).
+    atoms: index array — forces are gathered for these atoms only (rows of the others stay zero); the mesh
+    always carries every charge.  Atoms are processed in chunks so that million-atom boxes fit in memory."""
+    pos = np.asarray(positions, dtype=np.float64)
+    q = np.asarray(charges, dtype=np.float64).reshape(-1)
+    box = np.asarray(box, dtype=np.float64).reshape(3)
+    grid = tuple(int(g) for g in grid)
+    n = pos.shape[0]
+    pos = pos - box * np.round(pos / box)
+    nx, ny, nz = grid
+    Q = np.zeros(nx * ny * nz)
+    for lo in range(0, n, chunk):
+        sl = slice(lo, min(n, lo + chunk))
+        th, _, idx = _spline_terms(pos[sl], box, grid, order)
+        flat = ((idx[0][:, :, None, None] * ny + idx[1][:, None, :, None]) * nz + idx[2][:, None, None, :])
+        wgt = q[sl, None, None, None] * th[0][:, :, None, None] * th[1][:, None, :, None] * th[2][:, None, None, :]
+        Q += np.bincount(flat.ravel(), weights=wgt.ravel(), minlength=Q.size)
+    Q = Q.reshape(grid)
     G = influence_function(box, grid, order, alpha, k_e)
     FQ = np.fft.fftn(Q)
     e_rec = 0.5 * float((G * np.abs(FQ) ** 2).sum())
-    phi = np.real(np.fft.ifftn(G * FQ)) * Q.size
-    p = phi[np.broadcast_to(ix, wgt.shape), np.broadcast_to(iy, wgt.shape), np.broadcast_to(iz, wgt.shape)]
-    fx = (dth[0][:, :, None, None] * th[1][:, None, :, None] * th[2][:, None, None, :] * p).sum((1, 2, 3))
-    fy = (th[0][:, :, None, None] * dth[1][:, None, :, None] * th[2][:, None, None, :] * p).sum((1, 2, 3))
-    fz = (th[0][:, :, None, None] * th[1][:, None, :, None] * dth[2][:, None, None, :] * p).sum((1, 2, 3))
+    phi = (np.real(np.fft.ifftn(G * FQ)) * Q.size).ravel()
+    forces = np.zeros((n, 3))
+    which = np.arange(n) if atoms is None else np.asarray(atoms, dtype=np.int64)
     scale = np.array(grid) / box
-    forces = -q[:, None] * np.stack([fx, fy, fz], 1) * scale[None, :]
+    for lo in range(0, len(which), chunk):
+        sel = which[lo:lo + chunk]
+        th, dth, idx = _spline_terms(pos[sel], box, grid, order)
+        flat = ((idx[0][:, :, None, None] * ny + idx[1][:, None, :, None]) * nz + idx[2][:, None, None, :])
+        p = phi[flat]
+        fx = (dth[0][:, :, None, None] * th[1][:, None, :, None] * th[2][:, None, None, :] * p).sum((1, 2, 3))
+        fy = (th[0][:, :, None, None] * dth[1][:, None, :, None] * th[2][:, None, None, :] * p).sum((1, 2, 3))
+        fz = (th[0][:, :, None, None] * th[1][:, None, :, None] * dth[2][:, None, None, :] * p).sum((1, 2, 3))
+        forces[sel] = -q[sel, None] * np.stack([fx, fy, fz], 1) * scale[None, :]
     return forces, e_rec
 
 
-def pme_total(positions, charges, box, bonded, grid, order, alpha, rc, k_e):
+def pme_total(positions, charges, box, bonded, grid, order, alpha, rc, k_e, threads=1):
     """Full PME electrostatics in float64 (direct erfc inside rc + reciprocal + self + background +
     excluded-pair correction) — what ElectrostaticPMEConstraint evaluates.
     Returns (forces, dict of energy terms)."""
     from . import cpu_oracle as ora
     n = np.asarray(positions).shape[0]
     d = ora.nonbonded_bruteforce(positions, box, np.zeros((n, 4)), charges, bonded, -np.ones((n, 1), dtype=np.int32),
-                                 rc_lj=0.0, coul_mode=1, k_e=k_e, alpha=alpha, rc_coul=rc)
+                                 rc_lj=0.0, coul_mode=1, k_e=k_e, alpha=alpha, rc_coul=rc, threads=threads)
     f_rec, e_rec = spme_reciprocal(positions, charges, box, grid, order, alpha, k_e)
     q = np.asarray(charges, dtype=np.float64).reshape(-1)
     V = float(np.prod(np.asarray(box, dtype=np.float64)))

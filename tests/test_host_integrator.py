@@ -70,23 +70,55 @@ def test_integrate_hands_the_host_state_in_and_installs_what_comes_back(stub_ens
     assert ens.constraints[0].potential_energy == -3.0
 
 
-def test_state_buffers_alternate_and_the_previous_output_is_the_next_input(stub_ensemble):
+def test_state_arrays_are_never_overwritten_while_referenced(stub_ensemble):
+    """The arrays a call publishes as the new State come from a pool of page-locked blocks; a block is reused only
+    when nobody holds it any more, so kept frames stay intact (the reference allocates a fresh array per
+    set_positions, state.py:58-60)."""
     s, ens = stub_ensemble
-    dev = _native.context_of(ens).dev
+    ctx = _native.context_of(ens)
+    dev = ctx.dev
     integ = LangevinIntegrator(2.0, 300, 1e-3, seed=1)
     integ.integrate(ens, 1)
     first_out = ens.state.positions
+    first_copy = first_out.copy()
     integ.integrate(ens, 1)
-    second_out = ens.state.positions
     steps = [c for c in dev.calls if isinstance(c, tuple)]
     assert steps[1][1] == id(first_out)               # the State array itself goes in: no copy, no revision check
-    assert second_out is not first_out                # ... and is not the buffer being written
-    integ.integrate(ens, 1)
-    assert ens.state.positions is first_out           # two pairs of page-locked buffers take turns
+    assert ens.state.positions is not first_out       # ... and is not the buffer being written
+    frames = [ens.state.positions]
+    for _ in range(5):                                # a dumper that keeps references
+        integ.integrate(ens, 1)
+        frames.append(ens.state.positions)
+    assert np.array_equal(first_out, first_copy)
+    for a, b in zip(frames[:-1], frames[1:]):
+        assert np.allclose(b, a + 0.01, atol=1e-6)    # every kept frame is still its own step
+    # views count as references too
+    view = ens.state.positions[::2]
+    keep = view.copy()
+    for _ in range(3):
+        integ.integrate(ens, 1)
+    assert np.array_equal(view, keep)
+    # once nobody holds the old arrays the blocks are reused: the pool stops growing
+    del frames, first_out, view
+    for _ in range(4):
+        integ.integrate(ens, 1)
+    size = len(ctx._state_pool)
+    used = set()
+    for _ in range(6):
+        integ.integrate(ens, 1)
+        used.add(id(ens.state.positions))
+    assert len(ctx._state_pool) == size <= ctx.MAX_STATE_BUFFERS
+    assert len(used) == 2                             # steady state: two blocks take turns
     # in-place edits of the State arrays are part of the next call's input
     ens.state.positions[0, 0] = 5.0
     integ.integrate(ens, 1)
     assert ens.state.positions[0, 0] == pytest.approx(5.01, abs=1e-6)
+    # a caller that keeps more frames than the pool holds gets plain arrays, still never overwritten
+    hoard = []
+    for _ in range(ctx.MAX_STATE_BUFFERS + 3):
+        integ.integrate(ens, 1)
+        hoard.append((ens.state.positions, ens.state.positions.copy()))
+    assert all(np.array_equal(a, b) for a, b in hoard)
 
 
 def test_a_new_integrator_object_drops_the_device_step_caches(stub_ensemble):
@@ -159,6 +191,18 @@ def test_ensemble_update_fuses_native_constraints_into_one_evaluation(monkeypatc
     assert ens.potential_energy == pytest.approx(-1.0 + 0.25 + 0.125)
     m = np.asarray(ens.topology.masses, dtype=np.float64).reshape(-1)
     assert ens.kinetic_energy > 0 and ens.total_energy == pytest.approx(ens.potential_energy + ens.kinetic_energy)
+    # each constraint's own forces: evaluated on first access, with its own terms, energy kept
+    lj = ens.constraints[0]
+    e_lj = lj.potential_energy
+    f = lj.forces
+    computes = [c for c in dev.calls if isinstance(c, tuple) and c[0] == 'compute']
+    assert computes[-1] == ('compute', lj.terms) and f.shape == (900, 3) and lj.potential_energy == e_lj
+    assert lj.forces is f and len([c for c in dev.calls if isinstance(c, tuple) and c[0] == 'compute']) == len(computes)
+    ens.update()
+    ens.state.set_positions(ens.state.positions + np.float32(0.01))
+    with pytest.raises(RuntimeError):
+        ens.constraints[1].forces          # positions moved on since the fused evaluation
+    computes = [c for c in dev.calls if isinstance(c, tuple) and c[0] == 'compute']
     n_before = len(computes)
     ens.update(fused=False)
     computes = [c for c in dev.calls if isinstance(c, tuple) and c[0] == 'compute']

@@ -268,3 +268,30 @@ def test_restatement_matches_reference_at_benchmark_size():
     assert rel_rms(f[::stride], g['coul_forces_strided']) < 1e-9
     assert (f ** 2).sum() == pytest.approx(float(g['coul_force_sumsq']), rel=1e-9)
     assert e == pytest.approx(float(g['coul_energy']), rel=1e-8)
+
+
+def test_langevin_oracle_is_pinned_to_published_philox_vectors_and_gjf_limits():
+    """oracle/cpu_oracle.py:philox4x32_10 against the known-answer vectors published with Random123
+    (kat_vectors: philox4x32 10 rounds), and the G-JF restatement against its analytic limits: gamma = 0 is
+    velocity Verlet; a free particle's velocity variance after many steps is kT/m."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = ora.philox4x32_10(*[np.uint32(c) for c in ctr], key[0], key[1])
+        assert tuple(int(x) for x in got) == want
+    z = ora.langevin_noise(7, 100000, 3)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01 and not np.array_equal(z, ora.langevin_noise(7, 100000, 4))
+    assert np.array_equal(z, ora.langevin_noise(7, 100000, 3))          # counter based: reproducible
+    # gamma = 0: x' = x + dt v + dt^2 f / 2m, v' = v + dt (f + f') / 2m with a harmonic force
+    rng = np.random.default_rng(0)
+    x, v, m, k, dt = rng.normal(size=(5, 3)), rng.normal(size=(5, 3)), np.array([1., 2, 3, 4, 5]), 0.3, 0.1
+    xn, vn, fn = ora.gjf_step(x, v, -k * x, lambda y: -k * y, m, dt, 0.0, 1.0, 1, 0)
+    assert np.allclose(xn, x + dt * v + 0.5 * dt * dt * (-k * x) / m[:, None])
+    assert np.allclose(vn, v + 0.5 * dt * (-k * x - k * xn) / m[:, None])
+    # free particles in a bath: <v^2> -> kT / m
+    n, kT, gamma = 20000, 0.5, 0.5
+    x = np.zeros((n, 3)); v = np.zeros((n, 3)); f = np.zeros((n, 3)); mm = np.full(n, 2.0)
+    for step in range(60):
+        x, v, f = ora.gjf_step(x, v, f, lambda y: np.zeros_like(y), mm, 0.5, gamma, kT, 11, step)
+    assert (v ** 2).mean() == pytest.approx(kT / 2.0, rel=0.02)

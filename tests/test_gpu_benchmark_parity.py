@@ -209,6 +209,11 @@ def test_config3_forces_and_energies_match_float64_oracle():
     assert abs(pme.potential_energy - e_el) < ENERGY_TOL * scale
     assert e[2] == pytest.approx(e_rec, rel=ENERGY_TOL) and e[4] == pytest.approx(t['e_excl'], rel=ENERGY_TOL)
     assert pme._ctx.dev.timing()['shift_ok'] == 1.0
+    # size-independent properties: Newton's third law, idempotence (the list is reused, results are bitwise equal)
+    f_lj = lj.forces.astype(np.float64)
+    assert np.abs(f_lj.sum(0)).max() < 1e-6 * np.abs(f_lj).sum()
+    lj.update()
+    assert np.array_equal(lj.forces.astype(np.float64), f_lj)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -195,11 +195,26 @@ def test_config1_bonded_terms_match_reference():
               CharmmDihedralConstraint=CharmmDihedralConstraint(g['CharmmDihedralConstraint_par']),
               CharmmImproperConstraint=CharmmImproperConstraint(g['CharmmImproperConstraint_par']))
     ens.add_constraints(*cs.values())
+    # The gates (1e-5 force RMS, 1e-6 energy) are taken on IDENTICAL inputs: oracle/bonded.py (equal to the reference
+    # to 1e-10 on the reference's float64 inputs, tests/test_oracle.py) evaluated at the float32 positions the
+    # device holds.  The PDB's 3-decimal coordinates are not float32 numbers, and a 1e-6 A shift of a stiff
+    # bond moves its force by ~1e-4 of itself; against the golden values themselves the distance is recorded.
+    from oracle import bonded
+    x32 = ens.state.positions.astype(np.float64)
+    fns = dict(CharmmBondConstraint=bonded.bonds, CharmmAngleConstraint=bonded.angles, CharmmImproperConstraint=bonded.impropers)
     for name, c in cs.items():
         c.update()
-        assert c.potential_energy == pytest.approx(float(g[name + '_energy']), rel=2e-6), name
-        if name != 'CharmmDihedralConstraint':   # the reference's dihedral force is not the gradient (DESIGN Q12)
-            assert rel_rms(c.forces, g[name + '_forces']) < 2e-5, name
+        if name == 'CharmmDihedralConstraint':   # the reference's dihedral force is not the gradient (DESIGN Q12)
+            e_ref = bonded.dihedral_energy(x32, g['box'], g[name + '_idx'], g[name + '_par'])
+            assert c.potential_energy == pytest.approx(e_ref, rel=ENERGY_TOL), name
+            assert c.potential_energy == pytest.approx(float(g[name + '_energy']), rel=1e-5), name
+            continue
+        f_ref, e_ref = fns[name](x32, g['box'], g[name + '_idx'], g[name + '_par'])
+        assert rel_rms(c.forces, f_ref) < FORCE_TOL, name
+        assert c.potential_energy == pytest.approx(e_ref, rel=ENERGY_TOL), name
+        # and the reference's own numbers (float64 inputs): within what the input rounding explains
+        assert rel_rms(c.forces, g[name + '_forces']) < 1e-4, name
+        assert c.potential_energy == pytest.approx(float(g[name + '_energy']), rel=1e-5), name
 
 
 def test_pair_set_is_bit_exact():
@@ -333,7 +348,7 @@ def test_verlet_matches_reference_trajectory():
     assert integ.is_cached
 
 
-def test_verlet_nve_energy_is_bounded():
+def test_verlet_nve_energy_is_bounded_short():
     """Bounded NVE drift on a 23k-atom water box (own kinetic energy, textbook velocities; Q4)."""
     s = synthetic.water_box(7852, 20260001)
     ens = s.ensemble(cutoff=9.0, pme=True, grid=(64, 64, 64))
@@ -349,7 +364,7 @@ def test_verlet_nve_energy_is_bounded():
     assert np.abs(e_tot - e_tot[0]).max() < 1e-2 * np.mean(ke)
 
 
-def test_langevin_equipartition():
+def test_langevin_equipartition_quick():
     s = synthetic.water_box(2000, 5, box=np.full(3, 39.2))
     ens = s.ensemble(cutoff=9.0, pme=True, grid=(40, 40, 40))
     integ = LangevinIntegrator(0.5, 300, 0.02, seed=11)
@@ -407,26 +422,4 @@ def test_langevin_host_state_edits_are_honoured():
         integ.integrate(ens, 1)
 
 
-# ---------------------------------------------------------------------------------------------
-# benchmark sizes: size-independent properties + sub-sampled oracle
-def test_92k_box_subsample_parity_and_momentum():
-    s = synthetic.solvated_protein_box()
-    ens = s.ensemble(cutoff=12.0, switch=10.0, pme=True, bonded=False)
-    lj, pme = ens.constraints
-    lj.update()
-    f_lj = lj.forces.astype(np.float64)
-    assert np.abs(f_lj.sum(0)).max() < 1e-6 * np.abs(f_lj).sum()      # Newton's third law
-    rng = np.random.default_rng(0)
-    sub = np.sort(rng.choice(s.num_particles, size=24, replace=False))
-    topo = ens.topology
-    for i in sub:
-        t = ora.nonbonded_bruteforce(ens.state.positions, s.box, s.lj_table(), s.charges, topo.bonded_particles,
-                                     topo.scaling_particles, rc_lj=12.0, r_on=10.0, coul_mode=1, k_e=K_E,
-                                     alpha=pme.alpha, rc_coul=12.0, i_range=(int(i), int(i) + 1))
-        assert np.linalg.norm(f_lj[i] - t['f_lj'][i]) < 2e-5 * max(np.linalg.norm(t['f_lj'][i]), np.abs(f_lj).mean())
-    # idempotence: a second evaluation on the same positions reuses the list and is bitwise identical
-    lj.update()
-    assert np.array_equal(lj.forces.astype(np.float64), f_lj)
-    pme.update()
-    f = pme.forces.astype(np.float64)
-    assert np.abs(f.sum(0)).max() < 1e-5 * np.abs(f).sum()   # SPME conserves momentum only to discretisation error
+# benchmark sizes (configs 1-4): tests/test_gpu_benchmark_parity.py

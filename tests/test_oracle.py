@@ -295,3 +295,17 @@ def test_langevin_oracle_is_pinned_to_published_philox_vectors_and_gjf_limits():
     for step in range(60):
         x, v, f = ora.gjf_step(x, v, f, lambda y: np.zeros_like(y), mm, 0.5, gamma, kT, 11, step)
     assert (v ** 2).mean() == pytest.approx(kT / 2.0, rel=0.02)
+
+
+def test_bonded_restatement_matches_reference_on_config1():
+    """oracle/bonded.py against the unmodified reference's bonded constraints on the example system (DOUBLE mode)."""
+    from oracle import bonded
+    g = load_golden('config1_f64')
+    x, box = g['positions'], g['box']
+    for name, fn in (('CharmmBondConstraint', bonded.bonds), ('CharmmAngleConstraint', bonded.angles),
+                     ('CharmmImproperConstraint', bonded.impropers)):
+        f, e = fn(x, box, g[name + '_idx'], g[name + '_par'])
+        assert rel_rms(f, g[name + '_forces']) < 1e-10, name
+        assert e == pytest.approx(float(g[name + '_energy']), rel=1e-10), name
+    e = bonded.dihedral_energy(x, box, g['CharmmDihedralConstraint_idx'], g['CharmmDihedralConstraint_par'])
+    assert e == pytest.approx(float(g['CharmmDihedralConstraint_energy']), rel=1e-10)

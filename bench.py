@@ -4,20 +4,26 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME]
 
 A "step" is one MD step of the hot path on one synthetic box: neighbour-list upkeep, CHARMM LJ +
-erfc direct space over the tile list, PME reciprocal (spread, cuFFT, influence function, gather),
-bonded terms and the Langevin position/velocity update.  Default workload = BASELINE.json configs[1]:
-23 556-atom TIP3P box, 9 A cutoff, PME 64^3 order 4, Langevin 300 K, 2 fs.
+erfc direct space over the tile list, PME reciprocal (spread, FFT, influence function, gather),
+bonded terms and the Langevin position/velocity update.
 
-Prints ONE JSON line (rank 0).  metric = atom-steps/s (BASELINE.json names "ns/day and atom-steps/s";
-atom-steps/s is the one that stays comparable when the box changes with the GPU count: N = 1 runs
-configs[1], the 23k water box; N > 1 runs configs[3], the 1.07 M-atom box the 1/2/4/8-GPU numbers are
-quoted on); ns_per_day rides along.  value = state resident on the device (CUDA events around K
-steps); e2e = the same metric through the drop-in integrator call with HOST state: every step is one
-LangevinIntegrator.integrate(ensemble, 1), i.e. positions + velocities H2D from page-locked memory,
-one step, positions + velocities + energies D2H (mdk_step_langevin_host).  roofline = the pair kernel against the FP32 CUDA-core
-peak (70 flop per in-cutoff pair), roofline_pme = spread/FFT/gather against measured
-HBM bandwidth.  cpu_baseline / --impl reference = the reference's per-step work (27-cell-list LJ +
-all-pairs Coulomb, no PME) restated in C (oracle/), on the host cores.
+Workload: the SAME box at every GPU count — BASELINE.json configs[3], the 1 066 628-atom solvated box
+(12/10 A switch, PME 216^3, Langevin 300 K, 2 fs; it fits one GPU), so the driver's 1 -> 8 scaling curve is
+the strong scaling of one system.  At N = 1 the line also carries `sub_records` for configs[1] (water_23k)
+and configs[2] (protein_92k, the config the >= 10x target is quoted on), each with value / e2e / roofline
+and the reference's own numba.cuda path run live on the same GPU from baseline/_ref.
+
+Prints ONE JSON line (rank 0).  metric = atom-steps/s (BASELINE.json names "ns/day and atom-steps/s");
+ns_per_day rides along.  value = state resident on the device: W warm-up steps, then REPS = 5 repetitions of
+exactly K steps, each bracketed by a barrier and timed with CUDA events on the context stream (max over
+ranks); the MEDIAN repetition is the value, all of them are listed in reps_ms.  The nvidia-smi clock sampler
+starts >= 1 s before the first repetition while the GPU runs the same steps untimed, so the clocks are
+sampled under the timed load whatever K is.  e2e = the same metric through the drop-in integrator call
+with HOST state: every step is one LangevinIntegrator.integrate(ensemble, 1), i.e. positions + velocities
+H2D, one step, positions + velocities + energies D2H (mdk_step_langevin_host).  roofline = the pair kernel
+against the FP32 CUDA-core peak (70 flop per in-cutoff pair), roofline_pme = spread / FFT / gather
+against measured HBM bandwidth.  cpu_baseline / --impl reference = the reference's per-step work
+(27-cell-list LJ + all-pairs Coulomb, no PME) restated in C (oracle/), on the host cores.
 """
 import argparse
 import json
@@ -186,11 +192,203 @@ def run_reference(args, cfg):
 
 
 # ---------------------------------------------------------------------------------------------
+RELAX = ((0.1, 0.2, 200), (0.5, 0.05, 200), (1.0, 0.01, 300))   # (dt fs, gamma 1/fs, steps): untimed lattice relaxation
+REPS = 5                                                         # timed repetitions of K steps; the median is reported
+
+
+class Workload:
+    """One synthetic box on this rank's GPU, relaxed and warmed up, ready to be timed."""
+
+    def __init__(self, name, args):
+        from mdpy_b200 import _native
+        from mdpy_b200.integrator import LangevinIntegrator
+        from mdpy_b200.unit import KB, Quantity, default_energy_unit, kelvin
+        self.name, self.cfg = name, CONFIGS[name]
+        cfg = self.cfg
+        self.system = build_system(cfg)
+        self.n = self.system.num_particles
+        self.ens = self.system.ensemble(cutoff=cfg['cutoff'], switch=cfg['switch'], pme=True, ewald_error=1e-6,
+                                        grid=cfg['grid'], order=4, bonded=True)
+        self.ctx = _native.context_of(self.ens)
+        self.dev = self.ctx.dev
+        self.kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
+        self.dt = cfg['dt']
+        self.skin = float(cfg.get('skin', 2.0))
+        if self.skin != 2.0:
+            self.dev.set_nlist(self.skin)
+        if args.no_graph:
+            self.dev.set_option('graph', 0)
+        for kv in filter(None, os.environ.get('MDK_OPTS', '').split(',')):   # experiments: MDK_OPTS=concurrent=0,graph=1
+            k, v = kv.split('=')
+            self.dev.set_option(k, float(v))
+        # relax the lattice start (untimed; every rank runs it redundantly and deterministically, so all
+        # ranks hold bit-identical state): short, strongly damped steps, then the production step
+        for rdt, gamma, steps in RELAX:
+            LangevinIntegrator(rdt, TEMPERATURE, gamma, seed=1).integrate(self.ens, max(1, int(steps * args.relax)))
+        self.integ = LangevinIntegrator(self.dt, TEMPERATURE, GAMMA, seed=1)
+        self.integ.integrate(self.ens, 20)
+        self.terms = 0
+        for c in self.ens.constraints:
+            self.terms |= c.terms
+        self.terms &= int(os.environ.get('MDK_TERMS_MASK', '0xffff'), 0)   # experiments: drop force terms from the direct step calls
+
+    def step(self, nsteps):
+        self.dev.step_langevin(self.dt, self.kT, GAMMA, 1, nsteps, self.terms)
+
+    def phase_profile(self, steps):
+        """Per-phase device times (ms per step): a separate untimed pass, per-phase events add syncs."""
+        self.dev.set_profiling(2)
+        self.step(steps)
+        ph = self.dev.timing()
+        self.dev.set_profiling(0)
+        keys = ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms', 'comm_ms')
+        out = {k: ph[k] / steps for k in keys}
+        out.update({k: ph[k] for k in ('work_units', 'j_chunks', 'masked_chunks', 'seg_chunks')})
+        return out
+
+    def pair_count(self):
+        """In-cutoff pair count of the current configuration (the flop model's unit count)."""
+        lj = self.ens.constraints[0]
+        self.ens.state._positions = self.dev.download_positions()
+        self.ctx._pos_rev = None
+        lj._configure(); self.ctx.sync_positions()
+        return self.dev.pair_count()
+
+    def timed_reps(self, steps, reps, reduce_max, barrier):
+        """reps x (K steps, device resident, CUDA events on the ctx stream around the whole call).
+        Returns (per-rep ms [max over ranks], launches of this rank over all reps, rebuilds)."""
+        dev = self.dev
+        dev.set_profiling(1)
+        before = dev.timing()
+        ms = []
+        for _ in range(reps):
+            barrier()
+            self.step(steps)
+            ms.append(reduce_max(dev.timing()['total_ms']))
+        barrier()
+        after = dev.timing()
+        dev.set_profiling(0)
+        return ms, after['launches'] - before['launches'], int(after['rebuilds'] - before['rebuilds'])
+
+    def e2e(self, steps, reduce_max, barrier):
+        """The drop-in integrator call with HOST state, one call per step: every call uploads ensemble.state
+        (positions + velocities, float32), runs one step and downloads the new state and the energies."""
+        from mdpy_b200.integrator import LangevinIntegrator
+        dev, ens = self.dev, self.ens
+        ens.state._positions = dev.download_positions()      # the timed region stepped the device directly
+        ens.state._velocities = dev.download_velocities()
+        if hasattr(ens.state, 'revision'):
+            ens.state.revision += 1
+        integ = LangevinIntegrator(self.dt, TEMPERATURE, GAMMA, seed=2)
+        for _ in range(5):   # warm-up of the host path (graph capture of the single-step variant, pinned buffers)
+            integ.integrate(ens, 1)
+        l0 = dev.timing()['launches']
+        secs = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                integ.integrate(ens, 1)
+            secs.append(reduce_max(time.perf_counter() - t0))
+        sec = float(np.median(secs))
+        return dict(value=self.n * steps / sec, unit='atom-steps/s', h2d_bytes_per_step=24 * self.n,
+                    d2h_bytes_per_step=24 * self.n + 224, steps=steps, reps=3, ms_per_step=sec * 1e3 / steps,
+                    ns_per_day=ns_per_day(steps, sec, self.dt),
+                    gpu_launches_per_step=(dev.timing()['launches'] - l0) / (3 * steps),
+                    potential_energy_last_step=float(ens.potential_energy),
+                    path='LangevinIntegrator.integrate(ensemble, 1) per step: host State (float32 positions + velocities) '
+                         '-> mdk_step_langevin_host -> host State + energies; wall clock, median of 3 x %d calls, max over ranks' % steps)
+
+
+def roofline_records(w, ph, n_pairs, slots_single, world, peaks):
+    cfg = w.cfg
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json'))).get(w.name)
+    except (OSError, ValueError):
+        pass
+    fp32_peak = 148 * 128 * 2 * peaks['sm_max_mhz'] * 1e6 / 1e12
+    share = (ph['j_chunks'] * 1024.0) / max(1.0, slots_single)      # this rank's share of the pair slots (1 at N = 1)
+    achieved = FLOP_PER_PAIR * n_pairs * share / (ph['pair_ms'] * 1e-3) / 1e12
+    K = int(np.prod(cfg['grid']))
+    pme_ms = ph['spread_ms'] + ph['fft_ms'] + ph['gather_ms']
+    pme_bytes = 44.0 * w.n + 34.0 * K
+    pme_gbs = pme_bytes / max(pme_ms, 1e-9) / 1e6
+    roof = dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak,
+                traffic=None if traffic is None or world > 1 else traffic['bytes'],
+                traffic_source=None if traffic is None or world > 1 else traffic['source'] + ' (ncu dram bytes read + written per launch)',
+                kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=ph['pair_ms'],
+                peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source'],
+                note='rank 0 share of the pair work at N > 1' if world > 1 else 'whole pair kernel; kernel_ms = CUDA events around the launch, per-phase pass')
+    roof_pme = dict(bound='hbm', achieved=pme_gbs, peak=peaks['hbm_gbs'], unit='GB/s', frac=pme_gbs / peaks['hbm_gbs'],
+                    bytes_per_step=pme_bytes, kernels_ms=pme_ms, peak_source=peaks['source'],
+                    note='spread + mesh FFT / influence function + gather (44 N + 34 K algorithmic bytes, SURVEY 8d); the mesh is L2 resident')
+    return roof, roof_pme
+
+
+def numba_cuda_reference(name, budget_s=170):
+    """The reference's own numba.cuda path on this GPU, live (baseline/ref_numba_cuda.py in a subprocess: the
+    unmodified package from baseline/_ref).  Falls back to the value recorded in round 1 when the subprocess fails."""
+    rec = None
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'baseline', 'ref_numba_cuda.py'), '--config', name, '--evals', '2'],
+                             capture_output=True, text=True, timeout=budget_s)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                d = json.loads(ln)
+                if 'unavailable' not in d:
+                    rec = dict(atom_steps_per_s=d['atom_steps_per_s'], ns_per_day=d['ns_per_day_at_2fs'],
+                               seconds_per_step=d['seconds_per_step'], live=True,
+                               source='baseline/ref_numba_cuda.py run now on this GPU (unmodified reference from baseline/_ref: '
+                                      'plain-cutoff LJ + bare 27-cell Coulomb, no PME, no bonded terms, no integrator)')
+                else:
+                    rec = dict(unavailable=d['unavailable'], live=True)
+                break
+    except (subprocess.TimeoutExpired, OSError, ValueError, KeyError) as e:
+        rec = dict(unavailable='live run failed: %r' % (e,), live=True)
+    if rec is None or 'unavailable' in rec:
+        try:
+            old = json.load(open(os.path.join(ROOT, 'profiles', 'r01_reference_numba_cuda.json'))).get(name)
+            if old:
+                rec = dict(atom_steps_per_s=old['atom_steps_per_s'], ns_per_day=old['ns_per_day_at_2fs'], seconds_per_step=old['seconds_per_step'],
+                           live=False, live_error=(rec or {}).get('unavailable'),
+                           source='profiles/r01_reference_numba_cuda.json (recorded in round 1 on one B200)')
+        except (OSError, ValueError):
+            pass
+    return rec
+
+
+def sub_record(name, args, peaks, identity, nobarrier):
+    """A single-GPU side record (water_23k, protein_92k) inside the N = 1 line: the same measurements as the
+    headline workload, so that the 92k-atom target config is in every driver-run line."""
+    w = Workload(name, args)
+    steps = max(args.steps, 200 if w.n > 50000 else 500)
+    w.step(max(args.warmup, 20))
+    ms, _, rebuilds = w.timed_reps(steps, REPS, identity, nobarrier)
+    med = float(np.median(ms))
+    ph = w.phase_profile(100)
+    n_pairs = w.pair_count()
+    roof, roof_pme = roofline_records(w, ph, n_pairs, ph['j_chunks'] * 1024.0, 1, peaks)
+    e2e = w.e2e(200, identity, nobarrier)
+    rec = dict(workload=name, atoms=w.n, value=w.n * steps / (med * 1e-3), unit='atom-steps/s', steps=steps, reps_ms=ms,
+               ms_per_step=med / steps, ns_per_day=ns_per_day(steps, med * 1e-3, w.dt), nlist_rebuilds_per_rep=rebuilds / REPS,
+               e2e=e2e, roofline=roof, roofline_pme=roof_pme,
+               phases_ms_per_step={k: ph[k] for k in ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms')},
+               slot_efficiency=n_pairs / max(1.0, ph['j_chunks'] * 1024.0))
+    if not args.no_numba:
+        ref = numba_cuda_reference(name)
+        if ref:
+            rec['reference_numba_cuda'] = ref
+            if 'ns_per_day' in ref:
+                rec['speedup_vs_reference_numba_cuda'] = dict(device_resident=rec['ns_per_day'] / ref['ns_per_day'],
+                                                              e2e=e2e['ns_per_day'] / ref['ns_per_day'])
+    w.dev.close()
+    return rec
+
+
 def run_b200(args, cfg):
     import mdpy_b200 as md  # noqa: F401
-    from mdpy_b200 import _native, multigpu
-    from mdpy_b200.integrator import LangevinIntegrator
-    from mdpy_b200.unit import KB, Quantity, default_energy_unit, kelvin
+    from mdpy_b200 import multigpu
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -207,23 +405,6 @@ def run_b200(args, cfg):
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     os.environ['MDPY_B200_DEVICE'] = str(local)
-
-    system = build_system(cfg)
-    n = system.num_particles
-    ens = system.ensemble(cutoff=cfg['cutoff'], switch=cfg['switch'], pme=True, ewald_error=1e-6, grid=cfg['grid'],
-                          order=4, bonded=True)
-    ctx = _native.context_of(ens)
-    dev = ctx.dev
-    kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
-    dt = cfg['dt']
-    skin = float(cfg.get('skin', 2.0))
-    if skin != 2.0:
-        dev.set_nlist(skin)
-    if args.no_graph:
-        dev.set_option('graph', 0)
-    for kv in filter(None, os.environ.get('MDK_OPTS', '').split(',')):   # experiments: MDK_OPTS=concurrent=0,graph=1
-        k, v = kv.split('=')
-        dev.set_option(k, float(v))
 
     def barrier():
         if dist is not None:
@@ -243,181 +424,113 @@ def run_b200(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # relax the lattice start (untimed; every rank runs it redundantly and deterministically, so all
-    # ranks hold bit-identical state): short, strongly damped steps, then the production step
-    for rdt, gamma, steps in ((0.1, 0.2, 200), (0.5, 0.05, 200), (1.0, 0.01, 300)):
-        LangevinIntegrator(rdt, TEMPERATURE, gamma, seed=1).integrate(ens, max(1, int(steps * args.relax)))
-    integ = LangevinIntegrator(dt, TEMPERATURE, GAMMA, seed=1)
-    integ.integrate(ens, 20)
-    terms = 0
-    for c in ens.constraints:
-        terms |= c.terms
-    terms &= int(os.environ.get('MDK_TERMS_MASK', '0xffff'), 0)   # experiments: drop force terms from the direct step calls
+    w = Workload(args.config, args)
+    n, dev, dt = w.n, w.dev, w.dt
+    prof_steps = 30 if n > 200000 else 100
+    ph1 = w.phase_profile(prof_steps)                      # single-GPU profile (every rank, before the job is sharded)
+    n_pairs = w.pair_count()
+    slots_single = ph1['j_chunks'] * 1024.0
 
-    # ---- per-phase profile (separate untimed pass; per-phase events add syncs) ----
-    prof_steps = 50 if n > 200000 else 200
-    dev.set_profiling(2)
-    dev.step_langevin(dt, kT, GAMMA, 1, prof_steps, terms)
-    ph = dev.timing()
-    dev.set_profiling(0)
-    pair_ms = ph['pair_ms'] / prof_steps
-    pme_ms = (ph['spread_ms'] + ph['fft_ms'] + ph['gather_ms']) / prof_steps
-    bonded_ms = ph['bonded_ms'] / prof_steps
-    lj = ens.constraints[0]
-    ens.state._positions = dev.download_positions()
-    ctx._pos_rev = None
-    lj._configure(); ctx.sync_positions()
-    n_pairs = dev.pair_count()               # in-cutoff pair count of the current configuration (flop model)
-    slots_single = dev.timing()['j_chunks'] * 1024.0
-
-    # ---- multi-GPU: join the communicator, deal i-blocks to ranks weighted by the extra roles ----
+    # ---- multi-GPU: join the communicator, shard the work ----
     weights = None
     if world > 1:
-        weights = multigpu.role_weights(world, pair_ms + ph['nlist_ms'] / prof_steps, pme_ms, 0.0)   # bonded terms are split evenly
+        pme_ms = ph1['spread_ms'] + ph1['fft_ms'] + ph1['gather_ms']
+        weights = multigpu.role_weights(world, ph1['pair_ms'] + ph1['nlist_ms'], pme_ms, 0.0)   # bonded terms are split evenly
         weights = multigpu.broadcast_array(dist, weights, rank)   # one set of shard ranges for all ranks
-        multigpu.attach(ctx, dist, rank, world, weights)
-    integ.integrate(ens, max(args.warmup, 3))
+        multigpu.attach(w.ctx, dist, rank, world, weights)
+    w.integ.integrate(w.ens, max(args.warmup, 3))
 
-    # ---- timed region: K steps, state resident on the device, CUDA events on the ctx stream ----
-    dev.set_profiling(1)
-    t_before = dev.timing()
-    barrier()
+    # ---- timed region.  The clock sampler runs from >= 1 s before the first timed repetition to after the last
+    # one, and the GPU does the same steps (untimed) during the pre-roll, so every clock sample is taken under
+    # the load that is being timed — however short K steps are.
     with ClockSampler(local) as clocks:
-        w0 = time.perf_counter()
-        dev.step_langevin(dt, kT, GAMMA, 1, args.steps, terms)
-        wall = time.perf_counter() - w0
-    barrier()
-    t_after = dev.timing()
-    dev_ms = max_over_ranks(t_after['total_ms'])
-    launches = int(sum_over_ranks(t_after['launches'] - t_before['launches']))
-    rebuilds = int(t_after['rebuilds'] - t_before['rebuilds'])
-    value = ns_per_day(args.steps, dev_ms * 1e-3, dt)
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < 1.2:
+            w.step(max(args.steps, 20))
+        ms, launches_rank, rebuilds = w.timed_reps(args.steps, REPS, max_over_ranks, barrier)
+        t_post = time.perf_counter()
+        while time.perf_counter() - t_post < 0.25:
+            w.step(max(args.steps, 20))
+    dev_ms = float(np.median(ms))
+    launches = int(sum_over_ranks(launches_rank) / REPS)
 
     if args.skip_extras:
         if rank == 0:
             print(json.dumps(dict(metric='atom_steps_per_s', value=n * args.steps / (dev_ms * 1e-3), unit='atom-steps/s',
-                                  ns_per_day=value, steps=args.steps, warmup=args.warmup,
-                                  n_gpus=world, ms_per_step=dev_ms / args.steps, gpu_launches=launches, rebuilds=rebuilds,
-                                  note='skip-extras (profiling run)')))
+                                  ns_per_day=ns_per_day(args.steps, dev_ms * 1e-3, dt), steps=args.steps, warmup=args.warmup,
+                                  n_gpus=world, ms_per_step=dev_ms / args.steps, reps_ms=ms, gpu_launches=launches,
+                                  rebuilds_per_rep=rebuilds / REPS, note='skip-extras (profiling run)')))
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # per-phase profile of the (possibly sharded) step, every rank in lockstep
-    dev.set_profiling(2)
-    dev.step_langevin(dt, kT, GAMMA, 1, prof_steps, terms)
-    ph_n = dev.timing()
-    dev.set_profiling(1)
+    ph_n = w.phase_profile(prof_steps)                     # per-phase profile of the (possibly sharded) step, ranks in lockstep
     # L2-flushed variant: one step at a time with a 256 MB memset in between (outside the events)
+    dev.set_profiling(1)
     fl = []
-    for _ in range(min(50, args.steps)):
+    for _ in range(min(30, max(args.steps, 10))):
         dev.flush_l2()
-        dev.step_langevin(dt, kT, GAMMA, 1, 1, terms)
+        w.step(1)
         fl.append(dev.timing()['total_ms'])
     dev.set_profiling(0)
-
-    # ---- e2e: the drop-in integrator call with host state, one call per step (all ranks in lockstep) ----
-    # Every call uploads ensemble.state (positions + velocities, float32, page-locked), runs one step and
-    # downloads the new state and the energies; between calls the state lives in host memory only as far
-    # as the API is concerned (the device continues its float64 trajectory when the host copy is unchanged).
-    e2e_steps = min(args.steps, 1000 if n < 200000 else 100)
-    ens.state._positions = dev.download_positions()      # the timed region above stepped the device directly
-    ens.state._velocities = dev.download_velocities()
-    ens.state.revision += 1
-    e2e_integ = LangevinIntegrator(dt, TEMPERATURE, GAMMA, seed=2)
-    for _ in range(5):   # warm-up of the host path (graph capture of the single-step variant, pinned buffers)
-        e2e_integ.integrate(ens, 1)
-    l_before = dev.timing()['launches']
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_integ.integrate(ens, 1)
-    e2e_sec = max_over_ranks(time.perf_counter() - t0)
-    e2e_launches = (dev.timing()['launches'] - l_before) / e2e_steps
-    e2e_value = n * e2e_steps / e2e_sec
-    e2e_energy = float(ens.potential_energy)
+    e2e = w.e2e(min(max(args.steps, 20), 500 if n < 200000 else 50), max_over_ranks, barrier)
 
     if rank != 0:
         dist.destroy_process_group()
         return
 
     peaks = measured_peaks()
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json'))).get(args.config)
-    except (OSError, ValueError):
-        pass
-    fp32_peak = 148 * 128 * 2 * peaks['sm_max_mhz'] * 1e6 / 1e12
-    pair_ms_n = ph_n['pair_ms'] / prof_steps
-    # this rank evaluates its share of the pair slots; at N=1 that is everything
-    share = (ph_n['j_chunks'] * 1024.0) / max(1.0, slots_single)
-    achieved = FLOP_PER_PAIR * n_pairs * share / (pair_ms_n * 1e-3) / 1e12
-    K = int(np.prod(cfg['grid']))
-    pme_bytes = 44.0 * n + 34.0 * K
-    pme_gbs = pme_bytes / (pme_ms * 1e-3) / 1e9
-
+    roof, roof_pme = roofline_records(w, ph_n, n_pairs, slots_single, world, peaks)
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----
     cpu = None
     if world == 1:
-        cpu_sec, sample = reference_step_seconds(system, cfg, 1, budget_s=10.0)
+        cpu_sec, sample = reference_step_seconds(w.system, cfg, 1, budget_s=10.0)
         cpu = dict(value=n / cpu_sec, unit='atom-steps/s', cores=1, kind='port', sample=sample,
                    host_cores=os.cpu_count(), seconds_per_step=cpu_sec, ns_per_day=ns_per_day(1, cpu_sec, dt))
 
     phase_keys = ('nlist_ms', 'pair_ms', 'spread_ms', 'fft_ms', 'gather_ms', 'bonded_ms', 'integrate_ms', 'comm_ms')
+    K = int(np.prod(cfg['grid']))
     line = dict(
         metric='atom_steps_per_s', value=n * args.steps / (dev_ms * 1e-3), unit='atom-steps/s', n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong',
-        vs_baseline=None, dtype='f32', data='synthetic', ns_per_day=value, wall_ms_per_step=wall * 1e3 / args.steps,
-        scaling_note='default workloads follow BASELINE.json: --gpus 1 = configs[1] (23 556-atom water box), --gpus > 1 = configs[3] '
-                     '(1 066 628-atom box, strong scaling of that box); atom-steps/s is the size-normalised metric that makes the '
-                     'two comparable (one GPU: 2.25e8 at 23k, 2.20e8 at 92k atoms)',
+        vs_baseline=None, dtype='f32', data='synthetic', ns_per_day=ns_per_day(args.steps, dev_ms * 1e-3, dt),
+        timing='median of %d repetitions of K = %d steps, each bracketed by a barrier and timed with CUDA events on the '
+               'context stream, max over ranks per repetition; reps_ms lists them all' % (REPS, args.steps),
+        reps_ms=ms,
+        scaling_note='the same workload (%s) at every GPU count: strong scaling of one box; single-GPU side records of '
+                     'BASELINE configs[1] (water_23k) and configs[2] (protein_92k, the >=10x target config) ride along at N = 1' % args.config,
         config=dict(workload=args.config, atoms=n, cutoff_A=cfg['cutoff'], switch_A=cfg['switch'], pme_grid=list(cfg['grid']),
-                    pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=skin,
-                    terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_in_timed=rebuilds,
+                    pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=w.skin,
+                    terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_per_rep=rebuilds / REPS,
                     parallelism='single GPU' if world == 1 else
                     'replicated positions, i-block sharded pair forces (weights %s), bonded terms split evenly, PME on last rank, int64 all-reduce per step'
                     % np.round(weights, 3).tolist(),
                     l2='steady-state MD trajectory: every step consumes the previous step\'s output, nothing is re-timed '
-                       'on a repeated input; working set %.1f MB; l2_flushed_ms_per_step gives the same step with a '
-                       '256 MB L2 flush before it' % ((32.0 * n + 12.0 * K) / 1e6)),
+                       'on a repeated input; working set %.1f MB (> L2 for this box: %s); l2_flushed_ms_per_step gives the same '
+                       'step with a 256 MB L2 flush before it' % ((190.0 * n + 20.0 * K) / 1e6, (190.0 * n + 20.0 * K) > 126e6)),
         l2_flushed_ms_per_step=float(np.median(fl)),
         clocks=clocks.summary(), gpu_launches=launches,
-        e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=24 * n, d2h_bytes_per_step=24 * n + 128,
-                 steps=e2e_steps, ms_per_step=e2e_sec * 1e3 / e2e_steps, ns_per_day=ns_per_day(e2e_steps, e2e_sec, dt),
-                 gpu_launches_per_step=e2e_launches, potential_energy_last_step=e2e_energy,
-                 path='LangevinIntegrator.integrate(ensemble, 1) per step: host State (float32 positions + velocities, '
-                      'page-locked) -> mdk_step_langevin_host -> host State + energies; wall clock, max over ranks'),
-        roofline=dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak,
-                      traffic=None if traffic is None or world > 1 else traffic['bytes'],
-                      traffic_source=None if traffic is None or world > 1 else traffic['source'] + ' (ncu dram bytes read + written per launch)',
-                      kernel='k_pair<LJ,COUL>', flop_per_pair=FLOP_PER_PAIR, pairs_in_cutoff=n_pairs, kernel_ms=pair_ms_n,
-                      peak_source='148 SM x 128 lanes x 2 flop x sm_max_mhz (%s)' % peaks['source'],
-                      note='rank 0 share of the pair work at N > 1' if world > 1 else 'whole pair kernel'),
-        roofline_pme=dict(bound='hbm', achieved=pme_gbs, peak=peaks['hbm_gbs'], unit='GB/s', frac=pme_gbs / peaks['hbm_gbs'],
-                          bytes_per_step=pme_bytes, kernels_ms=pme_ms, peak_source=peaks['source'],
-                          note='spread + convert + cuFFT R2C/C2R + convolve + gather (single-GPU pass); mesh is L2 resident'),
-        phases_ms_per_step={k: ph_n[k] / prof_steps for k in phase_keys},
-        phases_ms_per_step_single_gpu={k: ph[k] / prof_steps for k in phase_keys},
+        e2e=e2e, roofline=roof, roofline_pme=roof_pme,
+        phases_ms_per_step={k: ph_n[k] for k in phase_keys},
+        phases_ms_per_step_single_gpu={k: ph1[k] for k in phase_keys},
         nlist=dict(work_units=int(ph_n['work_units']), j_chunks=int(ph_n['j_chunks']), masked_chunks=int(ph_n['masked_chunks']),
                    seg_chunks=int(ph_n['seg_chunks']), pair_slots=int(slots_single),
                    slot_efficiency=n_pairs / max(1.0, slots_single)),
     )
     if cpu is not None:
         line['cpu_baseline'] = cpu
-    try:   # recorded, not live: the reference's own numba.cuda path on one B200 (baseline/ref_numba_cuda.py)
-        rec = json.load(open(os.path.join(ROOT, 'profiles', 'r01_reference_numba_cuda.json'))).get(args.config)
-        if rec:
-            line['reference_numba_cuda_recorded'] = dict(
-                atom_steps_per_s=rec['atom_steps_per_s'], ns_per_day=rec['ns_per_day_at_2fs'], seconds_per_step=rec['seconds_per_step'],
-                source='profiles/r01_reference_numba_cuda.json (unmodified reference, one B200, plain-cutoff LJ + bare Coulomb, no PME)')
-    except (OSError, ValueError):
-        pass
-    if args.config == 'water_23k':   # recorded, not live: the unmodified reference's CPU path on this very box (1 core, DOUBLE mode)
-        try:
+    if world == 1 and not args.no_sub:
+        dev.close()
+        identity, nobarrier = (lambda x: float(x)), (lambda: None)
+        line['sub_records'] = {}
+        for name in ('water_23k', 'protein_92k'):
+            if name != args.config:
+                line['sub_records'][name] = sub_record(name, args, peaks, identity, nobarrier)
+        try:   # recorded, not live: the unmodified reference's CPU path on the 23k box (1 core, DOUBLE mode)
             g = np.load(os.path.join(ROOT, 'tests', 'golden', 'config2_full_f64.npz'))
             sec = float(np.sum(g['ref_seconds']))
             line['reference_cpu_recorded'] = dict(
-                seconds_per_step=sec, atom_steps_per_s=n / sec, ns_per_day=ns_per_day(1, sec, dt),
+                workload='water_23k', seconds_per_step=sec, atom_steps_per_s=23556 / sec, ns_per_day=ns_per_day(1, sec, 2.0),
                 source='tests/golden/config2_full_f64.npz:ref_seconds (oracle/make_golden.py --only config2_full: one LJ + one '
                        'Coulomb evaluation of the unmodified reference, numba CPU kernels, 1 core of the build container)')
         except (OSError, KeyError, ValueError):
@@ -430,17 +543,17 @@ def run_b200(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=2000)
-    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default=None, choices=sorted(CONFIGS),
-                    help='default: water_23k (BASELINE configs[1]) at --gpus 1, protein_1m (configs[3]) at --gpus > 1')
+    ap.add_argument('--config', default='protein_1m', choices=sorted(CONFIGS),
+                    help='headline workload, the same at every GPU count (default: protein_1m, BASELINE configs[3])')
+    ap.add_argument('--no-sub', action='store_true', help='N = 1: skip the water_23k / protein_92k side records')
+    ap.add_argument('--no-numba', action='store_true', help='side records: skip the live run of the reference numba.cuda path')
     ap.add_argument('--relax', type=float, default=1.0, help='scale of the untimed lattice-relaxation phase')
     ap.add_argument('--skip-extras', action='store_true', help='only the timed region (for ncu runs)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host (no CUDA-graph steps)')
     args = ap.parse_args()
-    if args.config is None:
-        args.config = 'water_23k' if args.gpus <= 1 else 'protein_1m'
     cfg = CONFIGS[args.config]
     if args.impl == 'reference':
         run_reference(args, cfg)

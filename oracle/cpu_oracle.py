@@ -175,13 +175,14 @@ def coulomb_allpairs(positions, charges, pbc, bonded, k, i_range=None, threads=1
     return sum(p[0] for p in parts), sum(p[1] for p in parts)
 
 
-def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn):
+def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn, snapshot_steps=None):
     """VerletIntegrator.integrate (verlet_integrator.py:20-50) for a fresh integrator:
     x_prev = x - v dt + a dt^2 (:31-34, sic), x_new = 2x - x_prev + a dt^2 (:40-43), positions
     wrapped into State every step (:44 -> state.py:56-61), reported velocity
     minimg(x_cur - x_prev)/(2 dt) (:47-50, sic — half the true value).
     force_fn(wrapped_positions) -> forces [n,3].  float64 host arithmetic like the reference.
-    Returns (state_positions, state_velocities, cur_positions_unwrapped, pre_positions)."""
+    Returns (state_positions, state_velocities, cur_positions_unwrapped, pre_positions); with snapshot_steps
+    also a dict {step: cur_positions_unwrapped after that many steps}."""
     pbc = np.asarray(pbc, dtype=np.float64)
     pbc_inv = np.linalg.inv(pbc)
     masses = np.asarray(masses, dtype=np.float64).reshape(-1, 1)
@@ -189,6 +190,7 @@ def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn):
     acc = force_fn(state_pos) / masses
     cur = state_pos.copy()
     pre = cur - np.asarray(velocities, dtype=np.float64) * dt_fs + acc * dt_fs ** 2
+    snaps = {}
     for step in range(num_steps):
         if step != 0:
             acc = force_fn(state_pos) / masses
@@ -196,11 +198,34 @@ def verlet(positions, velocities, masses, pbc, dt_fs, num_steps, force_fn):
         state_pos, lost, _ = wrap_positions(cur, pbc, pbc_inv)
         if lost:
             raise RuntimeError('ParticleLossError')
+        if snapshot_steps is not None and (step + 1) in snapshot_steps:
+            snaps[step + 1] = cur.copy()
     d = cur - pre
     s = d @ pbc_inv
     s -= np.round(s)
     vel = (s @ pbc) / 2 / dt_fs
+    if snapshot_steps is not None:
+        return state_pos, vel, cur, pre, snaps
     return state_pos, vel, cur, pre
+
+
+def config1_force_fn(c1, threads=1):
+    """Force function of the example system without its dihedral term (the terms of
+    tests/golden/config1_verlet_f64.npz): LJ + bare all-pairs Coulomb from the C restatement, bonds / angles /
+    impropers from oracle/bonded.py.  c1 = the config1_f64 fixture."""
+    from . import bonded
+    k_e = 1.0 / (4 * np.pi * float(np.float32(0.5727653)))   # 1 / (4 pi EPSILON0), the reference's float32-rounded constant (Q7)
+    box = np.asarray(c1['box'], dtype=np.float64)
+
+    def force(pos):
+        t = nonbonded_bruteforce(pos, box, c1['lj_table'], c1['charges'], c1['bonded'], c1['scaling'],
+                                 rc_lj=float(c1['rc']), coul_mode=2, k_e=k_e, threads=threads)
+        f = t['f_lj'] + t['f_coul']
+        f += bonded.bonds(pos, box, c1['CharmmBondConstraint_idx'], c1['CharmmBondConstraint_par'])[0]
+        f += bonded.angles(pos, box, c1['CharmmAngleConstraint_idx'], c1['CharmmAngleConstraint_par'])[0]
+        f += bonded.impropers(pos, box, c1['CharmmImproperConstraint_idx'], c1['CharmmImproperConstraint_par'])[0]
+        return f
+    return force
 
 
 # ----------------------------------------------------------------------------

@@ -24,7 +24,7 @@ class BenchStubDevice:
         self.n = int(np.asarray(q).reshape(-1).size)
 
     def __getattr__(self, name):
-        if name.startswith('set_') or name in ('reset_integrator', 'flush_l2', 'upload_positions', 'upload_velocities'):
+        if name.startswith('set_') or name in ('reset_integrator', 'flush_l2', 'upload_positions', 'upload_velocities', 'close'):
             return lambda *a, **k: None
         raise AttributeError(name)
 
@@ -66,17 +66,22 @@ class BenchStubDevice:
         return self._energies()
 
 
-def test_bench_line_has_every_key_of_the_contract(monkeypatch, capsys):
+def _run_bench(monkeypatch, capsys, argv):
     import bench
     monkeypatch.setattr(_native, 'Device', BenchStubDevice)
     monkeypatch.setattr(bench, 'reference_step_seconds', lambda system, cfg, threads, budget_s=10.0: (5.0, 'stub sample'))
+    monkeypatch.setattr(bench.time, 'sleep', lambda s: None)
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MDK_OPTS', 'MDK_TERMS_MASK'):
         monkeypatch.delenv(k, raising=False)
-    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '20', '--warmup', '3', '--relax', '0.01'])
+    monkeypatch.setattr(sys, 'argv', ['bench.py'] + argv)
     bench.main()
-    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    return json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+
+def test_bench_line_has_every_key_of_the_contract(monkeypatch, capsys):
+    line = _run_bench(monkeypatch, capsys, ['--steps', '20', '--warmup', '3', '--relax', '0.01', '--config', 'water_23k', '--no-sub'])
     for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
-                'dtype', 'data', 'config', 'clocks', 'gpu_launches', 'e2e', 'roofline', 'cpu_baseline'):
+                'dtype', 'data', 'config', 'clocks', 'gpu_launches', 'e2e', 'roofline', 'cpu_baseline', 'reps_ms'):
         assert key in line, key
     assert line['metric'] == 'atom_steps_per_s' and line['unit'] == 'atom-steps/s' and line['n_gpus'] == 1
     assert line['config']['workload'] == 'water_23k' and line['config']['atoms'] == 23556 and line['vs_baseline'] is None
@@ -84,24 +89,32 @@ def test_bench_line_has_every_key_of_the_contract(monkeypatch, capsys):
     assert line['e2e']['h2d_bytes_per_step'] == 24 * 23556 and line['e2e']['unit'] == line['unit']
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
     assert line['roofline']['frac'] == pytest.approx(line['roofline']['achieved'] / line['roofline']['peak'])
-    assert line['roofline']['traffic'] == 5504000          # profiles/pair_kernel_traffic.json, water_23k
     assert set(line['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'} and line['cpu_baseline']['kind'] == 'port'
-    assert line['gpu_launches'] == 13 * 20
+    assert len(line['reps_ms']) == 5                       # five timed repetitions of exactly K steps, the median is the value
+    assert line['gpu_launches'] == 13 * 20                 # launches of ONE repetition of K steps
     assert line['value'] == pytest.approx(23556 * 20 / (0.1 * 20 * 1e-3))
-    assert 'reference_numba_cuda_recorded' in line
+    assert 'sub_records' not in line
+
+
+def test_side_records_of_the_23k_and_92k_boxes_ride_in_the_single_gpu_line(monkeypatch, capsys):
+    line = _run_bench(monkeypatch, capsys, ['--steps', '20', '--warmup', '3', '--relax', '0.01', '--config', 'water_23k', '--no-numba'])
+    sub = line['sub_records']
+    assert set(sub) == {'protein_92k'} and sub['protein_92k']['atoms'] == 92224
+    rec = sub['protein_92k']
+    for key in ('value', 'ms_per_step', 'ns_per_day', 'e2e', 'roofline', 'roofline_pme', 'phases_ms_per_step'):
+        assert key in rec, key
+    assert rec['roofline']['frac'] == pytest.approx(rec['roofline']['achieved'] / rec['roofline']['peak'])
     assert line['reference_cpu_recorded']['seconds_per_step'] == pytest.approx(419.5, rel=0.01)   # the reference itself, 1 core
 
 
-def test_default_workload_follows_the_gpu_count(monkeypatch):
+def test_the_workload_is_the_same_at_every_gpu_count(monkeypatch):
     import bench
     seen = {}
-    monkeypatch.setattr(bench, 'run_b200', lambda args, cfg: seen.update(config=args.config, grid=cfg['grid']))
-    monkeypatch.setattr(sys, 'argv', ['bench.py'])
-    bench.main()
-    assert seen['config'] == 'water_23k'
-    monkeypatch.setattr(sys, 'argv', ['bench.py', '--gpus', '8'])
-    bench.main()
-    assert seen['config'] == 'protein_1m' and tuple(seen['grid']) == (216, 216, 216)
+    monkeypatch.setattr(bench, 'run_b200', lambda args, cfg: seen.update(config=args.config, grid=cfg['grid'], steps=args.steps))
+    for argv in (['bench.py'], ['bench.py', '--gpus', '2'], ['bench.py', '--gpus', '8']):
+        monkeypatch.setattr(sys, 'argv', argv)
+        bench.main()
+        assert seen['config'] == 'protein_1m' and tuple(seen['grid']) == (216, 216, 216) and seen['steps'] == 200
     monkeypatch.setattr(sys, 'argv', ['bench.py', '--gpus', '2', '--config', 'protein_92k'])
     bench.main()
     assert seen['config'] == 'protein_92k'

@@ -309,3 +309,18 @@ def test_bonded_restatement_matches_reference_on_config1():
         assert e == pytest.approx(float(g[name + '_energy']), rel=1e-10), name
     e = bonded.dihedral_energy(x, box, g['CharmmDihedralConstraint_idx'], g['CharmmDihedralConstraint_par'])
     assert e == pytest.approx(float(g['CharmmDihedralConstraint_energy']), rel=1e-10)
+
+
+def test_oracle_reproduces_the_reference_config1_trajectory():
+    """100 steps of the reference's VerletIntegrator on the example system (tests/golden/config1_verlet_f64.npz)
+    against oracle.verlet + the restated force terms, from the golden's own float64 start: the checker the GPU
+    trajectory test uses is the reference's trajectory to 1e-8 A."""
+    g = load_golden('config1_verlet_f64')
+    c1 = load_golden('config1_f64')
+    steps = [int(v) for v in g['snapshot_steps']]
+    _, vel, _, _, snaps = ora.verlet(g['positions0'], np.zeros_like(g['positions0']), c1['masses'], np.diag(c1['box']),
+                                     float(g['dt']), steps[-1], ora.config1_force_fn(c1, threads=os.cpu_count() or 1),
+                                     snapshot_steps=steps)
+    for k, step in enumerate(steps):
+        assert np.abs(snaps[step] - g['snapshots'][k]).max() < 1e-8, step
+    assert np.abs(vel - g['final_velocities']).max() < 1e-8

@@ -432,12 +432,9 @@ def run_b200(args, cfg):
     slots_single = ph1['j_chunks'] * 1024.0
 
     # ---- multi-GPU: join the communicator, shard the work ----
-    weights = None
+    grid = (1, 1, 1)
     if world > 1:
-        pme_ms = ph1['spread_ms'] + ph1['fft_ms'] + ph1['gather_ms']
-        weights = multigpu.role_weights(world, ph1['pair_ms'] + ph1['nlist_ms'], pme_ms, 0.0)   # bonded terms are split evenly
-        weights = multigpu.broadcast_array(dist, weights, rank)   # one set of shard ranges for all ranks
-        multigpu.attach(w.ctx, dist, rank, world, weights)
+        grid = multigpu.attach(w.ctx, dist, rank, world)   # one spatial domain per rank, halo exchange per step
     w.integ.integrate(w.ens, max(args.warmup, 3))
 
     # ---- timed region.  The clock sampler runs from >= 1 s before the first timed repetition to after the last
@@ -503,8 +500,10 @@ def run_b200(args, cfg):
                     pme_order=4, ewald_error=1e-6, dt_fs=dt, integrator='langevin_gjf_300K_1ps', skin_A=w.skin,
                     terms='lj+erfc_direct+pme_recip+bond+angle+dihedral+improper', nlist_rebuilds_per_rep=rebuilds / REPS,
                     parallelism='single GPU' if world == 1 else
-                    'replicated positions, i-block sharded pair forces (weights %s), bonded terms split evenly, PME on last rank, int64 all-reduce per step'
-                    % np.round(weights, 3).tolist(),
+                    'spatial domain decomposition %d x %d x %d, one domain per rank: halo positions out / halo forces back by grouped '
+                    'ncclSend / ncclRecv every step, owner-only integration, PME sub-meshes to / from the mesh rank, state all-gather at '
+                    'list rebuilds' % grid,
+                    domain_decomposition=None if world == 1 else dict(grid=list(grid), **dev.dd_stats()),
                     l2='steady-state MD trajectory: every step consumes the previous step\'s output, nothing is re-timed '
                        'on a repeated input; working set %.1f MB (> L2 for this box: %s); l2_flushed_ms_per_step gives the same '
                        'step with a 256 MB L2 flush before it' % ((190.0 * n + 20.0 * K) / 1e6, (190.0 * n + 20.0 * K) > 126e6)),

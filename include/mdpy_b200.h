@@ -195,20 +195,33 @@ MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64
  * (default 0: hoisted out of the pair loop when the box allows it), 3 = energy sums in every graph
  * step, 4 = NCCL inside the captured step (N > 1; default 0), 5 = persistent pair-kernel blocks per SM
  * (default 4), 6 = cuFFT also for small power-of-two meshes (default 0: fused mesh kernels),
- * 7 = N > 1: device-driven list upkeep graph with host-launched step kernels (default 0). */
+ * 7 = unused. */
 MDK_API int mdk_set_option(mdk_ctx *ctx, int key, double value);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);
-/* Restrict the i-blocks whose work units this ctx builds and evaluates to those with
- * (block % modulus) in [lo, hi) (replicated-data force decomposition; weights = range widths). */
-MDK_API int mdk_set_shard(mdk_ctx *ctx, int lo, int hi, int modulus);
 /* Multi-GPU: one process per GPU.  mdk_comm_unique_id wraps ncclGetUniqueId (rank 0 calls it and
  * ships the 128 bytes to the other ranks by any means, e.g. torch.distributed.broadcast);
- * mdk_comm_init joins the communicator.  Afterwards every force evaluation ends with one
- * ncclAllReduce(sum) of the int64 force accumulator; bonded / excluded-pair terms are dealt to the
- * ranks in contiguous ranges, the PME mesh runs on the last rank. */
+ * mdk_comm_init joins the communicator. */
 MDK_API int mdk_comm_unique_id(void *out128);
 MDK_API int mdk_comm_init(mdk_ctx *ctx, int rank, int nranks, const void *unique_id128);
+/* Spatial domain decomposition with halo exchange (mdk_dd.cu; the reference has one State on one device,
+ * core/state.py:18-28).  The box is cut into px x py x pz domains, rank r = (rz * py + ry) * px + rx owns one:
+ * it lists and evaluates the pair work of its own i-blocks, owns the bonded / excluded-pair terms of its atoms,
+ * spreads / gathers them on the PME mesh and integrates only them.  Afterwards mdk_compute, mdk_step_langevin
+ * and mdk_step_langevin_host of this ctx are collective calls (every rank makes the same call with the same
+ * state); per step: grouped ncclSend / ncclRecv of halo positions and of halo forces, PME sub-meshes to and from
+ * the mesh rank (the last one), an all-gather of the state at every list rebuild and at the end of a call.
+ * local_group < 0: NCCL backend (mdk_comm_init first).  local_group >= 0: the ranks are contexts of THIS process on
+ * ONE device (tests on a single-GPU box): transfers are device-to-device copies and the group is driven through
+ * the *_group calls below. */
+MDK_API int mdk_dd_init(mdk_ctx *ctx, int rank, int nranks, int px, int py, int pz, int local_group);
+/* Local groups: ctxs = every context of the group in rank order; same semantics as mdk_compute / mdk_step_langevin. */
+MDK_API int mdk_dd_compute_group(mdk_ctx *const *ctxs, int n, unsigned terms, double *energies);
+MDK_API int mdk_dd_step_langevin_group(mdk_ctx *const *ctxs, int n, double dt, double kT, double gamma, uint64_t seed,
+                               int nsteps, unsigned terms, double *energies);
+/* out8: own tile slots [lo, hi), halo atoms received per step, own atoms sent per step, exchanges so far, list
+ * rebuilds, PME sub-mesh points of this rank, ranks. */
+MDK_API int mdk_dd_stats(mdk_ctx *ctx, int64_t *out8);
 
 #ifdef __cplusplus
 }

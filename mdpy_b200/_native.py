@@ -40,7 +40,8 @@ EXPORTS = [
     'mdk_download_positions_f64', 'mdk_download_velocities', 'mdk_build_nlist', 'mdk_compute',
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
-    'mdk_set_shard', 'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
+    'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -90,7 +91,10 @@ def load_library():
         'mdk_get_timing': (i32, [vp, vp]),
         'mdk_set_profiling': (i32, [vp, i32]),
         'mdk_force_accumulator': (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
-        'mdk_set_shard': (i32, [vp, i32, i32, i32]),
+        'mdk_dd_init': (i32, [vp, i32, i32, i32, i32, i32, i32]),
+        'mdk_dd_compute_group': (i32, [vp, i32, C.c_uint, vp]),
+        'mdk_dd_step_langevin_group': (i32, [vp, i32, f64, f64, f64, u64, i32, C.c_uint, vp]),
+        'mdk_dd_stats': (i32, [vp, vp]),
         'mdk_comm_unique_id': (i32, [vp]),
         'mdk_comm_init': (i32, [vp, i32, i32, vp]),
         'mdk_flush_l2': (i32, [vp]),
@@ -186,8 +190,16 @@ class Device:
     def set_stream(self, cuda_stream):
         self._ck(self._lib.mdk_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
-    def set_shard(self, lo, hi, modulus):
-        self._ck(self._lib.mdk_set_shard(self._h, int(lo), int(hi), int(modulus)))
+    def dd_init(self, rank, nranks, grid, local_group=-1):
+        """Spatial domain decomposition (mdk_dd_init): this context becomes rank `rank` of `nranks`, owning one
+        domain of the px x py x pz grid.  local_group >= 0: in-process group on one device (tests)."""
+        self._ck(self._lib.mdk_dd_init(self._h, int(rank), int(nranks), int(grid[0]), int(grid[1]), int(grid[2]), int(local_group)))
+
+    def dd_stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        self._ck(self._lib.mdk_dd_stats(self._h, _ptr(out)))
+        keys = ['own_lo', 'own_hi', 'halo_atoms_in', 'halo_atoms_out', 'exchanges', 'rebuilds', 'pme_box_points', 'ranks']
+        return dict(zip(keys, (int(v) for v in out)))
 
     def comm_unique_id(self):
         buf = (C.c_char * 128)()
@@ -329,7 +341,7 @@ class Device:
     def set_option(self, key, value):
         """Execution options of mdk_set_option (include/mdpy_b200.h): 'graph', 'concurrent',
         'canonical_min_image', 'graph_energy', 'graph_nccl', 'pair_blocks_per_sm', 'pme_cufft', 'graph_hosted'."""
-        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6, 'graph_hosted': 7}[key]
+        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6}[key]
         self._ck(self._lib.mdk_set_option(self._h, k, float(value)))
 
     def flush_l2(self):
@@ -444,6 +456,55 @@ class EnsembleContext:
             c._defer_forces(stamp)
             total += c._potential_energy
         return forces, total
+
+
+class LocalGroup:
+    """Several device contexts of THIS process on ONE GPU acting as the ranks of a domain-decomposed job
+    (mdk_dd_init with a local group id): the same decomposition code as a multi-process NCCL run, with the
+    transfers done by device-to-device copies.  For tests on a single-GPU box."""
+    _next_id = 0
+
+    def __init__(self, ensembles, grid):
+        self.ensembles = list(ensembles)
+        self.ctxs = [context_of(e) for e in self.ensembles]
+        n = len(self.ctxs)
+        if int(np.prod(grid)) != n:
+            raise ValueError('domain grid %s does not match %d ensembles' % (list(grid), n))
+        self.group_id = LocalGroup._next_id
+        LocalGroup._next_id += 1
+        for r, ctx in enumerate(self.ctxs):
+            ctx.dev.dd_init(r, n, grid, local_group=self.group_id)
+            ctx._pos_rev = None
+        self._lib = self.ctxs[0].dev._lib
+        self._handles = (C.c_void_p * n)(*[ctx.dev._h for ctx in self.ctxs])
+
+    def _terms(self):
+        terms = 0
+        for ens in self.ensembles:
+            terms = 0
+            for c in ens.constraints:
+                c._configure()
+                terms |= c.terms
+        return terms
+
+    def compute(self):
+        """One force evaluation of the job; returns (energies, [forces of rank 0, forces of rank 1, ...]) —
+        every rank ends up with all forces."""
+        terms = self._terms()
+        for ctx in self.ctxs:
+            ctx.sync_positions()
+        e = np.zeros(NUM_ENERGIES, dtype=np.float64)
+        self.ctxs[0].dev._ck(self._lib.mdk_dd_compute_group(self._handles, len(self.ctxs), terms, _ptr(e)))
+        return e, [ctx.dev.forces(np.float64) for ctx in self.ctxs]
+
+    def step_langevin(self, dt, kT, gamma, seed, nsteps):
+        terms = self._terms()
+        for ctx in self.ctxs:
+            ctx.sync_positions()
+        e = np.zeros(NUM_ENERGIES, dtype=np.float64)
+        self.ctxs[0].dev._ck(self._lib.mdk_dd_step_langevin_group(self._handles, len(self.ctxs), float(dt), float(kT), float(gamma),
+                                                                   int(seed), int(nsteps), terms, _ptr(e)))
+        return e
 
 
 def context_of(ensemble):

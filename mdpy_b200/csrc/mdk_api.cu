@@ -108,6 +108,15 @@ __global__ void k_export_state(int n, const double *__restrict__ x_cur, const do
     }
 }
 
+// self + neutralising-background energy of the Ewald sum (host constant, added to the energies read back)
+void prepare_pme_constants(mdk_ctx *c) {
+    if (c->have_coul && c->alpha > 0 && c->host_tmp.size() >= 2) {
+        double V = c->box.Ld[0] * c->box.Ld[1] * c->box.Ld[2];
+        c->e_self_bg = -c->k_e * c->alpha / sqrt(M_PI) * c->host_tmp[1] -
+                       c->k_e * M_PI * c->host_tmp[0] * c->host_tmp[0] / (2.0 * V * c->alpha * c->alpha);
+    }
+}
+
 }  // namespace mdk
 
 using namespace mdk;
@@ -219,8 +228,10 @@ void mdk_destroy(mdk_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    dd_destroy(c);
     comm_destroy(c);
     graph_destroy(c);
+    c->dd_blk.release(); c->dd_mark.release();
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
     c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release();
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
@@ -471,14 +482,6 @@ int mdk_download_velocities(mdk_ctx *c, float *out) {
 }
 
 // ---- hot path ----
-static void prepare_pme_constants(mdk_ctx *c) {
-    if (c->have_coul && c->alpha > 0 && c->host_tmp.size() >= 2) {
-        double V = c->box.Ld[0] * c->box.Ld[1] * c->box.Ld[2];
-        c->e_self_bg = -c->k_e * c->alpha / sqrt(M_PI) * c->host_tmp[1] -
-                       c->k_e * M_PI * c->host_tmp[0] * c->host_tmp[0] / (2.0 * V * c->alpha * c->alpha);
-    }
-}
-
 int mdk_build_nlist(mdk_ctx *c, int64_t *stats) {
     NEED_CTX(c);
     cudaSetDevice(c->device);
@@ -635,7 +638,7 @@ int mdk_step_langevin_host(mdk_ctx *c, const float *x_in, const float *v_in, flo
     const int *h_flags = reinterpret_cast<const int *>(c->pin_words + 24);
     const uint64_t step0 = c->langevin_step;
     bool ahead = (x_in || v_in) && nsteps > 0 && c->have_pos && c->langevin_cached && c->nlist_valid && c->use_graph &&
-                 c->profiling < 2 && (c->nranks == 1 || c->graph_nccl || c->graph_hosted);
+                 c->profiling < 2 && !c->dd;
     float *px = nullptr, *pv = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         if ((x_in || v_in) && pass == 0) MDK_TRY(host_state_in(c, x_in, v_in, m));

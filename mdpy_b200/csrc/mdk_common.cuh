@@ -44,6 +44,19 @@ struct Box {
     double Ld[3];
 };
 
+// ---------------------------------------------------------------------------
+// Spatial domain decomposition (mdk_dd.cu).  The cell grid is cut by planes into pdim[0] x pdim[1] x pdim[2]
+// domains; cells are numbered domain by domain (x fastest inside a domain), so after the cell sort every
+// domain's atoms — and with them every rank's i-blocks — are one contiguous range of the tile order.  One
+// domain (pdim = 1,1,1) reproduces the plain x-fastest numbering.
+constexpr int DD_MAXP = 4;                 // domains per axis
+constexpr int DD_MAXR = DD_MAXP * DD_MAXP * DD_MAXP;
+struct DDGeom {
+    int pdim[3];
+    int cut[3][DD_MAXP + 1];               // domain d along axis a covers cells [cut[a][d], cut[a][d+1])
+    int dom_base[DD_MAXR + 1];             // first cell key of each domain, [ndom] = number of cells
+};
+
 // kernel-side view of the tile list
 struct NlistView {
     const int4 *units;      // {i-block, first chunk, n chunks, unused}
@@ -53,6 +66,8 @@ struct NlistView {
     const unsigned *mask_excl;  // [slot][32] rotated exclusion bits per i-lane
     const unsigned *mask_14;    // [slot][32] rotated 1-4 bits per i-lane
 };
+
+struct DDState;
 
 struct BondedSet {
     int n = 0;
@@ -136,9 +151,13 @@ struct mdk_ctx {
     bool shift_ok = false;                    // box large enough to hoist the minimum image out of the pair loop
     int seg_chunks = 8;
     int64_t stat_units = 0, stat_chunks = 0, stat_masks = 0;
-    int shard_lo = 0, shard_hi = 1, shard_mod = 1;   // this rank owns i-blocks b with (b % mod) in [lo, hi)
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    mdk::DDState *dd = nullptr;               // spatial domain decomposition (mdk_dd.cu); null = single domain
+    mdk::DDGeom dd_geom{};                    // cell numbering (one domain unless dd is set)
+    mdk::DevBuf<int> dd_blk;                  // [ndom + 1] first i-block of each domain (device; written by every rebuild)
+    mdk::DevBuf<int> dd_mark;                 // [n_pad] 1 = tile slot referenced by this rank's work but owned by another
+    int own_lo = 0, own_hi = -1;              // tile slots this rank owns (integrates, spreads, owns the terms of); -1 = all
 
     // ---- PME ----
     int pme_n[3] = {0, 0, 0};
@@ -243,6 +262,11 @@ int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int6
 int coulomb_bare(mdk_ctx *c);
 int pme_prepare(mdk_ctx *c);
 int pme_compute(mdk_ctx *c);
+int pme_spread(mdk_ctx *c);                     // own atoms -> fixed-point mesh
+int pme_mesh(mdk_ctx *c, bool convert);         // (fixed point -> float,) FFT, influence function + energy, inverse FFT
+int pme_gather(mdk_ctx *c);                     // potential mesh -> forces on own atoms
+inline int own_first(const mdk_ctx *c) { return c->own_hi < 0 ? 0 : c->own_lo; }
+inline int own_end(const mdk_ctx *c) { return c->own_hi < 0 ? c->n : (c->own_hi < c->n ? c->own_hi : c->n); }
 int bonded_compute(mdk_ctx *c, unsigned terms);
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
@@ -254,9 +278,16 @@ int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry);
 void graph_destroy(mdk_ctx *c);
 int graph_finish(mdk_ctx *c);                        // counters / sticky errors of a queued graph run, after a sync
 int check_lost_flag(mdk_ctx *c);                     // flags[0] in the last read-back block -> MDK_ERR_PARTICLE_LOST
-int comm_allreduce_forces(mdk_ctx *c);
+struct Xfer { int peer; size_t soff, sbytes, roff, rbytes; };
+int comm_exchange(mdk_ctx *c, const void *sbuf, void *rbuf, const Xfer *x, int nx);   // grouped ncclSend / ncclRecv
+int comm_allgather_i32(mdk_ctx *c, const int *mine, int *all, int count);
 int comm_allreduce_energies(mdk_ctx *c);
 void comm_destroy(mdk_ctx *c);
+int dd_compute_single(mdk_ctx *c, unsigned terms, bool sync_energies);
+int dd_langevin_single(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms, bool defer_energies);
+void dd_destroy(mdk_ctx *c);
+int langevin_launch(mdk_ctx *c, int first, int end, int mode, double dt, double ca, double cb, double tg, uint64_t seed, uint64_t step);
+void prepare_pme_constants(mdk_ctx *c);
 
 // ---------------------------------------------------------------------------
 // device helpers

@@ -29,8 +29,33 @@ struct GridParams {
     float inv_cw[3];
     float R, R2;
     float skin_half2;
-    int shard_lo, shard_hi, shard_mod;
+    float wide_lim[3];    // a block whose bounding-box half extent exceeds this on an axis is "wide": canonical minimum image
+    DDGeom dd;            // cell numbering: domain by domain
+    int dd_rank, dd_nranks;   // nranks > 1: this rank builds the lists of its own domain's i-blocks only
 };
+
+// domain index and first / one-past-last cell of the domain that holds cell c along one axis
+__host__ __device__ __forceinline__ int dd_axis_domain(const DDGeom &d, int a, int c, int &lo, int &hi) {
+    int k = 0;
+    while (k + 1 < d.pdim[a] && c >= d.cut[a][k + 1]) ++k;
+    lo = d.cut[a][k]; hi = d.cut[a][k + 1];
+    return k;
+}
+// key of cell (cx, cy, cz): cells of one domain are contiguous, x fastest.  Along an axis that is cut, the walk
+// is a serpentine (x runs backwards on every other row, y on every other plane), so that consecutive cells — and
+// with them the 32 consecutive sorted atoms of an i-block — stay spatial neighbours at a row / plane end; along an
+// uncut axis the periodic wrap already makes the row end and the next row's start neighbours.
+__host__ __device__ __forceinline__ int dd_cell_key(const DDGeom &d, int cx, int cy, int cz) {
+    int lx, hx, ly, hy, lz, hz;
+    const int dx = dd_axis_domain(d, 0, cx, lx, hx), dy = dd_axis_domain(d, 1, cy, ly, hy), dz = dd_axis_domain(d, 2, cz, lz, hz);
+    const int dom = (dz * d.pdim[1] + dy) * d.pdim[0] + dx;
+    const int nx = hx - lx, ny = hy - ly, pz = cz - lz;
+    int py = cy - ly, px = cx - lx;
+    if (d.pdim[1] > 1 && (pz & 1)) py = ny - 1 - py;
+    const int row = pz * ny + py;
+    if (d.pdim[0] > 1 && (row & 1)) px = nx - 1 - px;
+    return d.dom_base[dom] + row * nx + px;
+}
 
 // ---------------------------------------------------------------------------
 __global__ void k_cell_keys(int n, const double *__restrict__ x_cur, GridParams g,
@@ -46,7 +71,7 @@ __global__ void k_cell_keys(int n, const double *__restrict__ x_cur, GridParams 
         int ci = (int)floorf((w + 0.5f * g.L[d]) * g.inv_cw[d]);
         cidx[d] = min(max(ci, 0), g.ncell[d] - 1);
     }
-    keys[a] = (unsigned)((cidx[2] * g.ncell[1] + cidx[1]) * g.ncell[0] + cidx[0]);
+    keys[a] = (unsigned)dd_cell_key(g.dd, cidx[0], cidx[1], cidx[2]);
     idx[a] = a;
 }
 
@@ -61,6 +86,14 @@ __global__ void k_cell_start(int n, int ncells, const unsigned *__restrict__ key
         if (keys_sorted[mid] < (unsigned)c) lo = mid + 1; else hi = mid;
     }
     cell_start[c] = lo;
+}
+
+// first i-block of every domain: a block that straddles a domain boundary belongs to the domain of its first atom
+__global__ void k_dd_bounds(DDGeom d, int n_blocks, const int *__restrict__ cell_start, int *__restrict__ blk) {
+    const int ndom = d.pdim[0] * d.pdim[1] * d.pdim[2];
+    const int r = threadIdx.x;
+    if (r > ndom) return;
+    blk[r] = r == 0 ? 0 : (r == ndom ? n_blocks : min(n_blocks, (cell_start[d.dom_base[r]] + TILE - 1) / TILE));
 }
 
 // tile-order gather of positions / charges / LJ parameters; also resets the displacement
@@ -168,10 +201,13 @@ struct BuildOut {
     int *flags;     // [2]=overflow
     int cap_units, cap_chunks, cap_masks;
     int seg;
+    int *mark;              // domain decomposition: listed j-atoms of other domains (halo), or null
+    int own_lo, own_hi;     // own tile slots
 };
 
 struct BlockEmitter {
     int b, lane, n;
+    int wide;
     bool i_valid, ragged;
     int seg_base, seg_fill;
     const int *excl_s, *p14_s;
@@ -187,7 +223,7 @@ struct BlockEmitter {
         if (seg_fill > 0) {
             int u = alloc(&o.counters[0], 1);
             if (u < o.cap_units) {
-                if (lane == 0) { o.units[u] = make_int4(b, seg_base, seg_fill, 0); atomicAdd(&o.counters[4], seg_fill); }
+                if (lane == 0) { o.units[u] = make_int4(b, seg_base, seg_fill, wide); atomicAdd(&o.counters[4], seg_fill); }
             } else if (lane == 0) o.flags[2] = 1;
         }
         seg_fill = 0;
@@ -240,6 +276,7 @@ struct BlockEmitter {
         if (ok) {
             o.chunk_j[(size_t)chunk * 32 + lane] = j < 0 ? 0 : j;
             if (lane == 0) o.chunk_mask[chunk] = slot;
+            if (o.mark && j >= 0 && (j < o.own_lo || j >= o.own_hi)) o.mark[j] = 1;
         }
     }
 };
@@ -250,7 +287,7 @@ constexpr int BUILD_WARPS = 4;
 
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
 k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const float4 *__restrict__ bbc,
-              const float4 *__restrict__ bbh, const int *__restrict__ cell_start,
+              const float4 *__restrict__ bbh, const int *__restrict__ cell_start, const int *__restrict__ dd_blk,
               const int *__restrict__ excl_s, int wb, const int *__restrict__ p14_s, int ws,
               BuildOut o) {
     __shared__ int stage_all[BUILD_WARPS][64];
@@ -258,17 +295,26 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int *stage = stage_all[wid];
     int warp_global = blockIdx.x * BUILD_WARPS + wid, n_warps = gridDim.x * BUILD_WARPS;
+    // domain decomposition: this rank lists the i-blocks of its own domain only.  Pairs inside the domain are
+    // taken half shell by tile index as on one GPU; a pair of blocks that straddles two domains is taken by the
+    // lower block when the sum of the two block indices is even, by the higher one when it is odd — both ranks
+    // evaluate the same rule on the same global order, exactly one of them lists the pair, and the cross-domain
+    // work is shared evenly whichever side of a boundary a block sits on.
+    const bool multi = g.dd_nranks > 1;
+    const int blk_lo = multi ? dd_blk[g.dd_rank] : 0, blk_hi = multi ? dd_blk[g.dd_rank + 1] : g.n_blocks;
+    if (multi) { o.own_lo = blk_lo * TILE; o.own_hi = blk_hi * TILE; } else { o.mark = nullptr; }
     // work item = (i-block, part): the candidate rows of a block are dealt round-robin to n_parts warps,
     // each emitting its own work units, so small systems still fill the machine during a rebuild
-    for (int w = warp_global; w < g.n_blocks * n_parts; w += n_warps) {
-        const int b = w / n_parts, part = w - b * n_parts;
-        if (g.shard_mod > 1) {  // multi-GPU: another rank owns this i-block
-            int r = b % g.shard_mod;
-            if (r < g.shard_lo || r >= g.shard_hi) continue;
-        }
+    for (int w = warp_global; w < (blk_hi - blk_lo) * n_parts; w += n_warps) {
+        const int b = blk_lo + w / n_parts, part = w % n_parts;
         float4 c = bbc[b], h = bbh[b];
         BlockEmitter em;
         em.b = b; em.lane = lane; em.n = g.n;
+        // hoisted minimum image (k_pair<..., SHIFT>): every listed j must have a unique image within L/2 of the
+        // block centre.  An interacting j is within R of some i-atom, which is within h of the centre, so
+        // R + h <= L/2 on every axis is enough (pairs farther apart than R may then see a non-minimal image, but
+        // both distances exceed the cutoff).  Blocks that break the bound are flagged and evaluated canonically.
+        em.wide = (h.x > g.wide_lim[0] || h.y > g.wide_lim[1] || h.z > g.wide_lim[2]) ? 1 : 0;
         em.i_valid = (b * TILE + lane) < g.n;
         em.ragged = (b == g.n_blocks - 1) && (g.n & 31);
         em.excl_s = excl_s; em.p14_s = p14_s; em.wb = wb; em.ws = ws; em.o = o;
@@ -301,21 +347,30 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
             for (int iy = 0; iy < len[1]; ++iy) {
                 if ((iz * len[1] + iy) % n_parts != part) continue;
                 int yy = lo[1] + iy; if (yy >= g.ncell[1]) yy -= g.ncell[1];
-                int row = (zz * g.ncell[1] + yy) * g.ncell[0];
-                // one or two contiguous x segments
-                int x0 = lo[0], cnt0 = min(len[0], g.ncell[0] - lo[0]);
-                int cnt1 = len[0] - cnt0;
+                // the x range in pieces that neither wrap around the box nor cross a domain cut: inside a piece
+                // the cells are consecutive keys, i.e. one contiguous run of the tile order
+                int xg = lo[0], rem = len[0];
 #pragma unroll 1
-                for (int sgm = 0; sgm < 2; ++sgm) {
-                    int xa = sgm == 0 ? x0 : 0, cn = sgm == 0 ? cnt0 : cnt1;
-                    if (cn <= 0) continue;
-                    int s = cell_start[row + xa], e = cell_start[row + xa + cn];
-                    s = max(s, first_j);
+                while (rem > 0) {
+                    int dlo, dhi;
+                    dd_axis_domain(g.dd, 0, xg, dlo, dhi);
+                    const int cn = min(rem, dhi - xg);
+                    const int key0 = min(dd_cell_key(g.dd, xg, yy, zz), dd_cell_key(g.dd, xg + cn - 1, yy, zz));   // a row may run backwards
+                    int s = cell_start[key0], e = cell_start[key0 + cn];
+                    xg += cn; if (xg >= g.ncell[0]) xg = 0;
+                    rem -= cn;
+                    if (!multi) s = max(s, first_j);
                     for (int base = s; base < e; base += 32) {
                         int j = base + lane;
                         bool pass = false, unsure = false;
                         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < e) {
+                        bool cand = j < e;
+                        if (multi && cand) {
+                            const int bj = j >> 5;
+                            if (bj >= blk_lo && bj < blk_hi) cand = bj > b;
+                            else cand = ((b + bj) & 1) ? (bj < b) : (bj > b);
+                        }
+                        if (cand) {
                             p = xs[j];
                             float dx = fmaxf(fabsf(min_image(p.x - cc[0], g.L[0], g.invL[0])) - hh[0], 0.f);
                             float dy = fmaxf(fabsf(min_image(p.y - cc[1], g.L[1], g.invL[1])) - hh[1], 0.f);
@@ -383,8 +438,10 @@ static GridParams make_grid_params(mdk_ctx *c) {
     float rc = fmaxf(c->have_lj ? c->rc_lj : 0.f, c->have_coul ? c->rc_coul : 0.f);
     g.R = rc + c->skin;
     g.R2 = g.R * g.R;
+    for (int a = 0; a < 3; ++a) g.wide_lim[a] = 0.5f * c->box.L[a] - g.R - 0.05f;
     g.skin_half2 = 0.25f * c->skin * c->skin;
-    g.shard_lo = c->shard_lo; g.shard_hi = c->shard_hi; g.shard_mod = c->shard_mod;
+    g.dd = c->dd_geom;
+    g.dd_rank = c->dd ? c->rank : 0; g.dd_nranks = c->dd ? c->nranks : 1;
     return g;
 }
 
@@ -447,6 +504,28 @@ static int nlist_plan(mdk_ctx *c) {
         ncells *= nc;
     }
     c->n_cells = ncells;
+    // cell numbering: one domain, or the domain grid of mdk_dd_init (cuts at equal cell counts per axis)
+    {
+        DDGeom &d = c->dd_geom;
+        const DDGeom before = d;
+        for (int a = 0; a < 3; ++a) {
+            int p = c->dd ? d.pdim[a] : 1;
+            if (p < 1) p = 1;
+            if (p > c->ncell[a]) return fail(c, MDK_ERR_BAD_ARG, "domain grid %d along axis %d exceeds the %d cells of the box", p, a, c->ncell[a]);
+            d.pdim[a] = p;
+            for (int k = 0; k <= p; ++k) d.cut[a][k] = (int)((long long)k * c->ncell[a] / p);
+            for (int k = p + 1; k <= DD_MAXP; ++k) d.cut[a][k] = c->ncell[a];
+        }
+        int base = 0, dom = 0;
+        for (int dz = 0; dz < d.pdim[2]; ++dz)
+            for (int dy = 0; dy < d.pdim[1]; ++dy)
+                for (int dx = 0; dx < d.pdim[0]; ++dx) {
+                    d.dom_base[dom++] = base;
+                    base += (d.cut[0][dx + 1] - d.cut[0][dx]) * (d.cut[1][dy + 1] - d.cut[1][dy]) * (d.cut[2][dz + 1] - d.cut[2][dz]);
+                }
+        for (; dom <= DD_MAXR; ++dom) d.dom_base[dom] = base;
+        if (memcmp(&before, &d, sizeof(d)) != 0) ++c->graph_epoch;   // kernel arguments of captured rebuilds
+    }
     c->n_parts = (int)((4096 + c->n_blocks - 1) / c->n_blocks);
     if (c->n_parts < 1) c->n_parts = 1;
     if (c->n_parts > 8) c->n_parts = 8;
@@ -472,6 +551,8 @@ static int nlist_plan(mdk_ctx *c) {
     MDK_CUDA(c, c->xs.reserve(c->n_pad)); MDK_CUDA(c, c->xs_ref.reserve(c->n_pad));
     MDK_CUDA(c, c->ljs.reserve(c->n_pad)); MDK_CUDA(c, c->f_acc.reserve((size_t)c->n_pad * 3));
     MDK_CUDA(c, c->bb_center.reserve(c->n_blocks)); MDK_CUDA(c, c->bb_half.reserve(c->n_blocks));
+    MDK_CUDA(c, c->dd_blk.reserve(DD_MAXR + 1));
+    if (c->dd) MDK_CUDA(c, c->dd_mark.reserve(c->n_pad));
     MDK_CUDA(c, c->excl_s.reserve((size_t)n * (c->wb > 0 ? c->wb : 1)));
     MDK_CUDA(c, c->p14_s.reserve((size_t)n * (c->ws > 0 ? c->ws : 1)));
     c->sort_end_bit = 1;
@@ -503,13 +584,8 @@ static int nlist_reserve_pools(mdk_ctx *c) {
 // Bookkeeping at the end of a rebuild that runs inside a CUDA graph (no host in the loop):
 // sticky error bits in flags[3] (1 = pool overflow, 2 = a block outgrew the hoisted-minimum-image
 // bound), rebuild counter and list sizes in counters[12..15].
-__global__ void k_after_build(int *counters, int *flags, float lim_x, float lim_y, float lim_z, int check_shift) {
+__global__ void k_after_build(int *counters, int *flags) {
     if (flags[2]) flags[3] |= 1;
-    if (check_shift) {
-        if (__int_as_float(counters[8]) > lim_x || __int_as_float(counters[9]) > lim_y ||
-            __int_as_float(counters[10]) > lim_z)
-            flags[3] |= 2;
-    }
     counters[12] += 1;
     counters[13] = counters[0]; counters[14] = counters[4]; counters[15] = counters[2];
 }
@@ -527,6 +603,8 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph) {
                                                 c->idx_tmp.p, c->order.p, n, 0, c->sort_end_bit, c->stream));
     k_cell_start<<<(int)((ncells + 1 + T - 1) / T), T, 0, c->stream>>>(n, (int)ncells, c->cell_key_sorted.p,
                                                                        c->cell_start.p);
+    k_dd_bounds<<<1, DD_MAXR + 1, 0, c->stream>>>(g.dd, c->n_blocks, c->cell_start.p, c->dd_blk.p);
+    if (c->dd) MDK_CUDA(c, cudaMemsetAsync(c->dd_mark.p, 0, (size_t)c->n_pad * sizeof(int), c->stream));
     float sqrt_ke = c->have_coul ? (float)sqrt(c->k_e) : 0.f;
     k_gather_sorted<<<(c->n_pad + T - 1) / T, T, 0, c->stream>>>(n, c->n_pad, c->order.p, c->x_cur.p, c->q.p,
                                                                  c->lj4.p, c->have_lj, sqrt_ke, Ld, c->xs.p,
@@ -547,18 +625,15 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph) {
     o.counters = c->counters.p; o.flags = c->flags.p;
     o.cap_units = (int)c->cap_units; o.cap_chunks = (int)c->cap_chunks; o.cap_masks = (int)c->cap_masks;
     o.seg = c->seg_chunks;
+    o.mark = c->dd ? c->dd_mark.p : nullptr; o.own_lo = 0; o.own_hi = c->n_pad;
     int blocks = (c->n_blocks * c->n_parts + BUILD_WARPS - 1) / BUILD_WARPS;
     int max_blocks = c->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     k_build_lists<<<blocks, BUILD_WARPS * 32, 0, c->stream>>>(g, c->n_parts, c->xs.p, c->bb_center.p, c->bb_half.p,
-                                                             c->cell_start.p, c->excl_s.p, c->wb, c->p14_s.p,
+                                                             c->cell_start.p, c->dd_blk.p, c->excl_s.p, c->wb, c->p14_s.p,
                                                              c->ws, o);
-    if (in_graph) {
-        float lim[3];
-        for (int a = 0; a < 3; ++a) lim[a] = 0.5f * c->box.L[a] - g.R - 0.05f;
-        k_after_build<<<1, 1, 0, c->stream>>>(c->counters.p, c->flags.p, lim[0], lim[1], lim[2], c->shift_ok ? 1 : 0);
-    }
-    c->n_launches += in_graph ? 0 : 9;
+    if (in_graph) k_after_build<<<1, 1, 0, c->stream>>>(c->counters.p, c->flags.p);
+    c->n_launches += in_graph ? 0 : 10;
     MDK_CUDA(c, cudaGetLastError());
     return MDK_OK;
 }
@@ -576,21 +651,13 @@ int nlist_rebuild(mdk_ctx *c) {
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
         if (!h_flags[2]) {
             c->stat_units = h_cnt[0]; c->stat_chunks = h_cnt[4]; c->stat_masks = h_cnt[2];  // [4] = filled chunks
-            // hoisted minimum image (k_pair<..., SHIFT>): every listed j must have a unique image within
-            // L/2 of the block centre.  An interacting j is within R of some i-atom, which is within h of
-            // the centre, so R + h_max <= L/2 on every axis is enough (pairs farther apart than R may then
-            // see a non-minimal image, but both distances exceed the cutoff).  1 A spare when later
-            // rebuilds will run inside a graph and cannot switch kernels.
+            // hoisted-image kernel where the box leaves room for it (a static property of box and cutoff: blocks
+            // that are too wide for it are flagged one by one by the builder)
             const bool shift_before = c->shift_ok;
             c->shift_ok = true;
-            for (int a = 0; a < 3; ++a) {
-                float hmax;
-                memcpy(&hmax, &h_cnt[8 + a], sizeof(float));
-                if (g.R + hmax + (c->graph_pools ? 1.0f : 0.f) + 0.05f > 0.5f * c->box.L[a]) c->shift_ok = false;
-            }
-            // the SHIFT / canonical choice is a template argument of the k_pair launch captured in the step
-            // graphs (and the in-graph bound check is armed only for SHIFT): a flip makes them stale
-            if (c->shift_ok != shift_before) ++c->graph_epoch;
+            for (int a = 0; a < 3; ++a)
+                if (g.wide_lim[a] < 1.5f) c->shift_ok = false;
+            if (c->shift_ok != shift_before) ++c->graph_epoch;   // template argument of the captured k_pair launch
             c->nlist_valid = true;
             ++c->n_rebuilds;
             return MDK_OK;

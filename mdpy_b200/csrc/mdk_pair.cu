@@ -174,14 +174,79 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
     }
 }
 
-// SHIFT: the box is large enough (nlist_rebuild sets ctx->shift_ok) that every atom of a unit has a
-// unique periodic image within L/2 of the i-block centre; positions are reduced to that frame once
-// per atom (i: once per unit, j: once per chunk when it is staged) and the 32 x 32 inner loop works on
-// plain differences.  Without SHIFT the loop applies the canonical minimum image to every pair
-// (small boxes, and the criterion the pair-set hook k_enumerate reproduces bit for bit); with SHIFT
-// the same criterion is evaluated on d rounded once more (pairs within an ulp of rc may differ).
-// ONECUT: LJ and Coulomb share one cutoff.  ENERGY: off for the steps of a graph run whose energies
-// nobody reads.
+// SHIFT: every atom of the unit has a unique periodic image within L/2 of the i-block centre (true when the block's
+// bounding box is small against the box: R + h <= L/2 on every axis; the list builder flags the rare "wide" blocks —
+// a block that straddles the end of a cell row or a domain boundary — in unit.w and those units take the
+// canonical path below).  Positions are reduced to that frame once per atom (i: once per unit, j: once per chunk
+// when it is staged) and the 32 x 32 inner loop works on plain differences; slots whose r^2 lands within a few
+// ulp(L) of a cutoff are re-decided on the canonical expression (chunk_loop), so the pair set is the canonical
+// one bit for bit.  Without SHIFT the loop applies the canonical minimum image to every pair (small boxes).
+// ONECUT: LJ and Coulomb share one cutoff.  ENERGY: off for the steps of a graph run whose energies nobody reads.
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool EMIT>
+__device__ __forceinline__ void pair_unit(const PairParams &P, const NlistView &nl, const int4 unit, const float4 *__restrict__ xs,
+                                          const float4 *__restrict__ ljs, const float4 *__restrict__ bbc,
+                                          long long *__restrict__ f_acc, float4 *__restrict__ s_x, float4 *__restrict__ s_lj,
+                                          const int lane, long long &e_lj_tot, long long &e_c_tot, const EmitOut &em) {
+    const int ia = unit.x * TILE + lane;
+    float4 xi = xs[ia];
+    const float4 li = ljs[ia];
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (SHIFT) {
+        const float4 c = bbc[unit.x];
+        cx = c.x; cy = c.y; cz = c.z;
+        xi.x = min_image(xi.x - cx, P.L[0], P.invL[0]);
+        xi.y = min_image(xi.y - cy, P.L[1], P.invL[1]);
+        xi.z = min_image(xi.z - cz, P.L[2], P.invL[2]);
+    }
+    float fix = 0.f, fiy = 0.f, fiz = 0.f;
+    float e_lj = 0.f, e_c = 0.f;
+
+    for (int cidx = 0; cidx < unit.z; ++cidx) {
+        const int chunk = unit.y + cidx;
+        const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
+        const int mslot = nl.chunk_mask[chunk];
+        float4 xj_own = xs[j];
+        if (SHIFT) {
+            xj_own.x = min_image(xj_own.x - cx, P.L[0], P.invL[0]);
+            xj_own.y = min_image(xj_own.y - cy, P.L[1], P.invL[1]);
+            xj_own.z = min_image(xj_own.z - cz, P.L[2], P.invL[2]);
+        }
+        __syncwarp();
+        s_x[lane] = xj_own; s_x[lane + 32] = xj_own;
+        if (DO_LJ) { const float4 lo = ljs[j]; s_lj[lane] = lo; s_lj[lane + 32] = lo; }
+        __syncwarp();
+        float fjx = 0.f, fjy = 0.f, fjz = 0.f;
+        if (mslot >= 0) {
+            const unsigned excl = nl.mask_excl[(size_t)mslot * 32 + lane];
+            const unsigned m14 = DO_LJ ? nl.mask_14[(size_t)mslot * 32 + lane] : 0u;
+            chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, true, EMIT>(
+                P, s_x, s_lj, lane, xi, li, excl, m14, fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c, xs,
+                nl.chunk_j + (size_t)chunk * 32, ia, em);
+        } else {
+            chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, false, EMIT>(
+                P, s_x, s_lj, lane, xi, li, 0u, 0u, fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c, xs,
+                nl.chunk_j + (size_t)chunk * 32, ia, em);
+        }
+        // after 32 rotations lane l holds the sum for slot l again
+        if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {
+            atomic_add_fix(&f_acc[3 * (size_t)j + 0], to_fix(fjx));
+            atomic_add_fix(&f_acc[3 * (size_t)j + 1], to_fix(fjy));
+            atomic_add_fix(&f_acc[3 * (size_t)j + 2], to_fix(fjz));
+        }
+    }
+    if (fix != 0.f || fiy != 0.f || fiz != 0.f) {
+        atomic_add_fix(&f_acc[3 * (size_t)ia + 0], to_fix(fix));
+        atomic_add_fix(&f_acc[3 * (size_t)ia + 1], to_fix(fiy));
+        atomic_add_fix(&f_acc[3 * (size_t)ia + 2], to_fix(fiz));
+    }
+    if (ENERGY) {
+        // per-unit energies are converted to fixed point one by one: the total is then independent of
+        // which warp (or which rank) happened to evaluate which unit
+        e_lj_tot += to_fix((double)e_lj);
+        e_c_tot += to_fix((double)e_c);
+    }
+}
+
 template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool EMIT = false>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
@@ -191,8 +256,6 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
     __shared__ float4 s_lj[PAIR_WARPS][64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_units = *nl.n_units;
-    // per-unit energies are converted to fixed point one by one: the total is then independent of
-    // which warp (or which rank) happened to evaluate which unit
     long long e_lj_tot = 0, e_c_tot = 0;
 
     for (;;) {
@@ -201,62 +264,12 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) break;
         const int4 unit = nl.units[u];
-        const int ia = unit.x * TILE + lane;
-        float4 xi = xs[ia];
-        const float4 li = ljs[ia];
-        float cx = 0.f, cy = 0.f, cz = 0.f;
-        if (SHIFT) {
-            const float4 c = bbc[unit.x];
-            cx = c.x; cy = c.y; cz = c.z;
-            xi.x = min_image(xi.x - cx, P.L[0], P.invL[0]);
-            xi.y = min_image(xi.y - cy, P.L[1], P.invL[1]);
-            xi.z = min_image(xi.z - cz, P.L[2], P.invL[2]);
-        }
-        float fix = 0.f, fiy = 0.f, fiz = 0.f;
-        float e_lj = 0.f, e_c = 0.f;
-
-        for (int cidx = 0; cidx < unit.z; ++cidx) {
-            const int chunk = unit.y + cidx;
-            const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
-            const int mslot = nl.chunk_mask[chunk];
-            float4 xj_own = xs[j];
-            if (SHIFT) {
-                xj_own.x = min_image(xj_own.x - cx, P.L[0], P.invL[0]);
-                xj_own.y = min_image(xj_own.y - cy, P.L[1], P.invL[1]);
-                xj_own.z = min_image(xj_own.z - cz, P.L[2], P.invL[2]);
-            }
-            __syncwarp();
-            s_x[wid][lane] = xj_own; s_x[wid][lane + 32] = xj_own;
-            if (DO_LJ) { const float4 lo = ljs[j]; s_lj[wid][lane] = lo; s_lj[wid][lane + 32] = lo; }
-            __syncwarp();
-            float fjx = 0.f, fjy = 0.f, fjz = 0.f;
-            if (mslot >= 0) {
-                const unsigned excl = nl.mask_excl[(size_t)mslot * 32 + lane];
-                const unsigned m14 = DO_LJ ? nl.mask_14[(size_t)mslot * 32 + lane] : 0u;
-                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, true, EMIT>(
-                    P, s_x[wid], s_lj[wid], lane, xi, li, excl, m14, fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c, xs,
-                    nl.chunk_j + (size_t)chunk * 32, ia, em);
-            } else {
-                chunk_loop<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, false, EMIT>(
-                    P, s_x[wid], s_lj[wid], lane, xi, li, 0u, 0u, fix, fiy, fiz, fjx, fjy, fjz, e_lj, e_c, xs,
-                    nl.chunk_j + (size_t)chunk * 32, ia, em);
-            }
-            // after 32 rotations lane l holds the sum for slot l again
-            if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {
-                atomic_add_fix(&f_acc[3 * (size_t)j + 0], to_fix(fjx));
-                atomic_add_fix(&f_acc[3 * (size_t)j + 1], to_fix(fjy));
-                atomic_add_fix(&f_acc[3 * (size_t)j + 2], to_fix(fjz));
-            }
-        }
-        if (fix != 0.f || fiy != 0.f || fiz != 0.f) {
-            atomic_add_fix(&f_acc[3 * (size_t)ia + 0], to_fix(fix));
-            atomic_add_fix(&f_acc[3 * (size_t)ia + 1], to_fix(fiy));
-            atomic_add_fix(&f_acc[3 * (size_t)ia + 2], to_fix(fiz));
-        }
-        if (ENERGY) {
-            e_lj_tot += to_fix((double)e_lj);
-            e_c_tot += to_fix((double)e_c);
-        }
+        if (SHIFT && unit.w)      // a wide i-block: canonical minimum image per pair (warp-uniform branch)
+            pair_unit<DO_LJ, DO_COUL, SWITCH, false, ONECUT, ENERGY, EMIT>(P, nl, unit, xs, ljs, bbc, f_acc, s_x[wid], s_lj[wid], lane,
+                                                                          e_lj_tot, e_c_tot, em);
+        else
+            pair_unit<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, EMIT>(P, nl, unit, xs, ljs, bbc, f_acc, s_x[wid], s_lj[wid], lane,
+                                                                          e_lj_tot, e_c_tot, em);
     }
     if (ENERGY && DO_LJ) {
         long long v = warp_sum_ll(e_lj_tot);
@@ -380,8 +393,9 @@ __global__ void k_excl_correction(int first, int end, int wb, const int *__restr
 int pair_special(mdk_ctx *c, bool pme_excl) {
     if (!pme_excl || c->wb <= 0) return MDK_OK;
     PhaseTimer pt(c, PH_BONDED);
-    const long long total = (long long)c->n * c->wb;      // multi-GPU: contiguous range of table entries per rank
-    const int first = (int)(total * c->rank / c->nranks), end = (int)(total * (c->rank + 1) / c->nranks);
+    // the table is in tile-slot order: the rows of this rank's own atoms are one contiguous range (a pair (k, p > k)
+    // belongs to the owner of k)
+    const int first = own_first(c) * c->wb, end = own_end(c) * c->wb;
     if (end <= first) return MDK_OK;
     k_excl_correction<<<(end - first + 255) / 256, 256, 0, c->stream>>>(
         first, end, c->wb, c->excl_s.p, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,

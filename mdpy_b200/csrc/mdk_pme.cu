@@ -47,7 +47,7 @@ __device__ __forceinline__ void bspline(float w, float (&th)[P], float (&dth)[P]
 }
 
 struct PmeParams {
-    int n;
+    int first, n;         // own tile slots [first, n)
     int nx, ny, nz, nzc;  // nzc = nz/2 + 1
     float invL[3];
     float scale[3];       // n_a / L_a
@@ -62,7 +62,7 @@ __device__ __forceinline__ void frac_index(float x, float invL, int n, int &k0, 
 
 template <int P>
 __global__ void k_spread(PmeParams p, const float4 *__restrict__ xs, long long *__restrict__ grid) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = p.first + blockIdx.x * blockDim.x + threadIdx.x;   // tile slots [first, n): the atoms this rank owns
     if (i >= p.n) return;
     float4 a = xs[i];
     if (a.w == 0.f) return;
@@ -126,7 +126,7 @@ __global__ void k_convolve(int nx, int ny, int nzc, int nz, float2 *__restrict__
 template <int P>
 __global__ void k_gather(PmeParams p, const float4 *__restrict__ xs, const float *__restrict__ phi,
                          long long *__restrict__ f_acc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = p.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     float4 a = xs[i];
     if (a.w == 0.f) return;
@@ -335,7 +335,7 @@ static int ilog2_exact(int n) {
     return (1 << l) == n ? l : -1;
 }
 static bool mesh_fast_ok(const mdk_ctx *c) {
-    if (c->pme_force_cufft) return false;
+    if (c->pme_force_cufft || c->dd) return false;   // the decomposed step adds the other domains' sub-meshes in float: cuFFT chain
     for (int a = 0; a < 3; ++a)
         if (c->pme_n[a] < 8 || c->pme_n[a] > FFT_NMAX || ilog2_exact(c->pme_n[a]) < 0) return false;
     return true;
@@ -432,76 +432,96 @@ int pme_prepare(mdk_ctx *c) {
     return MDK_OK;
 }
 
-template <int P>
-static int pme_run(mdk_ctx *c) {
+static PmeParams make_pme_params(mdk_ctx *c) {
     PmeParams p{};
-    p.n = c->n;
+    p.first = own_first(c); p.n = own_end(c);
     p.nx = c->pme_n[0]; p.ny = c->pme_n[1]; p.nz = c->pme_n[2]; p.nzc = p.nz / 2 + 1;
     for (int a = 0; a < 3; ++a) {
         p.invL[a] = c->box.invL[a];
         p.scale[a] = (float)(c->pme_n[a] / c->box.Ld[a]);
     }
-    size_t total = (size_t)p.nx * p.ny * p.nz, totc = (size_t)p.nx * p.ny * p.nzc;
+    return p;
+}
+
+// own atoms -> fixed-point charge mesh
+int pme_spread(mdk_ctx *c) {
+    PhaseTimer pt(c, PH_SPREAD);
+    PmeParams p = make_pme_params(c);
+    const int cnt = p.n - p.first;
+    if (cnt <= 0) return MDK_OK;
+    const int B = (cnt + 127) / 128;
+    switch (c->pme_order) {
+        case 4: k_spread<4><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+        case 5: k_spread<5><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+        case 6: k_spread<6><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+        case 8: k_spread<8><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+        default: return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", c->pme_order);
+    }
+    c->n_launches += 1;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// charge mesh -> potential mesh.  convert: the charge mesh is the fixed-point one (converted to float and cleared
+// here); otherwise grid_r already holds it in float (decomposed step: sub-meshes added on the mesh rank).
+int pme_mesh(mdk_ctx *c, bool convert) {
+    const PmeParams p = make_pme_params(c);
+    const size_t total = (size_t)p.nx * p.ny * p.nz, totc = (size_t)p.nx * p.ny * p.nzc;
     if (c->pme_fast) {
-        {
-            PhaseTimer pt(c, PH_SPREAD);
-            k_spread<P><<<(c->n + 127) / 128, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p);
-            c->n_launches += 1;
-        }
-        {
-            PhaseTimer pt(c, PH_FFT);
-            MeshDims d{p.nx, p.ny, p.nz, ilog2_exact(p.nx), ilog2_exact(p.ny), ilog2_exact(p.nz)};
-            const size_t smem = (64 + (size_t)std::max(p.ny * p.nz, p.nx * p.nz)) * sizeof(float2);
-            k_mesh_fwd_yz<<<p.nx, MESH_T, smem, c->stream>>>(d, c->grid_fix.p, c->grid_c.p, c->fft_tw.p);
-            k_mesh_x_conv<<<p.ny, MESH_T, smem, c->stream>>>(d, c->grid_c.p, c->influence.p, c->fft_tw.p,
-                                                         reinterpret_cast<long long *>(c->e_acc.p));
-            k_mesh_inv_yz<<<p.nx, MESH_T, smem, c->stream>>>(d, c->grid_c.p, c->grid_r.p, c->fft_tw.p);
-            c->n_launches += 3;
-        }
-        {
-            PhaseTimer pt(c, PH_GATHER);
-            k_gather<P><<<(c->n + 127) / 128, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p);
-            c->n_launches += 1;
-        }
+        PhaseTimer pt(c, PH_FFT);
+        MeshDims d{p.nx, p.ny, p.nz, ilog2_exact(p.nx), ilog2_exact(p.ny), ilog2_exact(p.nz)};
+        const size_t smem = (64 + (size_t)std::max(p.ny * p.nz, p.nx * p.nz)) * sizeof(float2);
+        k_mesh_fwd_yz<<<p.nx, MESH_T, smem, c->stream>>>(d, c->grid_fix.p, c->grid_c.p, c->fft_tw.p);
+        k_mesh_x_conv<<<p.ny, MESH_T, smem, c->stream>>>(d, c->grid_c.p, c->influence.p, c->fft_tw.p,
+                                                     reinterpret_cast<long long *>(c->e_acc.p));
+        k_mesh_inv_yz<<<p.nx, MESH_T, smem, c->stream>>>(d, c->grid_c.p, c->grid_r.p, c->fft_tw.p);
+        c->n_launches += 3;
         MDK_CUDA(c, cudaGetLastError());
         return MDK_OK;
     }
     cufftSetStream(c->plan_r2c, c->stream);
     cufftSetStream(c->plan_c2r, c->stream);
-    {
+    if (convert) {
         PhaseTimer pt(c, PH_SPREAD);
-        k_spread<P><<<(c->n + 127) / 128, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p);
         k_grid_convert<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(total, c->grid_fix.p, c->grid_r.p);
-        c->n_launches += 2;
-    }
-    {
-        PhaseTimer pt(c, PH_FFT);
-        if (cufftExecR2C(c->plan_r2c, c->grid_r.p, reinterpret_cast<cufftComplex *>(c->grid_c.p)) != CUFFT_SUCCESS)
-            return fail(c, MDK_ERR_CUDA, "cufftExecR2C failed");
-        k_convolve<<<(unsigned)((totc + 255) / 256), 256, 0, c->stream>>>(
-            p.nx, p.ny, p.nzc, p.nz, c->grid_c.p, c->influence.p, reinterpret_cast<long long *>(c->e_acc.p));
-        if (cufftExecC2R(c->plan_c2r, reinterpret_cast<cufftComplex *>(c->grid_c.p), c->grid_r.p) != CUFFT_SUCCESS)
-            return fail(c, MDK_ERR_CUDA, "cufftExecC2R failed");
         c->n_launches += 1;
     }
-    {
-        PhaseTimer pt(c, PH_GATHER);
-        k_gather<P><<<(c->n + 127) / 128, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p);
-        c->n_launches += 1;
+    PhaseTimer pt(c, PH_FFT);
+    if (cufftExecR2C(c->plan_r2c, c->grid_r.p, reinterpret_cast<cufftComplex *>(c->grid_c.p)) != CUFFT_SUCCESS)
+        return fail(c, MDK_ERR_CUDA, "cufftExecR2C failed");
+    k_convolve<<<(unsigned)((totc + 255) / 256), 256, 0, c->stream>>>(
+        p.nx, p.ny, p.nzc, p.nz, c->grid_c.p, c->influence.p, reinterpret_cast<long long *>(c->e_acc.p));
+    if (cufftExecC2R(c->plan_c2r, reinterpret_cast<cufftComplex *>(c->grid_c.p), c->grid_r.p) != CUFFT_SUCCESS)
+        return fail(c, MDK_ERR_CUDA, "cufftExecC2R failed");
+    c->n_launches += 1;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// potential mesh -> forces on own atoms
+int pme_gather(mdk_ctx *c) {
+    PhaseTimer pt(c, PH_GATHER);
+    PmeParams p = make_pme_params(c);
+    const int cnt = p.n - p.first;
+    if (cnt <= 0) return MDK_OK;
+    const int B = (cnt + 127) / 128;
+    switch (c->pme_order) {
+        case 4: k_gather<4><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p); break;
+        case 5: k_gather<5><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p); break;
+        case 6: k_gather<6><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p); break;
+        case 8: k_gather<8><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_r.p, c->f_acc.p); break;
+        default: return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", c->pme_order);
     }
+    c->n_launches += 1;
     MDK_CUDA(c, cudaGetLastError());
     return MDK_OK;
 }
 
 int pme_compute(mdk_ctx *c) {
     MDK_TRY(pme_prepare(c));
-    switch (c->pme_order) {
-        case 4: return pme_run<4>(c);
-        case 5: return pme_run<5>(c);
-        case 6: return pme_run<6>(c);
-        case 8: return pme_run<8>(c);
-    }
-    return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", c->pme_order);
+    MDK_TRY(pme_spread(c));
+    MDK_TRY(pme_mesh(c, true));
+    return pme_gather(c);
 }
 
 }  // namespace mdk

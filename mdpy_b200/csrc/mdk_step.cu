@@ -129,13 +129,16 @@ __device__ __forceinline__ void block_energy(double e, long long *e_acc, int whi
 }
 
 // E = k (r - r0)^2   (charmm_bond_constraint.py:53-73)
-__global__ void k_bonds(int first, int nb, const int *__restrict__ idx, const float *__restrict__ par,
+// A term belongs to the rank that owns its first atom (tile slot in [own_lo, own_hi)); every rank walks the whole
+// term list and skips the others' terms.
+__global__ void k_bonds(int own_lo, int own_hi, int nb, const int *__restrict__ idx, const float *__restrict__ par,
                         const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                         long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (t < nb) {
-        int s1 = inv_order[idx[2 * t]], s2 = inv_order[idx[2 * t + 1]];
+    int s1 = t < nb ? inv_order[idx[2 * t]] : -1;
+    if (s1 >= own_lo && s1 < own_hi) {
+        int s2 = inv_order[idx[2 * t + 1]];
         double k = par[2 * t], r0 = par[2 * t + 1];
         V3 d = mi_vec(xs[s1], xs[s2], bx);
         double r = sqrt(dot(d, d));
@@ -149,13 +152,14 @@ __global__ void k_bonds(int first, int nb, const int *__restrict__ idx, const fl
 }
 
 // E = k (theta - theta0)^2 + k_ub (r13 - r_ub)^2   (charmm_angle_constraint.py:55-96)
-__global__ void k_angles(int first, int na, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_angles(int own_lo, int own_hi, int na, const int *__restrict__ idx, const float *__restrict__ par,
                          const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                          long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (t < na) {
-        int s1 = inv_order[idx[3 * t]], s2 = inv_order[idx[3 * t + 1]], s3 = inv_order[idx[3 * t + 2]];
+    int s1 = t < na ? inv_order[idx[3 * t]] : -1;
+    if (s1 >= own_lo && s1 < own_hi) {
+        int s2 = inv_order[idx[3 * t + 1]], s3 = inv_order[idx[3 * t + 2]];
         double k = par[4 * t], th0 = par[4 * t + 1], ku = par[4 * t + 2], u0 = par[4 * t + 3];
         float4 p1 = xs[s1], p2 = xs[s2], p3 = xs[s3];
         V3 r21 = mi_vec(p2, p1, bx), r23 = mi_vec(p2, p3, bx);
@@ -207,12 +211,13 @@ __device__ __forceinline__ double torsion(float4 p1, float4 p2, float4 p3, float
 
 // E = k (1 + cos(n phi - delta))   (charmm_dihedral_constraint.py:59-95; the force is the
 // analytic gradient of this energy — the reference's `-k (1 - n sin(..))` at :80 is not).
-__global__ void k_dihedrals(int first, int nd, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_dihedrals(int own_lo, int own_hi, int nd, const int *__restrict__ idx, const float *__restrict__ par,
                             const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                             long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (t < nd) {
+    int s0 = t < nd ? inv_order[idx[4 * t]] : -1;
+    if (s0 >= own_lo && s0 < own_hi) {
         int s[4];
         for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
         double k = par[3 * t], nn = par[3 * t + 1], delta = par[3 * t + 2];
@@ -230,12 +235,13 @@ __global__ void k_dihedrals(int first, int nd, const int *__restrict__ idx, cons
 }
 
 // E = k (psi - psi0)^2   (charmm_improper_constraint.py:57-94)
-__global__ void k_impropers(int first, int ni, const int *__restrict__ idx, const float *__restrict__ par,
+__global__ void k_impropers(int own_lo, int own_hi, int ni, const int *__restrict__ idx, const float *__restrict__ par,
                             const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
                             long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (t < ni) {
+    int s0 = t < ni ? inv_order[idx[4 * t]] : -1;
+    if (s0 >= own_lo && s0 < own_hi) {
         int s[4];
         for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
         double k = par[2 * t], psi0 = par[2 * t + 1];
@@ -252,28 +258,19 @@ __global__ void k_impropers(int first, int ni, const int *__restrict__ idx, cons
     block_energy(e, e_acc, MDK_E_IMPROPER);
 }
 
-// multi-GPU: the terms of each kind are dealt to the ranks in contiguous ranges (the forces meet in the
-// all-reduce, the energies in comm_allreduce_energies)
-static inline void rank_range(const mdk_ctx *c, int n, int &first, int &end) {
-    first = (int)((long long)n * c->rank / c->nranks);
-    end = (int)((long long)n * (c->rank + 1) / c->nranks);
-}
-
 int bonded_compute(mdk_ctx *c, unsigned terms) {
     BoxF bx;
     for (int a = 0; a < 3; ++a) bx.L[a] = c->box.Ld[a];
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
     PhaseTimer pt(c, PH_BONDED);
     const int T = 128;
-    int f, e;
+    const int lo = own_first(c), hi = c->own_hi < 0 ? c->n_pad : c->own_hi;
 #define BONDED(kind, bit, kernel)                                                                              \
     if ((terms & (bit)) && c->bonded[kind].n > 0) {                                                            \
-        rank_range(c, c->bonded[kind].n, f, e);                                                                \
-        if (e > f) {                                                                                           \
-            kernel<<<(e - f + T - 1) / T, T, 0, c->stream>>>(f, e, c->bonded[kind].idx.p, c->bonded[kind].par.p, \
-                                                             c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);  \
-            ++c->n_launches;                                                                                   \
-        }                                                                                                      \
+        const int nt = c->bonded[kind].n;                                                                      \
+        kernel<<<(nt + T - 1) / T, T, 0, c->stream>>>(lo, hi, nt, c->bonded[kind].idx.p, c->bonded[kind].par.p, \
+                                                      c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);         \
+        ++c->n_launches;                                                                                       \
     }
     BONDED(0, MDK_TERM_BOND, k_bonds)
     BONDED(1, MDK_TERM_ANGLE, k_angles)
@@ -295,9 +292,8 @@ int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry) {
         MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream));
         MDK_CUDA(c, cudaMemsetAsync(c->e_acc.p, 0, MDK_NUM_ENERGIES * sizeof(long long), c->stream));
     }
-    // multi-GPU roles (mdk_comm.cu): every rank evaluates its own i-blocks' pair units and its range of
-    // the bonded / excluded-pair terms; bare Coulomb runs on rank 0, the PME mesh on the last rank
-    const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
+    // (single domain; the domain-decomposed step has its own driver, mdk_dd.cu:dd_forces)
+    const bool first = true, last = true;
     // Three independent chains, all adding into the same int64 accumulators (integer atomics commute,
     // so concurrency does not change a single bit): k_pair on the main stream, the PME mesh on s_pme,
     // the O(N) kernels on s_aux.  Per-phase profiling (level 2) serialises them on the main stream.
@@ -325,13 +321,13 @@ int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry) {
     MDK_TRY(pair_compute(c, terms & MDK_TERM_LJ, terms & MDK_TERM_COUL_DIRECT));
     if (fork && want_pme) MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_pme, 0));
     if (fork && want_aux) MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));
-    MDK_TRY(comm_allreduce_forces(c));
     return MDK_OK;
 }
 
 int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies) {
     if (!c->have_box || c->n <= 0 || !c->have_pos)
         return fail(c, MDK_ERR_NOT_BOUND, "mdk_compute before box/atoms/positions were set");
+    if (c->dd) return dd_compute_single(c, terms, sync_energies);
     if (!c->xs_current) MDK_TRY(nlist_refresh_sorted(c));
     MDK_TRY(nlist_ensure(c));
     c->xs_current = true;
@@ -458,14 +454,14 @@ __global__ void k_verlet_velocity(int n, int quirks, double dt, const int *__res
 // mode bit 0 (FINISH): f_acc holds f(x_n+1); complete v_n+1 with noise index step-1, set f_prev.
 // mode bit 1 (ADVANCE): move x one step with noise index `step` using the newest force.
 // mode bit 2 (FROM_PREV): the newest force is f_prev (start of a call on a cached state).
-__global__ void k_langevin(int n, int mode, double dt, double ca, double cb, double two_g_kT_dt,
+__global__ void k_langevin(int first, int n, int mode, double dt, double ca, double cb, double two_g_kT_dt,
                            uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_dev,
                            const unsigned long long *__restrict__ mode_dev, const int *__restrict__ order,
                            const float *__restrict__ mass, long long *__restrict__ f_acc,
                            double *__restrict__ x_cur, double *__restrict__ vel, double *__restrict__ f_prev,
                            StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
                            int *__restrict__ flags) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = first + blockIdx.x * blockDim.x + threadIdx.x;   // tile slots [first, n): the atoms this rank owns
     if (k >= n) return;
     // a host-state call that ran ahead of its own change check (mdk_step_langevin_host): the host
     // positions turned out to differ from the device's, the cached force is stale — leave the state alone
@@ -526,19 +522,48 @@ __global__ void k_kinetic(int n, const float *__restrict__ mass, const double *_
     if ((threadIdx.x & 31) == 0 && e != 0.0) atomic_add_fix(&e_acc[MDK_E_KINETIC], to_fix(e));
 }
 
-static StepGeom make_geom(mdk_ctx *c) {
+__global__ void k_kinetic_own(int first, int end, const int *__restrict__ order, const float *__restrict__ mass,
+                              const double *__restrict__ vel, long long *__restrict__ e_acc) {
+    int k = first + blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (k < end) {
+        int a = order[k];
+        double vx = vel[3 * a], vy = vel[3 * a + 1], vz = vel[3 * a + 2];
+        e = 0.5 * (double)mass[a] * (vx * vx + vy * vy + vz * vz);
+    }
+    const long long v = warp_sum_ll(to_fix(e));
+    if ((threadIdx.x & 31) == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_KINETIC], v);
+}
+
+StepGeom make_geom(mdk_ctx *c) {
     StepGeom g;
     for (int a = 0; a < 3; ++a) { g.L[a] = c->box.Ld[a]; g.Lf[a] = c->box.L[a]; g.invLf[a] = c->box.invL[a]; }
     g.skin_half2 = 0.25f * c->skin * c->skin;
     return g;
 }
 
+// one Langevin update of tile slots [first, end) on the context stream (the domain-decomposed step, mdk_dd.cu)
+int langevin_launch(mdk_ctx *c, int first, int end, int mode, double dt, double ca, double cb, double tg, uint64_t seed, uint64_t step) {
+    if (end <= first) return MDK_OK;
+    PhaseTimer pt(c, PH_INTEGRATE);
+    StepGeom g = make_geom(c);
+    k_langevin<<<(end - first + 255) / 256, 256, 0, c->stream>>>(first, end, mode, dt, ca, cb, tg, seed, step, nullptr, nullptr, c->order.p,
+                                                                 c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p,
+                                                                 c->xs_ref.p, c->flags.p);
+    ++c->n_launches;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
 int energies_enqueue(mdk_ctx *c) {
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
-    if (c->rank == 0) {
+    if (c->dd) {     // every rank: its own atoms; the sum is taken with the other energies
+        const int f = own_first(c), e = own_end(c);
+        if (e > f) k_kinetic_own<<<(e - f + 255) / 256, 256, 0, c->stream>>>(f, e, c->order.p, c->mass.p, c->vel.p, e_acc);
+    } else {
         k_kinetic<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->mass.p, c->vel.p, e_acc);
-        ++c->n_launches;
     }
+    ++c->n_launches;
     MDK_TRY(comm_allreduce_energies(c));
     // energies, list counters and flags in one 224-byte copy
     MDK_CUDA(c, cudaMemcpyAsync(c->pin_words, c->readback.p, 28 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -570,6 +595,7 @@ static int fetch_energies(mdk_ctx *c, unsigned terms) {
 
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks) {
     if (nsteps <= 0) return MDK_OK;
+    if (c->dd) return fail(c, MDK_ERR_BAD_ARG, "the Verlet integrator is single domain; domain-decomposed runs use the Langevin step");
     if (terms != c->cached_terms) { c->verlet_cached = false; c->langevin_cached = false; c->cached_terms = terms; }
     const int n = c->n, T = 256, B = (n + T - 1) / T;
     StepGeom g = make_geom(c);
@@ -691,7 +717,7 @@ static int graph_build_step(mdk_ctx *c, int variant, double dt, double ca, doubl
     if (rc == MDK_OK) {
         rc = forces_enqueue(c, terms, true);
         if (rc == MDK_OK)
-            k_langevin<<<B, T, 0, s>>>(n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->step_dev.p + 1, c->order.p,
+            k_langevin<<<B, T, 0, s>>>(0, n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->step_dev.p + 1, c->order.p,
                                        c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p,
                                        c->xs_ref.p, c->flags.p);
         cudaError_t e = cudaStreamEndCapture(s, &graph);
@@ -752,7 +778,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
             const bool last = s + 1 == nsteps;
             MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
             MDK_TRY(forces_enqueue(c, terms, true));
-            k_langevin<<<B, T, 0, c->stream>>>(n, last ? 1 : 3, dt, ca, cb, tg, seed, c->langevin_step + (uint64_t)s, nullptr,
+            k_langevin<<<B, T, 0, c->stream>>>(0, n, last ? 1 : 3, dt, ca, cb, tg, seed, c->langevin_step + (uint64_t)s, nullptr,
                                                nullptr, c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p,
                                                c->f_prev.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
             c->n_launches += 2;
@@ -794,14 +820,13 @@ int graph_finish(mdk_ctx *c) {
     c->rebuilds_seen = h_after[12];
     c->n_rebuilds += rebuilt;
     if (rebuilt > 0) { c->stat_units = h_after[13]; c->stat_chunks = h_after[14]; c->stat_masks = h_after[15]; }
-    c->n_launches += (int64_t)rebuilt * 9;
+    c->n_launches += (int64_t)rebuilt * 10;
     if (!c->graph_pending_hosted) {
         c->n_launches += (int64_t)nsteps * c->graph_launches_per_step;
         c->n_pair_launches += nsteps;
     }
     MDK_TRY(check_lost_flag(c));
     if (h_flags[3] & 1) return fail(c, MDK_ERR_OOM, "tile-list pool overflow inside a graph step (raise the pools: more atoms per box than planned)");
-    if (h_flags[3] & 2) return fail(c, MDK_ERR_NLIST_STALE, "an i-block outgrew the hoisted-minimum-image bound inside a graph step");
     return MDK_OK;
 }
 
@@ -817,7 +842,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
 #define LANGEVIN(mode)                                                                                          \
     do {                                                                                                        \
         PhaseTimer pt(c, PH_INTEGRATE);                                                                         \
-        k_langevin<<<B, T, 0, c->stream>>>(n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, nullptr, \
+        k_langevin<<<B, T, 0, c->stream>>>(0, n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, nullptr, \
                                            c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, \
                                            c->xs.p, c->xs_ref.p, c->flags.p);                                   \
         ++c->n_launches;                                                                                        \
@@ -825,9 +850,9 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
     // multi-GPU: plain host-launched steps unless one of the two graph flavours is switched on — `hosted`
     // (upkeep graph + host-launched forces / NCCL / update, no host sync inside a run) or `graph_nccl`
     // (NCCL inside the captured step; hung in round 1)
-    const bool use_graph = c->use_graph && c->profiling < 2 && nsteps >= graph_min_steps &&
-                           (c->nranks == 1 || c->graph_nccl || c->graph_hosted);
-    const bool hosted = c->nranks > 1 && !c->graph_nccl;
+    if (c->dd) return dd_langevin_single(c, dt, kT, gamma, seed, nsteps, terms, defer_energies);
+    const bool use_graph = c->use_graph && c->profiling < 2 && nsteps >= graph_min_steps;
+    const bool hosted = false;
     if (!c->langevin_cached) {
         MDK_TRY(compute_terms(c, terms, false));  // f(x_0)
         LANGEVIN(2);

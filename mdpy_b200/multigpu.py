@@ -1,69 +1,30 @@
 """Multi-GPU host layer: one process per GPU (torchrun), NCCL over NVLink/NVSwitch.
 
-The reference is single-process, single-device; this is new design:
-
-* positions are replicated; every rank integrates all atoms (O(N), deterministic, so all ranks
-  stay bit-identical);
-* the i-blocks of the tile list are dealt to ranks by `block % modulus in [lo, hi)` — tile order is
-  spatial, so this is a fine spatial interleave that also balances the half-shell list lengths;
-  each rank builds and evaluates only its own blocks' work units;
-* the PME mesh runs on the last rank (its pair range is narrowed by the weights so that it still
-  finishes with the others); bonded and excluded-pair terms are dealt evenly, in contiguous ranges;
-* every force evaluation ends with ONE `ncclAllReduce(sum)` of the int64 fixed-point force
-  accumulator, issued by libmdpyb200 on its own stream (mdk_comm.cu).  Integer sums are exact and
-  order independent: the N-GPU forces equal the 1-GPU forces bit for bit.
-
-torch.distributed is used for the rendezvous only (broadcast of the 128-byte NCCL unique id).
+The reference is single-process, single-device; this is new design: spatial domain
+decomposition with halo exchange, implemented in csrc/mdk_dd.cu.  What lives here is the rendezvous — the choice of
+the domain grid, the broadcast of the 128-byte NCCL unique id with torch.distributed (its only use), and the two
+calls that turn a rank's device context into one domain of the job (mdk_comm_init, mdk_dd_init).
 """
 import numpy as np
 
-RESIDUES_PER_RANK = 32   # interleave period = 32 * world i-blocks: fine enough to balance the half-shell lists
 
-
-def shard_ranges(weights, modulus=None):
-    """Split residues [0, modulus) into len(weights) consecutive ranges with widths proportional to
-    weights (largest-remainder rounding, every positive weight gets at least one residue).
-    Returns a list of (lo, hi)."""
-    w = np.asarray(weights, dtype=np.float64)
-    if modulus is None:
-        modulus = RESIDUES_PER_RANK * len(w)
-    if (w < 0).any() or w.sum() <= 0:
-        raise ValueError('weights must be non-negative with a positive sum')
-    if len(w) > modulus:
-        raise ValueError('more ranks than residues')
-    ideal = w / w.sum() * modulus
-    width = np.floor(ideal).astype(int)
-    width[(w > 0) & (width == 0)] = 1
-    # distribute what is left (or take back what the minimum-one rule overspent) by largest remainder
-    while width.sum() < modulus:
-        k = int(np.argmax(ideal - width)); width[k] += 1
-    while width.sum() > modulus:
-        k = int(np.argmax(np.where(width > 1, width - ideal, -np.inf))); width[k] -= 1
-    hi = np.cumsum(width)
-    lo = hi - width
-    return [(int(a), int(b)) for a, b in zip(lo, hi)]
-
-
-def role_weights(nranks, pair_ms, pme_ms, bonded_ms=0.0):
-    """Pair-work weights that equalise rank times when the last rank also runs the PME mesh
-    (pme_ms) and rank 0 the bonded / excluded-pair terms (bonded_ms); pair_ms is the single-GPU
-    pair-kernel time.  Solves  pair_ms * x_r + extra_r = T  with  sum x_r = 1."""
-    extra = np.zeros(nranks)
-    extra[-1] += pme_ms
-    extra[0] += bonded_ms
-    if nranks == 1:
-        return np.ones(1)
-    active = np.ones(nranks, dtype=bool)
-    for _ in range(nranks):
-        T = (pair_ms + extra[active].sum()) / active.sum()
-        x = np.where(active, (T - extra) / pair_ms, 0.0)
-        if (x[active] >= 0).all():
-            break
-        active &= x > 0       # a rank whose extra work already exceeds T gets no pair work
-    x = np.clip(x, 0, None)
-    if x.sum() <= 0:
-        x = np.ones(nranks)
-    return x / x.sum()
+def domain_grid(world, box):
+    """(px, py, pz) with px * py * pz == world: factors of 2 (then 3) are dealt one at a time to the axis whose
+    domains are currently the longest, so 2 GPUs cut the longest axis, 4 -> 2 x 2 x 1, 8 -> 2 x 2 x 2 (SURVEY 8e:
+    slabs at 8 GPUs would be thinner than their own halo)."""
+    box = np.asarray(box, dtype=np.float64).reshape(3)
+    grid = [1, 1, 1]
+    rest = int(world)
+    if rest < 1:
+        raise ValueError('world size must be positive')
+    for f in (2, 3, 5, 7):
+        while rest % f == 0:
+            a = int(np.argmax(box / np.array(grid)))
+            grid[a] *= f
+            rest //= f
+    if rest != 1 or max(grid) > 4:
+        raise ValueError('no domain grid for %d ranks (factors of 2, 3, 5, 7; at most 4 domains per axis)' % world)
+    return tuple(grid)
 
 
 def broadcast_unique_id(dist, dev, rank):
@@ -80,11 +41,14 @@ def broadcast_unique_id(dist, dev, rank):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach(ctx, dist, rank, world, weights=None):
-    """Join this rank's device context to the job: communicator + i-block shard."""
+def attach(ctx, dist, rank, world, grid=None):
+    """Join this rank's device context to the job: NCCL communicator + its domain of the grid.  Afterwards
+    Ensemble.update / LangevinIntegrator.integrate on this ensemble are collective calls."""
     import os
     import sys
     dev = ctx.dev
+    box = np.asarray(ctx.ensemble.state.pbc_matrix, dtype=np.float64).diagonal()
+    grid = domain_grid(world, box) if grid is None else tuple(int(g) for g in grid)
     uid = broadcast_unique_id(dist, dev, rank)
     # NCCL may print its version banner on stdout at the first communicator; keep stdout clean for
     # callers that emit machine-readable output there (bench.py's single JSON line)
@@ -96,11 +60,10 @@ def attach(ctx, dist, rank, world, weights=None):
     finally:
         os.dup2(saved, 1)
         os.close(saved)
-    # The shard ranges MUST be identical on every rank (a block owned twice is counted twice, a block owned
-    # by nobody is lost): weights derived from per-rank timings differ in their last digits, so rank 0's
-    # copy is the one everybody uses.
-    w = np.ones(world) if weights is None else np.asarray(weights, dtype=np.float64)
-    set_weights(ctx, rank, world, broadcast_array(dist, w, rank))
+    dev.dd_init(rank, world, grid)
+    ctx._pos_rev = None          # the next call re-uploads the State: every rank starts from the same complete state
+    ctx.domain_grid = grid
+    return grid
 
 
 def broadcast_array(dist, values, rank, src=0):
@@ -113,8 +76,13 @@ def broadcast_array(dist, values, rank, src=0):
     return t.cpu().numpy()
 
 
-def set_weights(ctx, rank, world, weights):
-    modulus = RESIDUES_PER_RANK * world
-    lo, hi = shard_ranges(weights, modulus)[rank]
-    ctx.dev.set_shard(lo, hi, modulus)
-    ctx.shard = (lo, hi, modulus)
+def lists_pair(b, bj, own_lo, own_hi):
+    """Host mirror of the pair-ownership rule of csrc/mdk_nlist.cu:k_build_lists: does the rank that owns i-blocks
+    [own_lo, own_hi) list block bj in the work of its own block b?  Inside a domain: half shell by index.  Across a
+    domain boundary: the lower block takes the pair when b + bj is even, the higher one when it is odd — both ranks
+    evaluate this on the same global block order, so exactly one of them lists the pair."""
+    if bj == b:
+        return False                      # the diagonal chunk is emitted separately
+    if own_lo <= bj < own_hi:
+        return bj > b
+    return (bj < b) if ((b + bj) & 1) else (bj > b)

@@ -157,7 +157,10 @@ struct mdk_ctx {
     mdk::DDGeom dd_geom{};                    // cell numbering (one domain unless dd is set)
     mdk::DevBuf<int> dd_blk;                  // [ndom + 1] first i-block of each domain (device; written by every rebuild)
     mdk::DevBuf<int> dd_mark;                 // [n_pad] 1 = tile slot referenced by this rank's work but owned by another
-    int own_lo = 0, own_hi = -1;              // tile slots this rank owns (integrates, spreads, owns the terms of); -1 = all
+    int own_lo = 0, own_hi = -1;              // tile slots this rank owns (integrates, owns the terms of); -1 = all
+    int pme_lo = 0, pme_hi = -1;              // tile slots this rank spreads / gathers on the PME mesh: the atoms whose CELL lies in
+                                              // its domain (own slots are whole i-blocks; the block that straddles a domain boundary
+                                              // holds a few atoms of the next domain, which may sit anywhere on that domain's border)
 
     // ---- PME ----
     int pme_n[3] = {0, 0, 0};
@@ -265,6 +268,8 @@ int pme_compute(mdk_ctx *c);
 int pme_spread(mdk_ctx *c);                     // own atoms -> fixed-point mesh
 int pme_mesh(mdk_ctx *c, bool convert);         // (fixed point -> float,) FFT, influence function + energy, inverse FFT
 int pme_gather(mdk_ctx *c);                     // potential mesh -> forces on own atoms
+inline int pme_first(const mdk_ctx *c) { return c->pme_hi < 0 ? 0 : c->pme_lo; }
+inline int pme_end(const mdk_ctx *c) { return c->pme_hi < 0 ? c->n : c->pme_hi; }
 inline int own_first(const mdk_ctx *c) { return c->own_hi < 0 ? 0 : c->own_lo; }
 inline int own_end(const mdk_ctx *c) { return c->own_hi < 0 ? c->n : (c->own_hi < c->n ? c->own_hi : c->n); }
 int bonded_compute(mdk_ctx *c, unsigned terms);

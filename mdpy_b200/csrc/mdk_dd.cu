@@ -69,6 +69,8 @@ struct DDState {
     int64_t stat_exchanges = 0, stat_rebuilds = 0;
 };
 
+constexpr int PIN_ALL = 8 + 2 * (DD_MAXR + 1);     // pinned words: [0..7] flags, [8..] bounds / own counts, [PIN_ALL..] count matrix
+constexpr int PIN_WORDS = PIN_ALL + DD_MAXR * DD_MAXR + 8;
 using Group = std::vector<mdk_ctx *>;
 static std::map<int, Group> g_groups;
 
@@ -94,6 +96,10 @@ __global__ void k_dd_mark_excl(int first, int end, int wb, const int *__restrict
     if (t >= end) return;
     const int k = t / wb, p = excl_s[t];
     if (p > k && (p < own_lo || p >= own_hi)) mark[p] = 1;
+}
+
+__global__ void k_dd_mark_range(int lo, int hi, int *__restrict__ mark) {
+    for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) mark[k] = 1;
 }
 
 // cnt[r] = number of needed slots owned by rank r (need is ascending; rank r owns slots [32 blk[r], 32 blk[r+1]))
@@ -270,8 +276,8 @@ static int dd_gather_state(Group &g) {
     return MDK_OK;
 }
 
-// PME sub-mesh of every rank from the geometry alone (identical on all ranks): the domain's cell range + one cell
-// (a block that straddles a boundary belongs to the lower domain) + the drift allowed between rebuilds + spline support
+// PME sub-mesh of every rank from the geometry alone (identical on all ranks): the domain's cell range (a rank spreads
+// exactly the atoms whose cell lies in its domain) + the drift allowed between rebuilds + spline support
 static void dd_mesh_boxes(mdk_ctx *c) {
     DDState *d = c->dd;
     const DDGeom &gm = c->dd_geom;
@@ -284,7 +290,7 @@ static void dd_mesh_boxes(mdk_ctx *c) {
         b.pts = 1;
         for (int a = 0; a < 3; ++a) {
             const double w = c->cellw[a], L = c->box.Ld[a];
-            const double x0 = gm.cut[a][dom[a]] * w - 0.5 * c->skin - 0.05 * w, x1 = (gm.cut[a][dom[a] + 1] + 1) * w + 0.5 * c->skin + 0.05 * w;
+            const double x0 = gm.cut[a][dom[a]] * w - 0.5 * c->skin - 0.05 * w, x1 = gm.cut[a][dom[a] + 1] * w + 0.5 * c->skin + 0.05 * w;
             const int m = c->pme_n[a];
             int lo = (int)floor(x0 / L * m) - c->pme_order, hi = (int)floor(x1 / L * m) + 2;   // mesh index of x = -L/2 is 0
             int n = hi - lo + 1;
@@ -312,11 +318,17 @@ static int dd_rebuild(Group &g) {
         DDState *d = c->dd;
         MDK_TRY(nlist_rebuild(c));                // keys (domain-major) -> sort -> gathers -> bounds -> own lists (+ marks)
         // ownership of this rebuild
-        MDK_CUDA(c, cudaMemcpyAsync(d->pin + 8, c->dd_blk.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaMemcpyAsync(d->pin + 8, c->dd_blk.p, 2 * (DD_MAXR + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
         d->blk.assign(d->pin + 8, d->pin + 8 + P + 1);
         c->own_lo = d->blk[c->rank] * TILE;
         c->own_hi = d->blk[c->rank + 1] * TILE;
+        c->pme_lo = d->pin[8 + DD_MAXR + 1 + c->rank];
+        c->pme_hi = d->pin[8 + DD_MAXR + 1 + c->rank + 1];
+        // the few atoms of this domain that sit in the previous rank's last (straddling) i-block: spread / gathered
+        // here, integrated there — their positions come in and their mesh forces go back with the halo
+        if (c->pme_lo < c->own_lo)
+            k_dd_mark_range<<<1, 64, 0, c->stream>>>(c->pme_lo, c->own_lo, c->dd_mark.p);
         // halo: what the lists reference (marked by the builder) + the partners of the own bonded / excluded-pair terms
         static const int width[4] = {2, 3, 4, 4};
         for (int kind = 0; kind < 4; ++kind)
@@ -343,18 +355,18 @@ static int dd_rebuild(Group &g) {
     if (!g[0]->dd->local) {
         mdk_ctx *c = g[0];
         MDK_TRY(comm_allgather_i32(c, c->dd->cnt_dev.p, c->dd->cnt_all.p, P));
-        MDK_CUDA(c, cudaMemcpyAsync(c->dd->pin + 8 + DD_MAXR, c->dd->cnt_all.p, (size_t)P * P * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaMemcpyAsync(c->dd->pin + PIN_ALL, c->dd->cnt_all.p, (size_t)P * P * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     } else {
         cudaDeviceSynchronize();
         for (mdk_ctx *c : g)
             for (mdk_ctx *p : g)
-                for (int o = 0; o < P; ++o) c->dd->pin[8 + DD_MAXR + p->rank * P + o] = p->dd->pin[8 + o];
+                for (int o = 0; o < P; ++o) c->dd->pin[PIN_ALL + p->rank * P + o] = p->dd->pin[8 + o];
     }
     for (mdk_ctx *c : g) {
         each_set_device(c);
         DDState *d = c->dd;
-        const int *all = d->pin + 8 + DD_MAXR;
+        const int *all = d->pin + PIN_ALL;
         d->need_cnt.assign(P, 0); d->need_off.assign(P + 1, 0); d->send_cnt.assign(P, 0); d->send_off.assign(P + 1, 0);
         for (int r = 0; r < P; ++r) {
             d->need_cnt[r] = all[c->rank * P + r];
@@ -696,6 +708,7 @@ void dd_destroy(mdk_ctx *c) {
     delete d;
     c->dd = nullptr;
     c->own_lo = 0; c->own_hi = -1;
+    c->pme_lo = 0; c->pme_hi = -1;
 }
 
 }  // namespace mdk
@@ -718,11 +731,11 @@ int mdk_dd_init(mdk_ctx *c, int rank, int nranks, int px, int py, int pz, int lo
     d->pme_rank = nranks - 1;
     d->local = local_group >= 0;
     d->group_id = local_group;
-    if (cudaHostAlloc(reinterpret_cast<void **>(&d->pin), (8 + DD_MAXR + DD_MAXR * DD_MAXR + 8) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(reinterpret_cast<void **>(&d->pin), PIN_WORDS * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
         delete d;
         return fail(c, MDK_ERR_OOM, "cudaHostAlloc failed in mdk_dd_init");
     }
-    memset(d->pin, 0, (8 + DD_MAXR + DD_MAXR * DD_MAXR + 8) * sizeof(int));
+    memset(d->pin, 0, PIN_WORDS * sizeof(int));
     d->blk.assign(nranks + 1, 0);
     c->dd = d;
     c->dd_geom.pdim[0] = px; c->dd_geom.pdim[1] = py; c->dd_geom.pdim[2] = pz;

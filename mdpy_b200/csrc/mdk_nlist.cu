@@ -89,11 +89,14 @@ __global__ void k_cell_start(int n, int ncells, const unsigned *__restrict__ key
 }
 
 // first i-block of every domain: a block that straddles a domain boundary belongs to the domain of its first atom
-__global__ void k_dd_bounds(DDGeom d, int n_blocks, const int *__restrict__ cell_start, int *__restrict__ blk) {
+// (blk[DD_MAXR + 1 + r] = the exact first tile slot of domain r: the atoms whose cell lies in the domain)
+__global__ void k_dd_bounds(DDGeom d, int n, int n_blocks, const int *__restrict__ cell_start, int *__restrict__ blk) {
     const int ndom = d.pdim[0] * d.pdim[1] * d.pdim[2];
     const int r = threadIdx.x;
     if (r > ndom) return;
-    blk[r] = r == 0 ? 0 : (r == ndom ? n_blocks : min(n_blocks, (cell_start[d.dom_base[r]] + TILE - 1) / TILE));
+    const int first = r == ndom ? n : cell_start[d.dom_base[r]];
+    blk[r] = r == 0 ? 0 : (r == ndom ? n_blocks : min(n_blocks, (first + TILE - 1) / TILE));
+    blk[DD_MAXR + 1 + r] = first;
 }
 
 // tile-order gather of positions / charges / LJ parameters; also resets the displacement
@@ -499,6 +502,8 @@ static int nlist_plan(mdk_ctx *c) {
         int nc = (int)floor(c->box.Ld[a] / target[a]);
         if (nc < 1) nc = 1;
         if (nc > 1024) nc = 1024;
+        const int pd = c->dd ? c->dd_geom.pdim[a] : 1;
+        if (pd > 1) { nc -= nc % pd; if (nc < pd) nc = pd; }      // equal cell counts per domain
         c->ncell[a] = nc;
         c->cellw[a] = (float)(c->box.Ld[a] / nc);
         ncells *= nc;
@@ -551,7 +556,7 @@ static int nlist_plan(mdk_ctx *c) {
     MDK_CUDA(c, c->xs.reserve(c->n_pad)); MDK_CUDA(c, c->xs_ref.reserve(c->n_pad));
     MDK_CUDA(c, c->ljs.reserve(c->n_pad)); MDK_CUDA(c, c->f_acc.reserve((size_t)c->n_pad * 3));
     MDK_CUDA(c, c->bb_center.reserve(c->n_blocks)); MDK_CUDA(c, c->bb_half.reserve(c->n_blocks));
-    MDK_CUDA(c, c->dd_blk.reserve(DD_MAXR + 1));
+    MDK_CUDA(c, c->dd_blk.reserve(2 * (DD_MAXR + 1)));
     if (c->dd) MDK_CUDA(c, c->dd_mark.reserve(c->n_pad));
     MDK_CUDA(c, c->excl_s.reserve((size_t)n * (c->wb > 0 ? c->wb : 1)));
     MDK_CUDA(c, c->p14_s.reserve((size_t)n * (c->ws > 0 ? c->ws : 1)));
@@ -603,7 +608,7 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph) {
                                                 c->idx_tmp.p, c->order.p, n, 0, c->sort_end_bit, c->stream));
     k_cell_start<<<(int)((ncells + 1 + T - 1) / T), T, 0, c->stream>>>(n, (int)ncells, c->cell_key_sorted.p,
                                                                        c->cell_start.p);
-    k_dd_bounds<<<1, DD_MAXR + 1, 0, c->stream>>>(g.dd, c->n_blocks, c->cell_start.p, c->dd_blk.p);
+    k_dd_bounds<<<1, DD_MAXR + 1, 0, c->stream>>>(g.dd, n, c->n_blocks, c->cell_start.p, c->dd_blk.p);
     if (c->dd) MDK_CUDA(c, cudaMemsetAsync(c->dd_mark.p, 0, (size_t)c->n_pad * sizeof(int), c->stream));
     float sqrt_ke = c->have_coul ? (float)sqrt(c->k_e) : 0.f;
     k_gather_sorted<<<(c->n_pad + T - 1) / T, T, 0, c->stream>>>(n, c->n_pad, c->order.p, c->x_cur.p, c->q.p,

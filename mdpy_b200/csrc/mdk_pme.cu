@@ -434,7 +434,7 @@ int pme_prepare(mdk_ctx *c) {
 
 static PmeParams make_pme_params(mdk_ctx *c) {
     PmeParams p{};
-    p.first = own_first(c); p.n = own_end(c);
+    p.first = pme_first(c); p.n = pme_end(c);
     p.nx = c->pme_n[0]; p.ny = c->pme_n[1]; p.nz = c->pme_n[2]; p.nzc = p.nz / 2 + 1;
     for (int a = 0; a < 3; ++a) {
         p.invL[a] = c->box.invL[a];

@@ -161,6 +161,12 @@ MDK_API int mdk_step_langevin(mdk_ctx *ctx, double dt, double kT, double gamma, 
 MDK_API int mdk_step_langevin_host(mdk_ctx *ctx, const float *x_in, const float *v_in, float *x_out, float *v_out,
                            double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
                            double *energies);
+/* SteepestDescentMinimizer.minimize (mdpy/minimizer/steepest_descent_minimizer.py:30-53), device resident: up to
+ * max_iterations of x_i += alpha F_i / |F_i| (per-atom unit force vectors, as the reference normalises them), one force
+ * evaluation each, until |E_k - E_k-1| / |E_k-1| < energy_tolerance.  *iterations = iterations done;
+ * energy_first_prev_last[3] = potential energy before the first, before the last and after the last iteration. */
+MDK_API int mdk_minimize_sd(mdk_ctx *ctx, double alpha, double energy_tolerance, int max_iterations, unsigned terms,
+                    int *iterations, double *energy_first_prev_last, double *energies);
 /* Page-locked host memory owned by the ctx (freed by mdk_destroy at the latest): State arrays that
  * live in it move to / from the device by DMA without a staging copy. */
 MDK_API int mdk_host_alloc(mdk_ctx *ctx, size_t bytes, void **out);
@@ -195,7 +201,7 @@ MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64
  * (default 0: hoisted out of the pair loop when the box allows it), 3 = energy sums in every graph
  * step, 4 = NCCL inside the captured step (N > 1; default 0), 5 = persistent pair-kernel blocks per SM
  * (default 4), 6 = cuFFT also for small power-of-two meshes (default 0: fused mesh kernels),
- * 7 = unused. */
+ * 7 = shared-memory staged charge spreading (default 1; 0 = one global atomic per spline point). */
 MDK_API int mdk_set_option(mdk_ctx *ctx, int key, double value);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);

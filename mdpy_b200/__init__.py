@@ -7,7 +7,7 @@ Ensemble, constraint.*, integrator.*.  io / forcefield parsing / dumpers / analy
 SPATIAL_DIM = 3
 
 from .environment import env  # noqa: E402
-from . import unit, utils, error, core, constraint, integrator  # noqa: E402,F401
+from . import unit, utils, error, core, constraint, integrator, minimizer  # noqa: E402,F401
 from .ensemble import Ensemble  # noqa: E402,F401
 
 __version__ = '0.1.0'

@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -95,6 +95,7 @@ def load_library():
         'mdk_dd_compute_group': (i32, [vp, i32, C.c_uint, vp]),
         'mdk_dd_step_langevin_group': (i32, [vp, i32, f64, f64, f64, u64, i32, C.c_uint, vp]),
         'mdk_dd_stats': (i32, [vp, vp]),
+        'mdk_minimize_sd': (i32, [vp, f64, f64, i32, C.c_uint, C.POINTER(i32), vp, vp]),
         'mdk_comm_unique_id': (i32, [vp]),
         'mdk_comm_init': (i32, [vp, i32, i32, vp]),
         'mdk_flush_l2': (i32, [vp]),
@@ -268,6 +269,14 @@ class Device:
     def step_langevin(self, dt, kT, gamma, seed, nsteps, terms):
         self._ck(self._lib.mdk_step_langevin(self._h, float(dt), float(kT), float(gamma), int(seed), int(nsteps), int(terms)))
 
+    def minimize_sd(self, alpha, energy_tolerance, max_iterations, terms):
+        """mdk_minimize_sd -> (iterations, (E_first, E_before_last, E_last), energies[16])."""
+        it = C.c_int(0)
+        e3 = np.zeros(3, dtype=np.float64); e = np.zeros(NUM_ENERGIES, dtype=np.float64)
+        self._ck(self._lib.mdk_minimize_sd(self._h, float(alpha), float(energy_tolerance), int(max_iterations), int(terms),
+                                           C.byref(it), _ptr(e3), _ptr(e)))
+        return it.value, tuple(float(v) for v in e3), e
+
     def pinned_empty(self, shape, dtype=np.float32):
         """numpy array over page-locked memory of this context (mdk_host_alloc): host State arrays kept
         in it are copied to / from the device without a staging pass.  Lives as long as the context."""
@@ -340,8 +349,8 @@ class Device:
 
     def set_option(self, key, value):
         """Execution options of mdk_set_option (include/mdpy_b200.h): 'graph', 'concurrent',
-        'canonical_min_image', 'graph_energy', 'graph_nccl', 'pair_blocks_per_sm', 'pme_cufft', 'graph_hosted'."""
-        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6}[key]
+        'canonical_min_image', 'graph_energy', 'graph_nccl', 'pair_blocks_per_sm', 'pme_cufft', 'spread_smem'."""
+        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6, 'spread_smem': 7}[key]
         self._ck(self._lib.mdk_set_option(self._h, k, float(value)))
 
     def flush_l2(self):

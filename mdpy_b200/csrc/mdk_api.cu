@@ -233,7 +233,7 @@ void mdk_destroy(mdk_ctx *c) {
     graph_destroy(c);
     c->dd_blk.release(); c->dd_mark.release();
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
-    c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release();
+    c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release(); c->excl_pairs.release();
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
     c->x_cur.release(); c->x_prev.release(); c->vel.release(); c->f_prev.release();
     c->order.release(); c->inv_order.release(); c->xs.release(); c->xs_ref.release(); c->ljs.release();
@@ -329,6 +329,19 @@ int mdk_set_exclusions(mdk_ctx *c, const int32_t *bonded, int wb, const int32_t 
     for (size_t i = 0; i < (size_t)c->n * ws; ++i)
         if (scaling[i] < -1 || scaling[i] >= c->n) return fail(c, MDK_ERR_BAD_ARG, "scaling_particles entry %d out of range", scaling[i]);
     c->wb = wb; c->ws = ws;
+    {   // compact list of the excluded pairs for the Ewald correction kernel (one thread per pair instead of one per table entry)
+        std::vector<int2> pairs;
+        for (int i = 0; i < c->n; ++i)
+            for (int e = 0; e < wb; ++e) {
+                const int p = bonded[(size_t)i * wb + e];
+                if (p > i) pairs.push_back(make_int2(i, p));
+            }
+        c->n_excl_pairs = (int)pairs.size();
+        if (!pairs.empty()) {
+            MDK_CUDA(c, c->excl_pairs.reserve(pairs.size()));
+            MDK_CUDA(c, cudaMemcpy(c->excl_pairs.p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        }
+    }
     if (wb > 0) {
         MDK_CUDA(c, c->excl.reserve((size_t)c->n * wb));
         MDK_CUDA(c, cudaMemcpyAsync(c->excl.p, bonded, (size_t)c->n * wb * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -548,6 +561,20 @@ int mdk_step_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t s
     return MDK_OK;
 }
 
+int mdk_minimize_sd(mdk_ctx *c, double alpha, double energy_tolerance, int max_iterations, unsigned terms, int *iterations,
+                    double *energy_first_prev_last, double *energies) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!(alpha > 0) || energy_tolerance < 0 || max_iterations < 0 || !iterations || !energy_first_prev_last)
+        return fail(c, MDK_ERR_BAD_ARG, "mdk_minimize_sd: alpha=%g tolerance=%g max_iterations=%d", alpha, energy_tolerance, max_iterations);
+    prepare_pme_constants(c);
+    *iterations = 0;
+    MDK_TRY(minimize_sd(c, alpha, energy_tolerance, max_iterations, terms, iterations, energy_first_prev_last, energy_first_prev_last + 1,
+                        energy_first_prev_last + 2));
+    if (energies) memcpy(energies, c->last_e, sizeof(c->last_e));
+    return MDK_OK;
+}
+
 int mdk_host_alloc(mdk_ctx *c, size_t bytes, void **out) {
     NEED_CTX(c);
     if (!out || bytes == 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_host_alloc: bad arguments");
@@ -739,7 +766,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 4: c->graph_nccl = value != 0; break;         // N > 1: NCCL all-reduce inside the captured step (hung in round 1)
         case 5: c->pair_blocks_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value); break;
         case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;   // cuFFT also for small power-of-two meshes
-        case 7: c->graph_hosted = value != 0; break;       // N > 1: upkeep graph + host-launched step kernels
+        case 7: c->spread_smem = value != 0; break;        // shared-memory staged charge spreading (default on)
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

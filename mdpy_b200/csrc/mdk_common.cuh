@@ -101,6 +101,8 @@ struct mdk_ctx {
     float rc_lj = 0.f, r_switch = 0.f;
     mdk::DevBuf<int> excl, p14;          // [n, wb] / [n, ws], -1 padded, matrix ids
     int wb = 0, ws = 0;
+    mdk::DevBuf<int2> excl_pairs;        // the excluded pairs (a < b, matrix ids) of the bonded_particles table, compact
+    int n_excl_pairs = 0;
     double k_e = 0.0, alpha = 0.0;
     float rc_coul = 0.f;
     bool have_coul = false;
@@ -173,6 +175,7 @@ struct mdk_ctx {
     mdk::DevBuf<float2> fft_tw;               // twiddles of the small-mesh FFT kernels
     bool pme_fast = false;                    // every mesh axis a power of two in 8..64: own fused FFT kernels instead of cuFFT
     bool pme_force_cufft = false;             // test hook: cuFFT also for small power-of-two meshes
+    bool spread_smem = true;                  // shared-memory staged charge spreading (option 7; 0 = one global atomic per spline point)
     cufftHandle plan_r2c = 0, plan_c2r = 0;
     bool have_plans = false;
     double e_self_bg = 0.0;
@@ -276,6 +279,8 @@ int bonded_compute(mdk_ctx *c, unsigned terms);
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
                        int graph_min_steps, bool defer_energies);
+int minimize_sd(mdk_ctx *c, double alpha, double energy_tolerance, int max_iterations, unsigned terms, int *iterations,
+                double *e_first, double *e_prev, double *e_last);
 int energies_enqueue(mdk_ctx *c);                    // kinetic energy + all-reduce + D2H into pin_words (no sync)
 void energies_finish(mdk_ctx *c, unsigned terms);    // after the stream was synchronised
 int compute_terms(mdk_ctx *c, unsigned terms, bool sync_energies);

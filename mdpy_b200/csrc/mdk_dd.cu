@@ -90,12 +90,12 @@ __global__ void k_dd_mark_terms(int nt, int width, const int *__restrict__ idx, 
     }
 }
 
-__global__ void k_dd_mark_excl(int first, int end, int wb, const int *__restrict__ excl_s, int own_lo, int own_hi,
+__global__ void k_dd_mark_excl(int n_pairs, const int2 *__restrict__ pairs, const int *__restrict__ inv_order, int own_lo, int own_hi,
                                int *__restrict__ mark) {
-    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= end) return;
-    const int k = t / wb, p = excl_s[t];
-    if (p > k && (p < own_lo || p >= own_hi)) mark[p] = 1;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const int k = inv_order[pairs[t].x], p = inv_order[pairs[t].y];
+    if (k >= own_lo && k < own_hi && (p < own_lo || p >= own_hi)) mark[p] = 1;     // the pair belongs to the owner of its first atom
 }
 
 __global__ void k_dd_mark_range(int lo, int hi, int *__restrict__ mark) {
@@ -335,11 +335,9 @@ static int dd_rebuild(Group &g) {
             if (c->bonded[kind].n > 0)
                 k_dd_mark_terms<<<(c->bonded[kind].n + 255) / 256, 256, 0, c->stream>>>(c->bonded[kind].n, width[kind], c->bonded[kind].idx.p,
                                                                                      c->inv_order.p, c->own_lo, c->own_hi, c->dd_mark.p);
-        if (c->wb > 0) {
-            const int first = own_first(c) * c->wb, end = own_end(c) * c->wb;
-            if (end > first)
-                k_dd_mark_excl<<<(end - first + 255) / 256, 256, 0, c->stream>>>(first, end, c->wb, c->excl_s.p, c->own_lo, c->own_hi, c->dd_mark.p);
-        }
+        if (c->n_excl_pairs > 0)
+            k_dd_mark_excl<<<(c->n_excl_pairs + 255) / 256, 256, 0, c->stream>>>(c->n_excl_pairs, c->excl_pairs.p, c->inv_order.p, c->own_lo,
+                                                                              c->own_hi, c->dd_mark.p);
         MDK_CUDA(c, d->need.reserve(c->n_pad));
         MDK_CUDA(c, d->n_sel.reserve(1)); MDK_CUDA(c, d->cnt_dev.reserve(DD_MAXR)); MDK_CUDA(c, d->cnt_all.reserve(DD_MAXR * DD_MAXR));
         size_t tmp = 0;

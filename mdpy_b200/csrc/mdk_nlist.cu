@@ -363,7 +363,12 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                     xg += cn; if (xg >= g.ncell[0]) xg = 0;
                     rem -= cn;
                     if (!multi) s = max(s, first_j);
+                    // decomposed: inside the own domain only j > b counts (half shell by index), except the few slots
+                    // at the start of the domain's range that sit in the previous rank's straddling block
+                    int skip_lo = 0, skip_hi = 0;
+                    if (multi) { skip_lo = max(s, blk_lo * TILE); skip_hi = min(e, min(first_j, blk_hi * TILE)); }
                     for (int base = s; base < e; base += 32) {
+                        if (base >= skip_lo && base + 32 <= skip_hi) continue;   // a whole stride of own atoms at or before this block
                         int j = base + lane;
                         bool pass = false, unsure = false;
                         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);

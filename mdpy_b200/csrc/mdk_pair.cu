@@ -358,16 +358,18 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
 // ---------------------------------------------------------------------------
 // Excluded-pair Ewald correction: the reciprocal sum contains every pair, also the
 // bonded ones the direct sum skips; remove -k_e q_i q_j erf(alpha r)/r for each of them.
-__global__ void k_excl_correction(int first, int end, int wb, const int *__restrict__ excl_s,
-                                  const float4 *__restrict__ xs, double Lx, double Ly, double Lz,
-                                  double alpha, long long *__restrict__ f_acc,
-                                  long long *__restrict__ e_acc) {
-    int t = first + blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per excluded pair (a < b, matrix ids; the compact list mdk_set_exclusions builds from the
+// -1-padded bonded_particles table); the pair belongs to the rank that owns atom a.
+__global__ void k_excl_correction(int n_pairs, const int2 *__restrict__ pairs, const int *__restrict__ inv_order,
+                                  int own_lo, int own_hi, const float4 *__restrict__ xs, double Lx, double Ly, double Lz,
+                                  double alpha, long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
-    if (t < end) {
-        int k = t / wb;
-        int p = excl_s[t];
-        if (p > k) {
+    if (t < n_pairs) {
+        const int2 pr = pairs[t];
+        const int k = inv_order[pr.x];
+        if (k >= own_lo && k < own_hi) {
+            const int p = inv_order[pr.y];
             float4 a = xs[k], b = xs[p];
             double d[3] = {(double)b.x - a.x, (double)b.y - a.y, (double)b.z - a.z};
             d[0] -= Lx * rint(d[0] / Lx); d[1] -= Ly * rint(d[1] / Ly); d[2] -= Lz * rint(d[2] / Lz);
@@ -391,14 +393,11 @@ __global__ void k_excl_correction(int first, int end, int wb, const int *__restr
 }
 
 int pair_special(mdk_ctx *c, bool pme_excl) {
-    if (!pme_excl || c->wb <= 0) return MDK_OK;
+    if (!pme_excl || c->n_excl_pairs <= 0) return MDK_OK;
     PhaseTimer pt(c, PH_BONDED);
-    // the table is in tile-slot order: the rows of this rank's own atoms are one contiguous range (a pair (k, p > k)
-    // belongs to the owner of k)
-    const int first = own_first(c) * c->wb, end = own_end(c) * c->wb;
-    if (end <= first) return MDK_OK;
-    k_excl_correction<<<(end - first + 255) / 256, 256, 0, c->stream>>>(
-        first, end, c->wb, c->excl_s.p, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,
+    const int lo = own_first(c), hi = c->own_hi < 0 ? c->n_pad : c->own_hi;
+    k_excl_correction<<<(c->n_excl_pairs + 255) / 256, 256, 0, c->stream>>>(
+        c->n_excl_pairs, c->excl_pairs.p, c->inv_order.p, lo, hi, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,
         reinterpret_cast<long long *>(c->e_acc.p));
     ++c->n_launches;
     MDK_CUDA(c, cudaGetLastError());

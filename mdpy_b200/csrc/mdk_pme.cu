@@ -90,6 +90,105 @@ __global__ void k_spread(PmeParams p, const float4 *__restrict__ xs, long long *
     }
 }
 
+// Atomics-aware spreading.  Atoms arrive cell sorted, so the 256 consecutive atoms of a thread block sit in a small
+// region of the mesh: the block accumulates them in a shared-memory sub-mesh (int32 fixed point, native shared
+// atomics) and flushes every touched point with ONE 64-bit global atomic — a mesh point is touched by ~6 atoms at
+// water density, most of them in the same block.  Integer sums commute: the mesh stays bitwise reproducible and
+// independent of how the atoms are grouped into blocks (each contribution is rounded to 2^-26 on its own).
+// A block whose atoms span more mesh than fits (a block that wraps a cell row, a dilute system) falls back to
+// direct global atomics.
+constexpr int SPREAD_T = 256;
+constexpr int SPREAD_CAP = 15360;            // ints of dynamic shared memory (60 KB)
+constexpr float SPREAD_SCALE = 67108864.f;   // 2^26; global mesh = 2^40
+
+template <int P>
+__global__ void __launch_bounds__(SPREAD_T)
+k_spread_smem(PmeParams p, const float4 *__restrict__ xs, long long *__restrict__ grid) {
+    extern __shared__ int s_mesh[];
+    __shared__ int s_ref[3], s_lo[3], s_hi[3];
+    const int tid = threadIdx.x;
+    const int i = p.first + blockIdx.x * SPREAD_T + tid;
+    const bool live = i < p.n;
+    float4 a = live ? xs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int k0[3] = {0, 0, 0}; float w[3] = {0.f, 0.f, 0.f};
+    const int mesh[3] = {p.nx, p.ny, p.nz};
+    if (live) {
+        frac_index(a.x, p.invL[0], p.nx, k0[0], w[0]);
+        frac_index(a.y, p.invL[1], p.ny, k0[1], w[1]);
+        frac_index(a.z, p.invL[2], p.nz, k0[2], w[2]);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { s_ref[d] = k0[d]; s_lo[d] = 0; s_hi[d] = 0; }
+    }
+    __syncthreads();
+    const bool use = live && a.w != 0.f;
+    int rel[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {          // index relative to the block's first atom, periodic
+        int r = k0[d] - s_ref[d];
+        const int h = mesh[d] >> 1;
+        if (r > h) r -= mesh[d]; else if (r < -h) r += mesh[d];
+        rel[d] = r;
+        if (use) { atomicMin(&s_lo[d], r); atomicMax(&s_hi[d], r); }
+    }
+    __syncthreads();
+    const int sx = s_hi[0] - s_lo[0] + P, sy = s_hi[1] - s_lo[1] + P, sz = s_hi[2] - s_lo[2] + P;
+    const long long pts = (long long)sx * sy * sz;
+    const bool fits = pts <= SPREAD_CAP && sx <= p.nx && sy <= p.ny && sz <= p.nz;
+    float tx[P], ty[P], tz[P], dd[P];
+    if (use) { bspline<P>(w[0], tx, dd); bspline<P>(w[1], ty, dd); bspline<P>(w[2], tz, dd); }
+    if (!fits) {                            // direct global atomics (uniform branch)
+        if (use) {
+#pragma unroll
+            for (int jx = 0; jx < P; ++jx) {
+                int x = (k0[0] - P + 1 + jx) % p.nx; if (x < 0) x += p.nx;
+#pragma unroll
+                for (int jy = 0; jy < P; ++jy) {
+                    int y = (k0[1] - P + 1 + jy) % p.ny; if (y < 0) y += p.ny;
+                    long long *row = grid + ((size_t)x * p.ny + y) * p.nz;
+#pragma unroll
+                    for (int jz = 0; jz < P; ++jz) {
+                        int z = (k0[2] - P + 1 + jz) % p.nz; if (z < 0) z += p.nz;
+                        atomic_add_fix(row + z, ((long long)__float2int_rn(a.w * tx[jx] * ty[jy] * tz[jz] * SPREAD_SCALE)) << 14);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    for (int k = tid; k < (int)pts; k += SPREAD_T) s_mesh[k] = 0;
+    __syncthreads();
+    if (use) {
+        const int bx = rel[0] - s_lo[0], by = rel[1] - s_lo[1], bz = rel[2] - s_lo[2];   // >= 0: lowest point of the support
+#pragma unroll
+        for (int jx = 0; jx < P; ++jx) {
+            const float qx = a.w * tx[jx];
+#pragma unroll
+            for (int jy = 0; jy < P; ++jy) {
+                const float qxy = qx * ty[jy];
+                int *row = s_mesh + ((bx + jx) * sy + (by + jy)) * sz + bz;
+#pragma unroll
+                for (int jz = 0; jz < P; ++jz) atomicAdd(row + jz, __float2int_rn(qxy * tz[jz] * SPREAD_SCALE));
+            }
+        }
+    }
+    __syncthreads();
+    // lowest mesh index of the sub-mesh on each axis
+    int o[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { int v = (s_ref[d] + s_lo[d] - P + 1) % mesh[d]; o[d] = v < 0 ? v + mesh[d] : v; }
+    for (int k = tid; k < (int)pts; k += SPREAD_T) {
+        const int v = s_mesh[k];
+        if (!v) continue;
+        const int iz = k % sz, iy = (k / sz) % sy, ix = k / (sz * sy);
+        int x = o[0] + ix; if (x >= p.nx) x -= p.nx;
+        int y = o[1] + iy; if (y >= p.ny) y -= p.ny;
+        int z = o[2] + iz; if (z >= p.nz) z -= p.nz;
+        atomic_add_fix(grid + ((size_t)x * p.ny + y) * p.nz + z, ((long long)v) << 14);
+    }
+}
+
 __global__ void k_grid_convert(size_t total, long long *__restrict__ fix, float *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -428,6 +527,13 @@ int pme_prepare(mdk_ctx *c) {
             return fail(c, MDK_ERR_CUDA, "cufftPlan3d(%d,%d,%d) failed", nx, ny, nz);
         c->have_plans = true;
     }
+    {
+        const int smem = SPREAD_CAP * (int)sizeof(int);
+        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
     c->pme_dirty = false;
     return MDK_OK;
 }
@@ -449,6 +555,20 @@ int pme_spread(mdk_ctx *c) {
     PmeParams p = make_pme_params(c);
     const int cnt = p.n - p.first;
     if (cnt <= 0) return MDK_OK;
+    if (c->spread_smem) {
+        const int B = (cnt + SPREAD_T - 1) / SPREAD_T;
+        const size_t smem = SPREAD_CAP * sizeof(int);
+        switch (c->pme_order) {
+            case 4: k_spread_smem<4><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+            case 5: k_spread_smem<5><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+            case 6: k_spread_smem<6><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+            case 8: k_spread_smem<8><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+            default: return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", c->pme_order);
+        }
+        c->n_launches += 1;
+        MDK_CUDA(c, cudaGetLastError());
+        return MDK_OK;
+    }
     const int B = (cnt + 127) / 128;
     switch (c->pme_order) {
         case 4: k_spread<4><<<B, 128, 0, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;

@@ -618,6 +618,57 @@ int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quir
 }
 
 // ===========================================================================
+// Steepest descent (mdpy/minimizer/steepest_descent_minimizer.py:30-53): every atom moves a fixed
+// length alpha along ITS OWN unit force vector, x_i += alpha F_i / |F_i| (the reference normalises per atom,
+// np.linalg.norm(forces, axis=1)); the loop stops when the relative change of the potential energy between two
+// iterations drops under the tolerance.  An atom with zero force stays where it is (the reference would divide 0 / 0).
+__global__ void k_sd_step(int n, double alpha, const int *__restrict__ order, const long long *__restrict__ f_acc,
+                          double *__restrict__ x_cur, StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
+                          int *__restrict__ flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int a = order[k];
+    double f[3], xo[3], xn[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { f[d] = (double)f_acc[3 * (size_t)k + d] * (1.0 / FIX_SCALE); xo[d] = x_cur[3 * a + d]; }
+    const double norm = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    const double s = norm > 0.0 ? alpha / norm : 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { xn[d] = xo[d] + s * f[d]; x_cur[3 * a + d] = xn[d]; }
+    publish_position(k, xn, xo, g, xs, xs_ref, flags);
+}
+
+int minimize_sd(mdk_ctx *c, double alpha, double energy_tolerance, int max_iterations, unsigned terms, int *iterations,
+                double *e_first, double *e_prev, double *e_last) {
+    if (c->dd) return fail(c, MDK_ERR_BAD_ARG, "the steepest-descent minimizer is single domain");
+    const int n = c->n, T = 256, B = (n + T - 1) / T;
+    auto potential = [&]() {
+        double e = 0;
+        for (int k = 0; k < MDK_E_KINETIC; ++k) e += c->last_e[k];
+        return e;
+    };
+    MDK_TRY(compute_terms(c, terms, true));
+    double cur = potential(), pre = cur;
+    *e_first = cur; *e_prev = cur; *e_last = cur;
+    int it = 0;
+    c->verlet_cached = false; c->langevin_cached = false;
+    while (it < max_iterations) {
+        StepGeom g = make_geom(c);
+        k_sd_step<<<B, T, 0, c->stream>>>(n, alpha, c->order.p, c->f_acc.p, c->x_cur.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
+        ++c->n_launches;
+        MDK_TRY(compute_terms(c, terms, true));      // xs was published by the step: no refresh pass; rebuilds when flagged
+        cur = potential();
+        ++it;
+        *e_prev = pre; *e_last = cur;
+        if (!(fabs(cur) < 1e300)) return fail(c, MDK_ERR_PARTICLE_LOST, "steepest descent diverged (non-finite energy)");
+        if (fabs((cur - pre) / pre) < energy_tolerance) break;
+        pre = cur;
+    }
+    *iterations = it;
+    return MDK_OK;
+}
+
+// ===========================================================================
 // CUDA-graph step.  At 23 k atoms a step is ~25 kernels of 3-60 us: issuing them one by one, with a
 // host round trip per step to learn whether the list must be rebuilt, costs more than executing
 // them.  The steady-state Langevin step is therefore captured once into a graph whose rebuild

@@ -370,3 +370,24 @@ def gjf_step(x, v, f_old, force_fn, masses, dt, gamma, kT, seed, step):
     f_new = force_fn(x_new)
     v_new = a * v + 0.5 * dt / m * (a * f_old + f_new) + b / m * beta
     return x_new, v_new, f_new
+
+
+def steepest_descent(positions, box, force_energy_fn, alpha=0.01, energy_tolerance=0.001, max_iterations=1000):
+    """SteepestDescentMinimizer.minimize (mdpy/minimizer/steepest_descent_minimizer.py:30-53) in float64:
+    x_i += alpha F_i / |F_i| per atom (:38-41), wrap, re-evaluate; stop when |E - E_prev| / |E_prev| < tolerance (:44,48).
+    force_energy_fn(wrapped_positions) -> (forces, potential_energy).  Returns (positions, iterations, energies)."""
+    box = np.asarray(box, dtype=np.float64).reshape(3)
+    x = np.asarray(positions, dtype=np.float64)
+    x = x - box * np.round(x / box)
+    f, e = force_energy_fn(x)
+    energies = [e]
+    it = 0
+    while it < max_iterations:
+        x = x + alpha * f / np.linalg.norm(f, axis=1).reshape(-1, 1)
+        x = x - box * np.round(x / box)
+        f, e = force_energy_fn(x)
+        it += 1
+        energies.append(e)
+        if abs((e - energies[-2]) / energies[-2]) < energy_tolerance:
+            break
+    return x, it, energies

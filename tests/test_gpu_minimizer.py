@@ -1,0 +1,62 @@
+"""Device steepest descent against the host restatement of the reference's loop
+(mdpy/minimizer/steepest_descent_minimizer.py:30-53; oracle/cpu_oracle.py:steepest_descent with the float64 oracle
+forces), and the relaxation it is used for: a lattice start of the 23k water box loses its clashes."""
+import numpy as np
+import pytest
+
+import mdpy_b200 as md
+from conftest import load_golden
+from mdpy_b200 import synthetic
+from mdpy_b200.constraint import CharmmNonbondedConstraint, ElectrostaticConstraint
+from mdpy_b200.core import Topology
+from mdpy_b200.minimizer import Minimizer, SteepestDescentMinimizer
+from mdpy_b200.unit import coulomb_constant
+from oracle import cpu_oracle as ora
+
+pytestmark = pytest.mark.gpu
+
+
+def test_steepest_descent_follows_the_reference_iteration(capsys):
+    g = load_golden('mix_small_f64')
+    n = g['positions'].shape[0]
+    topo = Topology.from_tables(['X'] * n, g['masses'], g['charges'], g['bonded'], g['scaling'])
+    ens = md.Ensemble(topo, np.diag(g['box']))
+    ens.add_constraints(CharmmNonbondedConstraint(g['lj_table'], cutoff_radius=float(g['rc'])), ElectrostaticConstraint())
+    x0 = g['positions'].astype(np.float32)
+    ens.state.set_positions(x0)
+    k_e = coulomb_constant()
+
+    def fe(x):
+        t = ora.nonbonded_bruteforce(x, g['box'], g['lj_table'], g['charges'], g['bonded'], g['scaling'], rc_lj=float(g['rc']),
+                                     coul_mode=2, k_e=k_e, threads=8)
+        return t['f_lj'] + t['f_coul'], t['e_lj'] + t['e_coul']
+    iters = 12
+    x_ref, it_ref, e_ref = ora.steepest_descent(x0.astype(np.float64), g['box'], fe, alpha=0.01, energy_tolerance=0.0, max_iterations=iters)
+    m = SteepestDescentMinimizer(alpha=0.01)
+    assert isinstance(m, Minimizer)
+    m.minimize(ens, energy_tolerance=0.0, max_iterations=iters)
+    out = capsys.readouterr().out
+    assert 'Start energy minimization with steepest decent method' in out and 'Final potential energy' in out
+    assert m.num_iterations == it_ref == iters
+    d = ens.state.positions.astype(np.float64) - x_ref
+    d -= g['box'] * np.round(d / g['box'])
+    # every atom moved 12 x 0.01 A along unit vectors the device knows to ~1e-6: float32 output rounding dominates
+    assert np.abs(d).max() < 2e-5 and np.sqrt((d ** 2).mean()) < 3e-6
+    assert ens.potential_energy == pytest.approx(e_ref[-1], rel=1e-5)
+    assert e_ref[-1] < e_ref[0]
+    # the stopping rule: relative energy change under the tolerance (steepest_descent_minimizer.py:44-52)
+    ens.state.set_positions(x0)
+    _, it_tol, _ = ora.steepest_descent(x0.astype(np.float64), g['box'], fe, alpha=0.01, energy_tolerance=2e-3, max_iterations=60)
+    m.minimize(ens, energy_tolerance=2e-3, max_iterations=60)
+    assert m.num_iterations == it_tol < 60
+
+
+def test_steepest_descent_relaxes_the_lattice_start_of_the_water_box():
+    s = synthetic.CONFIGS['water_23k']()
+    ens = s.ensemble(cutoff=9.0, pme=True, grid=(64, 64, 64))
+    ens.update()
+    e0 = ens.potential_energy
+    SteepestDescentMinimizer(alpha=0.01).minimize(ens, energy_tolerance=1e-4, max_iterations=150)
+    assert ens.potential_energy < e0 - 0.05 * abs(e0)
+    ens.update()          # the State that came back is the relaxed configuration
+    assert np.isfinite(ens.potential_energy)

@@ -113,6 +113,14 @@ MDK_API int mdk_set_nlist(mdk_ctx *ctx, float skin);
 MDK_API int mdk_set_bonded(mdk_ctx *ctx, int kind /* 0 bond 1 angle 2 dihedral 3 improper */, int n,
                    const int32_t *idx, const float *par);
 
+/* Rigid three-site waters — what the reference's is_SHAKE flag asks for (forcefield/charmm_forcefield.py:24,32; the
+ * reference itself has no constraint code).  triplets int32 [n,3] = (O, H, H) matrix ids, all molecules with the same
+ * masses; d_oh / d_hh = the constrained O-H and H-H distances.  The Langevin step then integrates these molecules with
+ * SETTLE (positions) + a RATTLE velocity projection fused into the position / velocity update; their bond / angle terms
+ * must not be passed to mdk_set_bonded.  Positions that come from outside are projected onto the rigid geometry before
+ * the next step call.  n_waters = 0 switches the constraints off.  Single domain only. */
+MDK_API int mdk_set_rigid_waters(mdk_ctx *ctx, int n_waters, const int32_t *triplets, double d_oh, double d_hh);
+
 /* ---- state ---- */
 /* State.set_positions (state.py:56-61): wraps into [-L/2, L/2] (utils/pbc.py:28-36; an
  * atom >= 2 images away -> MDK_ERR_PARTICLE_LOST) and marks the tile list for a

@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -95,6 +95,7 @@ def load_library():
         'mdk_dd_compute_group': (i32, [vp, i32, C.c_uint, vp]),
         'mdk_dd_step_langevin_group': (i32, [vp, i32, f64, f64, f64, u64, i32, C.c_uint, vp]),
         'mdk_dd_stats': (i32, [vp, vp]),
+        'mdk_set_rigid_waters': (i32, [vp, i32, vp, f64, f64]),
         'mdk_minimize_sd': (i32, [vp, f64, f64, i32, C.c_uint, C.POINTER(i32), vp, vp]),
         'mdk_comm_unique_id': (i32, [vp]),
         'mdk_comm_init': (i32, [vp, i32, i32, vp]),
@@ -187,6 +188,14 @@ class Device:
     def set_bonded(self, kind, idx, par):
         idx = np.ascontiguousarray(idx, dtype=np.int32); par = np.ascontiguousarray(par, dtype=np.float32)
         self._ck(self._lib.mdk_set_bonded(self._h, int(kind), idx.shape[0], _ptr(idx), _ptr(par)))
+
+    def set_rigid_waters(self, triplets, d_oh, d_hh):
+        """mdk_set_rigid_waters: (O, H, H) matrix-id triplets [n,3]; None / empty switches the constraints off."""
+        if triplets is None or len(triplets) == 0:
+            self._ck(self._lib.mdk_set_rigid_waters(self._h, 0, None, 0.0, 0.0))
+            return
+        t = np.ascontiguousarray(triplets, dtype=np.int32).reshape(-1, 3)
+        self._ck(self._lib.mdk_set_rigid_waters(self._h, t.shape[0], _ptr(t), float(d_oh), float(d_hh)))
 
     def set_stream(self, cuda_stream):
         self._ck(self._lib.mdk_set_stream(self._h, C.c_void_p(int(cuda_stream))))

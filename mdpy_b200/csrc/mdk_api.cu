@@ -235,6 +235,7 @@ void mdk_destroy(mdk_ctx *c) {
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
     c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release(); c->excl_pairs.release();
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
+    c->rigid_trip.release(); c->rigid_flag.release();
     c->x_cur.release(); c->x_prev.release(); c->vel.release(); c->f_prev.release();
     c->order.release(); c->inv_order.release(); c->xs.release(); c->xs_ref.release(); c->ljs.release();
     c->excl_s.release(); c->p14_s.release(); c->f_acc.release(); c->readback.release();
@@ -406,6 +407,41 @@ int mdk_set_bonded(mdk_ctx *c, int kind, int n, const int32_t *idx, const float 
     return MDK_OK;
 }
 
+int mdk_set_rigid_waters(mdk_ctx *c, int n_waters, const int32_t *triplets, double d_oh, double d_hh) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_set_rigid_waters before mdk_set_atoms");
+    if (n_waters < 0 || (n_waters > 0 && (!triplets || !(d_oh > 0) || !(d_hh > 0) || d_hh >= 2 * d_oh)))
+        return fail(c, MDK_ERR_BAD_ARG, "mdk_set_rigid_waters: n=%d d_oh=%g d_hh=%g", n_waters, d_oh, d_hh);
+    c->n_rigid = 0;
+    c->verlet_cached = false; c->langevin_cached = false;
+    ++c->graph_epoch;              // the water kernel is (or is no longer) part of the captured step
+    if (n_waters == 0) return MDK_OK;
+    std::vector<float> mass(c->n);
+    MDK_CUDA(c, cudaMemcpy(mass.data(), c->mass.p, c->n * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> flag(c->n, 0);
+    for (int w = 0; w < n_waters; ++w) {
+        for (int t = 0; t < 3; ++t) {
+            const int a = triplets[3 * w + t];
+            if (a < 0 || a >= c->n || flag[a]) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_rigid_waters: atom %d out of range or in two molecules", a);
+            flag[a] = 1;
+        }
+        // one geometry for all molecules: same oxygen / hydrogen masses everywhere
+        const int o = triplets[3 * w], h1 = triplets[3 * w + 1], h2 = triplets[3 * w + 2];
+        if (mass[o] != mass[triplets[0]] || mass[h1] != mass[triplets[1]] || mass[h2] != mass[triplets[1]])
+            return fail(c, MDK_ERR_BAD_ARG, "mdk_set_rigid_waters: molecule %d has other masses than molecule 0", w);
+    }
+    MDK_CUDA(c, c->rigid_trip.reserve((size_t)3 * n_waters));
+    MDK_CUDA(c, c->rigid_flag.reserve(c->n));
+    MDK_CUDA(c, cudaMemcpy(c->rigid_trip.p, triplets, (size_t)3 * n_waters * sizeof(int), cudaMemcpyHostToDevice));
+    MDK_CUDA(c, cudaMemcpy(c->rigid_flag.p, flag.data(), c->n, cudaMemcpyHostToDevice));
+    c->rigid_d_oh = d_oh; c->rigid_d_hh = d_hh;
+    c->rigid_m_o = mass[triplets[0]]; c->rigid_m_h = mass[triplets[1]];
+    c->n_rigid = n_waters;
+    c->rigid_dirty = true;         // the geometry is projected onto the constraints before the next step call
+    return MDK_OK;
+}
+
 // ---- state ----
 static int check_lost(mdk_ctx *c, const double *x, const float *xf) {
     // utils/pbc.py:29-34: |round(x / L)| >= 2 on any axis
@@ -434,6 +470,7 @@ int mdk_upload_positions(mdk_ctx *c, const float *xyz) {
     c->have_pos = true;
     c->xs_current = false;
     c->verlet_cached = false; c->langevin_cached = false;
+    c->rigid_dirty = true;
     return MDK_OK;
 }
 
@@ -447,6 +484,7 @@ int mdk_upload_positions_f64(mdk_ctx *c, const double *xyz) {
     c->have_pos = true;
     c->xs_current = false;
     c->verlet_cached = false; c->langevin_cached = false;
+    c->rigid_dirty = true;
     return MDK_OK;
 }
 
@@ -550,6 +588,7 @@ int mdk_step_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t s
     cudaSetDevice(c->device);
     if (!(dt > 0) || kT < 0 || gamma < 0) return fail(c, MDK_ERR_BAD_ARG, "mdk_step_langevin: dt=%g kT=%g gamma=%g", dt, kT, gamma);
     prepare_pme_constants(c);
+    if (c->rigid_dirty && c->n_rigid > 0 && c->have_pos) { MDK_TRY(rigid_project(c)); c->rigid_dirty = false; }
     if (c->profiling) { for (auto &p : c->phase_ms) p = 0; cudaEventRecord(c->ev[2 * PH_TOTAL], c->stream); }
     MDK_TRY(integrate_langevin(c, dt, kT, gamma, seed, nsteps, terms, 5, false));
     if (c->profiling) {
@@ -685,8 +724,10 @@ int mdk_step_langevin_host(mdk_ctx *c, const float *x_in, const float *v_in, flo
                 c->have_pos = true;
                 c->xs_current = false;
                 c->verlet_cached = false; c->langevin_cached = false;
+                c->rigid_dirty = true;
             }
         }
+        if (c->rigid_dirty && c->n_rigid > 0 && c->have_pos && !ahead) { MDK_TRY(rigid_project(c)); c->rigid_dirty = false; }
         if (nsteps > 0) MDK_TRY(integrate_langevin(c, dt, kT, gamma, seed, nsteps, terms, 1, true));
         MDK_TRY(host_state_out(c, x_out, v_out, m, &px, &pv));
         if (c->profiling) cudaEventRecord(c->ev[2 * PH_TOTAL + 1], c->stream);

@@ -108,6 +108,12 @@ struct mdk_ctx {
     bool have_coul = false;
     float skin = 2.0f;
     mdk::BondedSet bonded[4];
+    // rigid three-site waters (SETTLE): triplets (O, H, H) of matrix ids, a flag per atom for the free-atom kernel
+    mdk::DevBuf<int> rigid_trip;
+    mdk::DevBuf<unsigned char> rigid_flag;
+    int n_rigid = 0;
+    double rigid_d_oh = 0, rigid_d_hh = 0, rigid_m_o = 0, rigid_m_h = 0;
+    bool rigid_dirty = false;                 // positions came from outside since the last projection onto the constraints
 
     // ---- state (matrix_id order) ----
     mdk::DevBuf<double> x_cur, x_prev, vel;   // [n,3] unwrapped fp64 positions / velocities
@@ -263,7 +269,6 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph);  // device work of a rebuild only 
 int nlist_ensure(mdk_ctx *c);                  // rebuild if flagged / invalid
 NlistView nlist_view(mdk_ctx *c);
 int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul);
-int pair_special(mdk_ctx *c, bool pme_excl);   // excluded-pair erf correction
 int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out, int production);
 int coulomb_bare(mdk_ctx *c);
 int pme_prepare(mdk_ctx *c);
@@ -275,7 +280,7 @@ inline int pme_first(const mdk_ctx *c) { return c->pme_hi < 0 ? 0 : c->pme_lo; }
 inline int pme_end(const mdk_ctx *c) { return c->pme_hi < 0 ? c->n : c->pme_hi; }
 inline int own_first(const mdk_ctx *c) { return c->own_hi < 0 ? 0 : c->own_lo; }
 inline int own_end(const mdk_ctx *c) { return c->own_hi < 0 ? c->n : (c->own_hi < c->n ? c->own_hi : c->n); }
-int bonded_compute(mdk_ctx *c, unsigned terms);
+int bonded_compute(mdk_ctx *c, unsigned terms);   // bonded terms + (with PME_RECIP) the excluded-pair Ewald correction, one launch
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks);
 int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t seed, int nsteps, unsigned terms,
                        int graph_min_steps, bool defer_energies);
@@ -298,6 +303,7 @@ int dd_langevin_single(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
 void dd_destroy(mdk_ctx *c);
 int langevin_launch(mdk_ctx *c, int first, int end, int mode, double dt, double ca, double cb, double tg, uint64_t seed, uint64_t step);
 void prepare_pme_constants(mdk_ctx *c);
+int rigid_project(mdk_ctx *c);
 
 // ---------------------------------------------------------------------------
 // device helpers

@@ -463,9 +463,7 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
             MDK_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
             MDK_CUDA(c, cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
             c->stream = c->s_aux;
-            int rc = MDK_OK;
-            if (pme) rc = pair_special(c, true);
-            if (rc == MDK_OK && bonded_bits) rc = bonded_compute(c, terms);
+            int rc = bonded_compute(c, terms);
             cudaEventRecord(c->ev_aux, c->s_aux);
             c->stream = main_stream;
             MDK_TRY(rc);
@@ -623,6 +621,8 @@ static int dd_langevin_group(Group &g, double dt, double kT, double gamma, uint6
     if (nsteps <= 0) return MDK_OK;
     const double ca = (1.0 - 0.5 * gamma * dt) / (1.0 + 0.5 * gamma * dt), cb = 1.0 / (1.0 + 0.5 * gamma * dt);
     const double tg = 2.0 * gamma * kT * dt;
+    for (mdk_ctx *c : g)
+        if (c->n_rigid > 0) return fail(c, MDK_ERR_BAD_ARG, "rigid waters are single domain (a molecule's atoms may belong to two ranks)");
     for (mdk_ctx *c : g) {
         each_set_device(c);
         MDK_CUDA(c, c->f_prev.reserve((size_t)3 * c->n));

@@ -356,55 +356,6 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
 }
 
 // ---------------------------------------------------------------------------
-// Excluded-pair Ewald correction: the reciprocal sum contains every pair, also the
-// bonded ones the direct sum skips; remove -k_e q_i q_j erf(alpha r)/r for each of them.
-// One thread per excluded pair (a < b, matrix ids; the compact list mdk_set_exclusions builds from the
-// -1-padded bonded_particles table); the pair belongs to the rank that owns atom a.
-__global__ void k_excl_correction(int n_pairs, const int2 *__restrict__ pairs, const int *__restrict__ inv_order,
-                                  int own_lo, int own_hi, const float4 *__restrict__ xs, double Lx, double Ly, double Lz,
-                                  double alpha, long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    double e = 0.0;
-    if (t < n_pairs) {
-        const int2 pr = pairs[t];
-        const int k = inv_order[pr.x];
-        if (k >= own_lo && k < own_hi) {
-            const int p = inv_order[pr.y];
-            float4 a = xs[k], b = xs[p];
-            double d[3] = {(double)b.x - a.x, (double)b.y - a.y, (double)b.z - a.z};
-            d[0] -= Lx * rint(d[0] / Lx); d[1] -= Ly * rint(d[1] / Ly); d[2] -= Lz * rint(d[2] / Lz);
-            double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-            double r = sqrt(r2);
-            double qq = (double)a.w * (double)b.w;
-            double ar = alpha * r;
-            double erf_ar = erf(ar);
-            e = -qq * erf_ar / r;
-            // dE/dr = -qq (2 alpha/sqrt(pi) exp(-a^2 r^2)/r - erf/r^2);  F_i = dE/dr d/r
-            double g = -qq * (1.1283791670955126 * alpha * exp(-ar * ar) / r - erf_ar / r2) / r;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                atomic_add_fix(&f_acc[3 * (size_t)k + x], to_fix(g * d[x]));
-                atomic_add_fix(&f_acc[3 * (size_t)p + x], to_fix(-g * d[x]));
-            }
-        }
-    }
-    const long long v = warp_sum_ll(to_fix(e));   // per-pair fixed point: independent of the rank split
-    if ((threadIdx.x & 31) == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_PME_EXCL], v);
-}
-
-int pair_special(mdk_ctx *c, bool pme_excl) {
-    if (!pme_excl || c->n_excl_pairs <= 0) return MDK_OK;
-    PhaseTimer pt(c, PH_BONDED);
-    const int lo = own_first(c), hi = c->own_hi < 0 ? c->n_pad : c->own_hi;
-    k_excl_correction<<<(c->n_excl_pairs + 255) / 256, 256, 0, c->stream>>>(
-        c->n_excl_pairs, c->excl_pairs.p, c->inv_order.p, lo, hi, c->xs.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->alpha, c->f_acc.p,
-        reinterpret_cast<long long *>(c->e_acc.p));
-    ++c->n_launches;
-    MDK_CUDA(c, cudaGetLastError());
-    return MDK_OK;
-}
-
-// ---------------------------------------------------------------------------
 // Test hook: walk the tile list exactly like k_pair and emit every pair that passes the
 // canonical cutoff test and is not masked.
 __global__ void k_enumerate(PairParams P, NlistView nl, const float4 *__restrict__ xs,

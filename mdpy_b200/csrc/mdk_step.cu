@@ -131,10 +131,8 @@ __device__ __forceinline__ void block_energy(double e, long long *e_acc, int whi
 // E = k (r - r0)^2   (charmm_bond_constraint.py:53-73)
 // A term belongs to the rank that owns its first atom (tile slot in [own_lo, own_hi)); every rank walks the whole
 // term list and skips the others' terms.
-__global__ void k_bonds(int own_lo, int own_hi, int nb, const int *__restrict__ idx, const float *__restrict__ par,
-                        const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
-                        long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double term_bond(int t, int own_lo, int own_hi, int nb, const int *__restrict__ idx, const float *__restrict__ par,
+        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s1 = t < nb ? inv_order[idx[2 * t]] : -1;
     if (s1 >= own_lo && s1 < own_hi) {
@@ -148,14 +146,12 @@ __global__ void k_bonds(int own_lo, int own_hi, int nb, const int *__restrict__ 
         add_force(f_acc, s1, f);
         add_force(f_acc, s2, -1. * f);
     }
-    block_energy(e, e_acc, MDK_E_BOND);
+    return e;
 }
 
 // E = k (theta - theta0)^2 + k_ub (r13 - r_ub)^2   (charmm_angle_constraint.py:55-96)
-__global__ void k_angles(int own_lo, int own_hi, int na, const int *__restrict__ idx, const float *__restrict__ par,
-                         const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
-                         long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double term_angle(int t, int own_lo, int own_hi, int na, const int *__restrict__ idx, const float *__restrict__ par,
+        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s1 = t < na ? inv_order[idx[3 * t]] : -1;
     if (s1 >= own_lo && s1 < own_hi) {
@@ -187,7 +183,7 @@ __global__ void k_angles(int own_lo, int own_hi, int na, const int *__restrict__
         add_force(f_acc, s1, f1);
         add_force(f_acc, s3, f3);
     }
-    block_energy(e, e_acc, MDK_E_ANGLE);
+    return e;
 }
 
 // Torsion geometry shared by dihedrals and impropers: phi by the reference's atan2
@@ -211,10 +207,8 @@ __device__ __forceinline__ double torsion(float4 p1, float4 p2, float4 p3, float
 
 // E = k (1 + cos(n phi - delta))   (charmm_dihedral_constraint.py:59-95; the force is the
 // analytic gradient of this energy — the reference's `-k (1 - n sin(..))` at :80 is not).
-__global__ void k_dihedrals(int own_lo, int own_hi, int nd, const int *__restrict__ idx, const float *__restrict__ par,
-                            const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
-                            long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double term_dihedral(int t, int own_lo, int own_hi, int nd, const int *__restrict__ idx, const float *__restrict__ par,
+        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s0 = t < nd ? inv_order[idx[4 * t]] : -1;
     if (s0 >= own_lo && s0 < own_hi) {
@@ -231,14 +225,12 @@ __global__ void k_dihedrals(int own_lo, int own_hi, int nd, const int *__restric
         add_force(f_acc, s[2], (-dEdphi) * g3);
         add_force(f_acc, s[3], (-dEdphi) * g4);
     }
-    block_energy(e, e_acc, MDK_E_DIHEDRAL);
+    return e;
 }
 
 // E = k (psi - psi0)^2   (charmm_improper_constraint.py:57-94)
-__global__ void k_impropers(int own_lo, int own_hi, int ni, const int *__restrict__ idx, const float *__restrict__ par,
-                            const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
-                            long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double term_improper(int t, int own_lo, int own_hi, int ni, const int *__restrict__ idx, const float *__restrict__ par,
+        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s0 = t < ni ? inv_order[idx[4 * t]] : -1;
     if (s0 >= own_lo && s0 < own_hi) {
@@ -255,28 +247,99 @@ __global__ void k_impropers(int own_lo, int own_hi, int ni, const int *__restric
         add_force(f_acc, s[2], (-dE) * g3);
         add_force(f_acc, s[3], (-dE) * g4);
     }
-    block_energy(e, e_acc, MDK_E_IMPROPER);
+    return e;
 }
 
+// erf for the small arguments of bonded neighbours (alpha r < 1.6): the Maclaurin series, 26 terms to 1e-16
+__device__ __forceinline__ double erf_small(double x) {
+    if (x > 1.6) return erf(x);
+    const double y = x * x;
+    double term = 1.0, sum = 1.0;
+#pragma unroll
+    for (int n = 1; n <= 26; ++n) {
+        term *= -y / n;
+        sum += term / (2 * n + 1);
+    }
+    return 1.1283791670955126 * x * sum;
+}
+
+// Excluded-pair Ewald correction: the reciprocal sum contains every pair, also the bonded ones the direct sum
+// skips; remove -k_e q_i q_j erf(alpha r)/r for each of them.  One thread per excluded pair (a < b, matrix ids; the
+// compact list mdk_set_exclusions builds from the -1-padded bonded_particles table); owner = the owner of atom a.
+__device__ __forceinline__ double term_excl(int t, int own_lo, int own_hi, int n_pairs, const int2 *__restrict__ pairs,
+                                            const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx,
+                                            double alpha, long long *__restrict__ f_acc) {
+    if (t >= n_pairs) return 0.0;
+    const int2 pr = pairs[t];
+    const int k = inv_order[pr.x];
+    if (k < own_lo || k >= own_hi) return 0.0;
+    const int p = inv_order[pr.y];
+    const float4 a = xs[k], b = xs[p];
+    const V3 d = mi_vec(a, b, bx);
+    const double r2 = dot(d, d), r = sqrt(r2);
+    const double qq = (double)a.w * (double)b.w;
+    const double ar = alpha * r, erf_ar = erf_small(ar);
+    // dE/dr = -qq (2 alpha/sqrt(pi) exp(-a^2 r^2)/r - erf/r^2);  F_i = dE/dr d/r
+    const double g = -qq * (1.1283791670955126 * alpha * exp(-ar * ar) / r - erf_ar / r2) / r;
+    add_force(f_acc, k, g * d);
+    add_force(f_acc, p, (-g) * d);
+    return -qq * erf_ar / r;
+}
+
+// All O(N) terms of a force evaluation in ONE launch: the blocks are dealt to the term kinds (bonds, angles, dihedrals,
+// impropers, excluded-pair corrections) by ranges, a block handles one kind.  At 23k atoms five separate launches of
+// ~5 us each were pure launch latency on the step's critical path.
+struct AuxTable {
+    int n[5];                // terms of each kind (0 = kind not requested)
+    int blk_off[6];          // first block of each kind
+    const int *idx[4];
+    const float *par[4];
+    const int2 *pairs;
+};
+constexpr int AUX_T = 128;
+
+__global__ void __launch_bounds__(AUX_T)
+k_aux_terms(AuxTable tb, int own_lo, int own_hi, const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
+            double alpha, long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
+    int kind = 0;
+    while (kind < 4 && (int)blockIdx.x >= tb.blk_off[kind + 1]) ++kind;
+    const int t = ((int)blockIdx.x - tb.blk_off[kind]) * AUX_T + threadIdx.x;
+    double e = 0.0;
+    int slot = MDK_E_BOND;
+    switch (kind) {
+        case 0: e = term_bond(t, own_lo, own_hi, tb.n[0], tb.idx[0], tb.par[0], inv_order, xs, bx, f_acc); slot = MDK_E_BOND; break;
+        case 1: e = term_angle(t, own_lo, own_hi, tb.n[1], tb.idx[1], tb.par[1], inv_order, xs, bx, f_acc); slot = MDK_E_ANGLE; break;
+        case 2: e = term_dihedral(t, own_lo, own_hi, tb.n[2], tb.idx[2], tb.par[2], inv_order, xs, bx, f_acc); slot = MDK_E_DIHEDRAL; break;
+        case 3: e = term_improper(t, own_lo, own_hi, tb.n[3], tb.idx[3], tb.par[3], inv_order, xs, bx, f_acc); slot = MDK_E_IMPROPER; break;
+        default: e = term_excl(t, own_lo, own_hi, tb.n[4], tb.pairs, inv_order, xs, bx, alpha, f_acc); slot = MDK_E_PME_EXCL; break;
+    }
+    block_energy(e, e_acc, slot);
+}
+
+// bonded terms of `terms` + (with MDK_TERM_PME_RECIP) the excluded-pair Ewald correction, own terms only
 int bonded_compute(mdk_ctx *c, unsigned terms) {
     BoxF bx;
     for (int a = 0; a < 3; ++a) bx.L[a] = c->box.Ld[a];
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
     PhaseTimer pt(c, PH_BONDED);
-    const int T = 128;
-    const int lo = own_first(c), hi = c->own_hi < 0 ? c->n_pad : c->own_hi;
-#define BONDED(kind, bit, kernel)                                                                              \
-    if ((terms & (bit)) && c->bonded[kind].n > 0) {                                                            \
-        const int nt = c->bonded[kind].n;                                                                      \
-        kernel<<<(nt + T - 1) / T, T, 0, c->stream>>>(lo, hi, nt, c->bonded[kind].idx.p, c->bonded[kind].par.p, \
-                                                      c->inv_order.p, c->xs.p, bx, c->f_acc.p, e_acc);         \
-        ++c->n_launches;                                                                                       \
+    static const unsigned bit[4] = {MDK_TERM_BOND, MDK_TERM_ANGLE, MDK_TERM_DIHEDRAL, MDK_TERM_IMPROPER};
+    AuxTable tb{};
+    int blocks = 0;
+    for (int k = 0; k < 4; ++k) {
+        tb.n[k] = (terms & bit[k]) ? c->bonded[k].n : 0;
+        tb.idx[k] = c->bonded[k].idx.p; tb.par[k] = c->bonded[k].par.p;
+        tb.blk_off[k] = blocks;
+        blocks += (tb.n[k] + AUX_T - 1) / AUX_T;
     }
-    BONDED(0, MDK_TERM_BOND, k_bonds)
-    BONDED(1, MDK_TERM_ANGLE, k_angles)
-    BONDED(2, MDK_TERM_DIHEDRAL, k_dihedrals)
-    BONDED(3, MDK_TERM_IMPROPER, k_impropers)
-#undef BONDED
+    tb.n[4] = (terms & MDK_TERM_PME_RECIP) ? c->n_excl_pairs : 0;
+    tb.pairs = c->excl_pairs.p;
+    tb.blk_off[4] = blocks;
+    blocks += (tb.n[4] + AUX_T - 1) / AUX_T;
+    tb.blk_off[5] = blocks;
+    if (blocks == 0) return MDK_OK;
+    const int lo = own_first(c), hi = c->own_hi < 0 ? c->n_pad : c->own_hi;
+    k_aux_terms<<<blocks, AUX_T, 0, c->stream>>>(tb, lo, hi, c->inv_order.p, c->xs.p, bx, c->alpha, c->f_acc.p, e_acc);
+    ++c->n_launches;
     MDK_CUDA(c, cudaGetLastError());
     return MDK_OK;
 }
@@ -312,9 +375,8 @@ int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry) {
     if (want_aux) {
         if (fork) { MDK_CUDA(c, cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); c->stream = c->s_aux; }
         int rc = MDK_OK;
-        if (terms & MDK_TERM_PME_RECIP) rc = pair_special(c, true);
-        if (rc == MDK_OK && first && (terms & MDK_TERM_COUL_BARE)) rc = coulomb_bare(c);
-        if (rc == MDK_OK && bonded_bits) rc = bonded_compute(c, terms);
+        if (first && (terms & MDK_TERM_COUL_BARE)) rc = coulomb_bare(c);
+        if (rc == MDK_OK && (bonded_bits || (terms & MDK_TERM_PME_RECIP))) rc = bonded_compute(c, terms);
         if (fork) { cudaEventRecord(c->ev_aux, c->s_aux); c->stream = main_stream; }
         MDK_TRY(rc);
     }
@@ -460,9 +522,10 @@ __global__ void k_langevin(int first, int n, int mode, double dt, double ca, dou
                            const float *__restrict__ mass, long long *__restrict__ f_acc,
                            double *__restrict__ x_cur, double *__restrict__ vel, double *__restrict__ f_prev,
                            StepGeom g, float4 *__restrict__ xs, const float4 *__restrict__ xs_ref,
-                           int *__restrict__ flags) {
+                           int *__restrict__ flags, const unsigned char *__restrict__ rigid) {
     int k = first + blockIdx.x * blockDim.x + threadIdx.x;   // tile slots [first, n): the atoms this rank owns
     if (k >= n) return;
+    if (rigid && rigid[order[k]]) return;                    // atoms of rigid waters: k_langevin_water
     // a host-state call that ran ahead of its own change check (mdk_step_langevin_host): the host
     // positions turned out to differ from the device's, the cached force is stale — leave the state alone
     if (flags[4] | flags[0]) return;
@@ -510,6 +573,217 @@ __global__ void k_langevin(int first, int n, int mode, double dt, double ca, dou
     }
 }
 
+// ---------------------------------------------------------------------------
+// Rigid three-site waters (the reference only carries the flag is_SHAKE,
+// forcefield/charmm_forcefield.py:24,32): the same G-JF update as k_langevin for the three atoms of one molecule,
+// with the constraints applied analytically — SETTLE (Miyamoto & Kollman 1992) resets the positions after the
+// unconstrained move, and the velocities are projected onto the constraint surface (RATTLE's velocity stage).
+// The displacement SETTLE applies, dx = x_c - x_unconstrained, is the constraint force's share b dt^2/(2m) g of the
+// position update; the same g enters the next velocity update as dt/(2m) a g = a dx / (b dt), which is added to the
+// stored velocity right here (the finish stage multiplies it by a), and the projection after the finish stage
+// supplies the constraint force at the new positions.
+struct WaterGeom { double d_oh, d_hh, m_o, m_h; };
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void unit3(double a[3]) {
+    const double s = rsqrt(dot3(a, a));
+    a[0] *= s; a[1] *= s; a[2] *= s;
+}
+
+// b: constrained positions at the start of the step, c: after the unconstrained update -> c is overwritten
+__device__ void settle_positions(const double b[3][3], double c[3][3], const WaterGeom &w) {
+    const double wohh = w.m_o + 2.0 * w.m_h, rc = 0.5 * w.d_hh;
+    const double t = sqrt(w.d_oh * w.d_oh - rc * rc);
+    const double ra = 2.0 * w.m_h * t / wohh, rb = t - ra;
+    double com[3], xb0[3], xc0[3], xa1[3], xb1[3], xc1[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        com[d] = (w.m_o * c[0][d] + w.m_h * (c[1][d] + c[2][d])) / wohh;
+        xb0[d] = b[1][d] - b[0][d]; xc0[d] = b[2][d] - b[0][d];
+        xa1[d] = c[0][d] - com[d]; xb1[d] = c[1][d] - com[d]; xc1[d] = c[2][d] - com[d];
+    }
+    double xax[3], yax[3], zax[3];
+    cross3(xb0, xc0, zax); cross3(xa1, zax, xax); cross3(zax, xax, yax);
+    unit3(xax); unit3(yax); unit3(zax);
+    const double b0x = dot3(xb0, xax), b0y = dot3(xb0, yax), c0x = dot3(xc0, xax), c0y = dot3(xc0, yax);
+    const double a1z = dot3(xa1, zax);
+    const double b1x = dot3(xb1, xax), b1y = dot3(xb1, yax), b1z = dot3(xb1, zax);
+    const double c1x = dot3(xc1, xax), c1y = dot3(xc1, yax), c1z = dot3(xc1, zax);
+    const double sinphi = a1z / ra, cosphi = sqrt(1.0 - sinphi * sinphi);
+    const double sinpsi = (b1z - c1z) / (2.0 * rc * cosphi), cospsi = sqrt(1.0 - sinpsi * sinpsi);
+    const double a2y = ra * cosphi, b2x = -rc * cospsi, t1 = -rb * cosphi, t2 = rc * sinpsi * sinphi;
+    const double b2y = t1 - t2, c2y = t1 + t2;
+    const double alpa = b2x * (b0x - c0x) + b0y * b2y + c0y * c2y;
+    const double beta = b2x * (c0y - b0y) + b0x * b2y + c0x * c2y;
+    const double gama = b0x * b1y - b1x * b0y + c0x * c1y - c1x * c0y;
+    const double al2be2 = alpa * alpa + beta * beta;
+    const double sinthe = (alpa * gama - beta * sqrt(al2be2 - gama * gama)) / al2be2, costhe = sqrt(1.0 - sinthe * sinthe);
+    const double a3[3] = {-a2y * sinthe, a2y * costhe, a1z};
+    const double b3[3] = {b2x * costhe - b2y * sinthe, b2x * sinthe + b2y * costhe, b1z};
+    const double c3[3] = {-b2x * costhe - c2y * sinthe, -b2x * sinthe + c2y * costhe, c1z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        c[0][d] = com[d] + a3[0] * xax[d] + a3[1] * yax[d] + a3[2] * zax[d];
+        c[1][d] = com[d] + b3[0] * xax[d] + b3[1] * yax[d] + b3[2] * zax[d];
+        c[2][d] = com[d] + c3[0] * xax[d] + c3[1] * yax[d] + c3[2] * zax[d];
+    }
+}
+
+// remove the velocity components along the three bonds with impulses along the bonds (3 x 3 system, Cramer)
+__device__ void rattle_velocities(const double x[3][3], double v[3][3], const WaterGeom &w) {
+    const double im[3] = {1.0 / w.m_o, 1.0 / w.m_h, 1.0 / w.m_h};
+    const int pi[3] = {0, 0, 1}, pj[3] = {1, 2, 2};
+    double e[3][3], A[3][3], rhs[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) e[k][d] = x[pj[k]][d] - x[pi[k]][d];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double dv[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dv[d] = v[pj[k]][d] - v[pi[k]][d];
+        rhs[k] = -dot3(dv, e[k]);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            // impulse lam_l along e_l: v_p += im_p lam e_l, v_q -= im_q lam e_l (p = pi[l], q = pj[l])
+            double coef = 0.0;
+            const double ee = dot3(e[l], e[k]);
+            if (pi[l] == pj[k]) coef += im[pi[l]] * ee;
+            if (pi[l] == pi[k]) coef -= im[pi[l]] * ee;
+            if (pj[l] == pj[k]) coef -= im[pj[l]] * ee;
+            if (pj[l] == pi[k]) coef += im[pj[l]] * ee;
+            A[k][l] = coef;
+        }
+    }
+    const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    const double l0 = (rhs[0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (rhs[1] * A[2][2] - A[1][2] * rhs[2]) +
+                       A[0][2] * (rhs[1] * A[2][1] - A[1][1] * rhs[2])) / det;
+    const double l1 = (A[0][0] * (rhs[1] * A[2][2] - A[1][2] * rhs[2]) - rhs[0] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * rhs[2] - rhs[1] * A[2][0])) / det;
+    const double l2 = (A[0][0] * (A[1][1] * rhs[2] - rhs[1] * A[2][1]) - A[0][1] * (A[1][0] * rhs[2] - rhs[1] * A[2][0]) +
+                       rhs[0] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) / det;
+    const double lam[3] = {l0, l1, l2};
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { v[pi[l]][d] += im[pi[l]] * lam[l] * e[l][d]; v[pj[l]][d] -= im[pj[l]] * lam[l] * e[l][d]; }
+}
+
+// mode as k_langevin; mode bit 3 (8): only project the current positions onto the rigid geometry and the velocities onto
+// the constraint surface (called once when the constraints are switched on)
+__global__ void k_langevin_water(int nw, const int *__restrict__ trip, int mode, double dt, double ca, double cb, double two_g_kT_dt,
+                                 uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_dev,
+                                 const unsigned long long *__restrict__ mode_dev, const int *__restrict__ inv_order,
+                                 long long *__restrict__ f_acc, double *__restrict__ x_cur, double *__restrict__ vel,
+                                 double *__restrict__ f_prev, StepGeom g, WaterGeom wg, float4 *__restrict__ xs,
+                                 const float4 *__restrict__ xs_ref, int *__restrict__ flags) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nw) return;
+    if (flags[4] | flags[0]) return;
+    if (step_dev) step = *step_dev;
+    if (mode_dev) mode = (int)*mode_dev;
+    int a[3], s[3];
+    double x[3][3], v[3][3], shift[3][3];
+    const double m[3] = {wg.m_o, wg.m_h, wg.m_h};
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { a[t] = trip[3 * w + t]; s[t] = inv_order[a[t]]; }
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            x[t][d] = x_cur[3 * a[t] + d]; v[t][d] = vel[3 * a[t] + d];
+            // the molecule whole: hydrogens as the images next to their oxygen (the stored coordinates keep their own image)
+            shift[t][d] = t == 0 ? 0.0 : g.L[d] * rint((x[t][d] - x[0][d]) / g.L[d]);
+            x[t][d] -= shift[t][d];
+        }
+    if (mode & 8) {
+        double c[3][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) c[t][d] = x[t][d];
+        settle_positions(x, c, wg);
+        rattle_velocities(c, v, wg);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double xn[3], xo[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { xn[d] = c[t][d] + shift[t][d]; xo[d] = x[t][d] + shift[t][d]; x_cur[3 * a[t] + d] = xn[d]; vel[3 * a[t] + d] = v[t][d]; }
+            if (xs) publish_position(s[t], xn, xo, g, xs, xs_ref, flags);
+        }
+        return;
+    }
+    double f_new[3][3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            f_new[t][d] = (mode & 4) ? f_prev[3 * a[t] + d] : (double)f_acc[3 * (size_t)s[t] + d] * (1.0 / FIX_SCALE);
+    if (mode & 1) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double xi[3];
+            normal3(seed, (uint32_t)a[t], step - 1, xi);
+            const double bs = sqrt(two_g_kT_dt * m[t]), inv_m = 1.0 / m[t];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                v[t][d] = ca * v[t][d] + 0.5 * dt * inv_m * (ca * f_prev[3 * a[t] + d] + f_new[t][d]) + cb * inv_m * bs * xi[d];
+        }
+        rattle_velocities(x, v, wg);
+    }
+    if (!(mode & 4)) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) f_prev[3 * a[t] + d] = f_new[t][d];
+    }
+    if (mode == 3) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) f_acc[3 * (size_t)s[t] + d] = 0;
+    }
+    if (mode & 2) {
+        double c[3][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double xi[3];
+            normal3(seed, (uint32_t)a[t], step, xi);
+            const double bs = sqrt(two_g_kT_dt * m[t]), inv_m = 1.0 / m[t];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                c[t][d] = x[t][d] + cb * dt * v[t][d] + 0.5 * cb * dt * dt * inv_m * f_new[t][d] + 0.5 * cb * dt * inv_m * bs * xi[d];
+        }
+        double u[3][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u[t][d] = c[t][d];
+        settle_positions(x, c, wg);
+        const double inv_bdt = 1.0 / (cb * dt);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double xn[3], xo[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                v[t][d] += (c[t][d] - u[t][d]) * inv_bdt;
+                xn[d] = c[t][d] + shift[t][d]; xo[d] = x[t][d] + shift[t][d];
+                x_cur[3 * a[t] + d] = xn[d];
+            }
+            publish_position(s[t], xn, xo, g, xs, xs_ref, flags);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) vel[3 * a[t] + d] = v[t][d];
+}
+
 __global__ void k_kinetic(int n, const float *__restrict__ mass, const double *__restrict__ vel,
                           long long *__restrict__ e_acc) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,15 +816,44 @@ StepGeom make_geom(mdk_ctx *c) {
     return g;
 }
 
+// the Langevin update kernels on the context stream: free atoms of tile slots [first, end), then the rigid waters
+static void langevin_kernels(mdk_ctx *c, int first, int end, int mode, double dt, double ca, double cb, double tg, uint64_t seed,
+                             uint64_t step, const unsigned long long *step_dev, const unsigned long long *mode_dev) {
+    StepGeom g = make_geom(c);
+    if (end > first)
+        k_langevin<<<(end - first + 255) / 256, 256, 0, c->stream>>>(first, end, mode, dt, ca, cb, tg, seed, step, step_dev, mode_dev,
+                                                                     c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p,
+                                                                     g, c->xs.p, c->xs_ref.p, c->flags.p, c->n_rigid ? c->rigid_flag.p : nullptr);
+    ++c->n_launches;
+    if (c->n_rigid > 0) {
+        WaterGeom wg{c->rigid_d_oh, c->rigid_d_hh, c->rigid_m_o, c->rigid_m_h};
+        k_langevin_water<<<(c->n_rigid + 127) / 128, 128, 0, c->stream>>>(c->n_rigid, c->rigid_trip.p, mode, dt, ca, cb, tg, seed, step, step_dev,
+                                                                          mode_dev, c->inv_order.p, c->f_acc.p, c->x_cur.p, c->vel.p,
+                                                                          c->f_prev.p, g, wg, c->xs.p, c->xs_ref.p, c->flags.p);
+        ++c->n_launches;
+    }
+}
+
 // one Langevin update of tile slots [first, end) on the context stream (the domain-decomposed step, mdk_dd.cu)
 int langevin_launch(mdk_ctx *c, int first, int end, int mode, double dt, double ca, double cb, double tg, uint64_t seed, uint64_t step) {
-    if (end <= first) return MDK_OK;
     PhaseTimer pt(c, PH_INTEGRATE);
+    langevin_kernels(c, first, end, mode, dt, ca, cb, tg, seed, step, nullptr, nullptr);
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
+// Switching the water constraints on: the current geometry is projected onto the rigid one (positions along their own
+// bond directions, velocities onto the constraint surface) so that SETTLE's starting point satisfies the constraints.
+int rigid_project(mdk_ctx *c) {
+    if (c->n_rigid <= 0 || !c->have_pos) return MDK_OK;
     StepGeom g = make_geom(c);
-    k_langevin<<<(end - first + 255) / 256, 256, 0, c->stream>>>(first, end, mode, dt, ca, cb, tg, seed, step, nullptr, nullptr, c->order.p,
-                                                                 c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p,
-                                                                 c->xs_ref.p, c->flags.p);
+    WaterGeom wg{c->rigid_d_oh, c->rigid_d_hh, c->rigid_m_o, c->rigid_m_h};
+    k_langevin_water<<<(c->n_rigid + 127) / 128, 128, 0, c->stream>>>(c->n_rigid, c->rigid_trip.p, 8, 0.0, 0.0, 0.0, 0.0, 0ull, 0ull, nullptr,
+                                                                      nullptr, c->rigid_trip.p /* unused */, nullptr, c->x_cur.p, c->vel.p,
+                                                                      nullptr, g, wg, nullptr, nullptr, c->flags.p);
     ++c->n_launches;
+    c->xs_current = false;
+    c->verlet_cached = false; c->langevin_cached = false;
     MDK_CUDA(c, cudaGetLastError());
     return MDK_OK;
 }
@@ -596,6 +899,7 @@ static int fetch_energies(mdk_ctx *c, unsigned terms) {
 int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quirks) {
     if (nsteps <= 0) return MDK_OK;
     if (c->dd) return fail(c, MDK_ERR_BAD_ARG, "the Verlet integrator is single domain; domain-decomposed runs use the Langevin step");
+    if (c->n_rigid > 0) return fail(c, MDK_ERR_BAD_ARG, "rigid waters are integrated by the Langevin step only");
     if (terms != c->cached_terms) { c->verlet_cached = false; c->langevin_cached = false; c->cached_terms = terms; }
     const int n = c->n, T = 256, B = (n + T - 1) / T;
     StepGeom g = make_geom(c);
@@ -767,10 +1071,7 @@ static int graph_build_step(mdk_ctx *c, int variant, double dt, double ca, doubl
     CAP(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
     if (rc == MDK_OK) {
         rc = forces_enqueue(c, terms, true);
-        if (rc == MDK_OK)
-            k_langevin<<<B, T, 0, s>>>(0, n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->step_dev.p + 1, c->order.p,
-                                       c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, c->xs.p,
-                                       c->xs_ref.p, c->flags.p);
+        if (rc == MDK_OK) langevin_kernels(c, 0, n, 3, dt, ca, cb, tg, seed, 0ull, c->step_dev.p, c->step_dev.p + 1);
         cudaError_t e = cudaStreamEndCapture(s, &graph);
         if (e != cudaSuccess && rc == MDK_OK) rc = fail(c, MDK_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
     }
@@ -829,10 +1130,8 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
             const bool last = s + 1 == nsteps;
             MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
             MDK_TRY(forces_enqueue(c, terms, true));
-            k_langevin<<<B, T, 0, c->stream>>>(0, n, last ? 1 : 3, dt, ca, cb, tg, seed, c->langevin_step + (uint64_t)s, nullptr,
-                                               nullptr, c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p,
-                                               c->f_prev.p, g, c->xs.p, c->xs_ref.p, c->flags.p);
-            c->n_launches += 2;
+            langevin_kernels(c, 0, n, last ? 1 : 3, dt, ca, cb, tg, seed, c->langevin_step + (uint64_t)s, nullptr, nullptr);
+            c->n_launches += 1;
         }
         c->n_pair_launches += nsteps;
         c->graph_pending = nsteps;
@@ -893,10 +1192,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
 #define LANGEVIN(mode)                                                                                          \
     do {                                                                                                        \
         PhaseTimer pt(c, PH_INTEGRATE);                                                                         \
-        k_langevin<<<B, T, 0, c->stream>>>(0, n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, nullptr, \
-                                           c->order.p, c->mass.p, c->f_acc.p, c->x_cur.p, c->vel.p, c->f_prev.p, g, \
-                                           c->xs.p, c->xs_ref.p, c->flags.p);                                   \
-        ++c->n_launches;                                                                                        \
+        langevin_kernels(c, 0, n, (mode), dt, ca, cb, tg, seed, c->langevin_step, nullptr, nullptr);            \
     } while (0)
     // multi-GPU: plain host-launched steps unless one of the two graph flavours is switched on — `hosted`
     // (upkeep graph + host-launched forces / NCCL / update, no host sync inside a run) or `graph_nccl`

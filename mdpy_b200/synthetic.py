@@ -73,8 +73,16 @@ class SyntheticSystem:
         rows = {k: (v + v if len(v) == 2 else v) for k, v in self.lj_parameters.items()}
         return np.array([rows[t] for t in self.types], dtype=np.float32)
 
-    def ensemble(self, cutoff=12.0, switch=None, pme=True, ewald_error=1e-6, grid=None, order=4, bonded=True):
-        """Ensemble with the native constraints bound (needs a B200)."""
+    def water_triplets(self):
+        """(O, H, H) matrix ids of the TIP3P molecules (the waters are the trailing OT HT HT triplets)."""
+        types = np.asarray(self.types)
+        first = int(np.argmax(types == 'OT')) if (types == 'OT').any() else len(types)
+        o = np.arange(first, len(types), 3)
+        return np.stack([o, o + 1, o + 2], 1).astype(np.int32)
+
+    def ensemble(self, cutoff=12.0, switch=None, pme=True, ewald_error=1e-6, grid=None, order=4, bonded=True, rigid_water=False):
+        """Ensemble with the native constraints bound (needs a B200).  rigid_water: the waters are held rigid by
+        SETTLE (what the reference's is_SHAKE flag asks for) and their bond / angle terms are left out."""
         from . import Ensemble
         from .constraint import (CharmmAngleConstraint, CharmmBondConstraint, CharmmDihedralConstraint,
                                  CharmmImproperConstraint, CharmmNonbondedConstraint, ElectrostaticPMEConstraint)
@@ -82,13 +90,24 @@ class SyntheticSystem:
         cs = [CharmmNonbondedConstraint(self.lj_parameters, cutoff, switch_radius=switch)]
         if pme:
             cs.append(ElectrostaticPMEConstraint(cutoff, ewald_error=ewald_error, grid=grid, order=order))
+        keep_b = keep_a = slice(None)
+        if rigid_water:
+            water_atoms = self.water_triplets().reshape(-1)
+            keep_b = ~np.isin(self.bonds[:, 0], water_atoms) if len(self.bonds) else slice(None)
+            keep_a = ~np.isin(self.angles[:, 1], water_atoms) if len(self.angles) else slice(None)
+            # exclusions come from the full bond graph (O-H, H-H stay excluded); the force terms lose the waters' rows
+            ens.topology._bonds = self.bonds[keep_b]
+            ens.topology._angles = self.angles[keep_a]
         if bonded:
-            if len(self.bonds): cs.append(CharmmBondConstraint(self.bond_par))
-            if len(self.angles): cs.append(CharmmAngleConstraint(self.angle_par))
+            if len(self.bonds[keep_b]): cs.append(CharmmBondConstraint(self.bond_par[keep_b]))
+            if len(self.angles[keep_a]): cs.append(CharmmAngleConstraint(self.angle_par[keep_a]))
             if len(self.dihedrals): cs.append(CharmmDihedralConstraint(self.dihedral_par))
             if len(self.impropers): cs.append(CharmmImproperConstraint(self.improper_par))
         ens.add_constraints(*cs)
         ens.state.set_positions(self.positions.astype(np.float32))
+        if rigid_water:
+            from . import _native
+            _native.context_of(ens).dev.set_rigid_waters(self.water_triplets(), _R_OH, 2 * _R_OH * np.sin(_ANG_HOH / 2))
         return ens
 
 

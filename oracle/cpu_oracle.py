@@ -391,3 +391,28 @@ def steepest_descent(positions, box, force_energy_fn, alpha=0.01, energy_toleran
         if abs((e - energies[-2]) / energies[-2]) < energy_tolerance:
             break
     return x, it, energies
+
+
+def gjf_rigid_water_call(x, v, f0, force_fn, masses, triplets, d_oh, d_hh, dt, gamma, kT, seed, step):
+    """One single-step call of the G-JF integrator with rigid three-site waters on a fresh state, in the order the step
+    is split around the force evaluation (advance x with f(x_0), evaluate f(x_1), finish v):
+        c   = x + b dt v + b dt^2/(2m) f0 + b dt/(2m) beta          (unconstrained)
+        x_1 = SETTLE(x, c);  v += (x_1 - c) / (b dt)                 (the constraint force's share of the velocity update)
+        v_1 = RATTLE_v(x_1, a v + dt/(2m) (a f0 + f(x_1)) + b/m beta)
+    x, v: [N,3] float64 (whole molecules), triplets [W,3].  Free atoms (not in any triplet) take the plain G-JF step.
+    Returns (x_1, v_1, f_1)."""
+    from . import settle as st
+    m = np.asarray(masses, dtype=np.float64).reshape(-1, 1)
+    half = 0.5 * gamma * dt
+    a, b = (1.0 - half) / (1.0 + half), 1.0 / (1.0 + half)
+    beta = np.sqrt(2.0 * gamma * kT * dt * m) * langevin_noise(seed, x.shape[0], step)
+    c = x + b * dt * v + 0.5 * b * dt * dt / m * f0 + 0.5 * b * dt / m * beta
+    t = np.asarray(triplets)
+    m_o, m_h = float(m[t[0, 0], 0]), float(m[t[0, 1], 0])
+    x1 = c.copy()
+    x1[t] = st.settle(x[t], c[t], m_o, m_h, d_oh, d_hh)
+    v_mid = v + (x1 - c) / (b * dt)
+    f1 = force_fn(x1)
+    v1 = a * v_mid + 0.5 * dt / m * (a * f0 + f1) + b / m * beta
+    v1[t] = st.rattle_velocities(x1[t], v1[t], m_o, m_h)
+    return x1, v1, f1

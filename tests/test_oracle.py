@@ -324,3 +324,32 @@ def test_oracle_reproduces_the_reference_config1_trajectory():
     for k, step in enumerate(steps):
         assert np.abs(snaps[step] - g['snapshots'][k]).max() < 1e-8, step
     assert np.abs(vel - g['final_velocities']).max() < 1e-8
+
+
+def test_settle_oracle_is_pinned_against_iterative_shake():
+    """oracle/settle.py: the analytic SETTLE positions equal what an independent iterative SHAKE converges to, the
+    constraints hold to rounding, the centre of mass does not move, and the velocity stage leaves no velocity along a bond."""
+    from oracle import settle as st
+    rng = np.random.default_rng(1)
+    W, d_oh, ang = 500, 0.9572, np.deg2rad(104.52)
+    d_hh = 2 * d_oh * np.sin(ang / 2)
+    local = np.array([[0, 0, 0], [d_oh * np.sin(ang / 2), 0, d_oh * np.cos(ang / 2)], [-d_oh * np.sin(ang / 2), 0, d_oh * np.cos(ang / 2)]])
+    q = rng.normal(size=(W, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                  np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                  np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
+    x_old = np.einsum('nij,kj->nki', R, local) + rng.uniform(-20, 20, size=(W, 1, 3))
+    x_new = x_old + rng.normal(size=(W, 3, 3)) * 0.05
+    mo, mh = 15.9994, 1.008
+    a = st.settle(x_old, x_new, mo, mh, d_oh, d_hh)
+    assert np.abs(a - st.shake(x_old, x_new, mo, mh, d_oh, d_hh)).max() < 1e-12
+    dist = lambda p, i, j: np.linalg.norm(p[:, i] - p[:, j], axis=1)
+    assert np.abs(dist(a, 0, 1) - d_oh).max() < 1e-13 and np.abs(dist(a, 0, 2) - d_oh).max() < 1e-13 and np.abs(dist(a, 1, 2) - d_hh).max() < 1e-13
+    m = np.array([mo, mh, mh])
+    assert np.abs((m[None, :, None] * (a - x_new)).sum(1)).max() < 1e-12
+    v = rng.normal(size=(W, 3, 3)) * 0.01
+    v2 = st.rattle_velocities(a, v, mo, mh)
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        assert np.abs(((v2[:, j] - v2[:, i]) * (a[:, j] - a[:, i])).sum(1)).max() < 1e-15
+    assert np.abs((m[None, :, None] * (v2 - v)).sum(1)).max() < 1e-15

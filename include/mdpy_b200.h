@@ -92,6 +92,13 @@ MDK_API int mdk_set_atoms(mdk_ctx *ctx, int n, const float *charges, const float
  * rc = cutoff (inclusive, :90).  r_switch >= rc: the reference's plain truncation;
  * r_switch < rc: CHARMM energy switch on (r_switch, rc] [not in the reference tree]. */
 MDK_API int mdk_set_lj(mdk_ctx *ctx, const float *eps_sigma, float rc, float r_switch);
+/* env.set_precision('DOUBLE') (mdpy/environment.py:23-42 switches the reference's arithmetic type).  With
+ * double_precision != 0 and the float64 parameter copies of mdk_set_params_f64 (charges [n], eps/sigma table [n,4]; either
+ * may be NULL), LJ, erfc direct space, the bonded terms, the excluded-pair correction and the all-pairs Coulomb sum are
+ * evaluated in float64 on the float64 positions (mdk_upload_positions_f64); sums stay int64 fixed point (2^-40).
+ * The PME mesh (spreading, FFT, gather) stays float32. */
+MDK_API int mdk_set_precision(mdk_ctx *ctx, int double_precision);
+MDK_API int mdk_set_params_f64(mdk_ctx *ctx, const double *charges, const double *eps_sigma);
 /* topology.bonded_particles (1-2 and 1-3 partners: excluded, charmm_nonbonded_constraint.py:83)
  * and topology.scaling_particles (1-4 partners: eps14/sigma14, :92-97), int32, -1 padded,
  * row widths wb / ws (topology.py:69-79).  Either pointer may be NULL with width 0. */

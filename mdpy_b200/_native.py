@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -96,6 +96,8 @@ def load_library():
         'mdk_dd_step_langevin_group': (i32, [vp, i32, f64, f64, f64, u64, i32, C.c_uint, vp]),
         'mdk_dd_stats': (i32, [vp, vp]),
         'mdk_set_rigid_waters': (i32, [vp, i32, vp, f64, f64]),
+        'mdk_set_precision': (i32, [vp, i32]),
+        'mdk_set_params_f64': (i32, [vp, vp, vp]),
         'mdk_minimize_sd': (i32, [vp, f64, f64, i32, C.c_uint, C.POINTER(i32), vp, vp]),
         'mdk_comm_unique_id': (i32, [vp]),
         'mdk_comm_init': (i32, [vp, i32, i32, vp]),
@@ -158,12 +160,23 @@ class Device:
         m = np.ascontiguousarray(masses, dtype=np.float32).reshape(-1)
         self.n = q.size
         self._ck(self._lib.mdk_set_atoms(self._h, q.size, _ptr(q), _ptr(m)))
+        if getattr(self, 'double_precision', False):
+            q64 = np.ascontiguousarray(charges, dtype=np.float64).reshape(-1)
+            self._ck(self._lib.mdk_set_params_f64(self._h, _ptr(q64), None))
 
     def set_lj(self, table, rc, r_switch=None):
         t = np.ascontiguousarray(table, dtype=np.float32)
         if t.shape != (self.n, 4):
             raise _err.ArrayDimError('LJ table should be [%d, 4], got %s' % (self.n, list(t.shape)))
         self._ck(self._lib.mdk_set_lj(self._h, _ptr(t), float(rc), float(rc if r_switch is None else r_switch)))
+        if getattr(self, 'double_precision', False):
+            t64 = np.ascontiguousarray(table, dtype=np.float64)
+            self._ck(self._lib.mdk_set_params_f64(self._h, None, _ptr(t64)))
+
+    def set_precision(self, double_precision):
+        """mdk_set_precision: float64 pair / bonded arithmetic (env.set_precision('DOUBLE'))."""
+        self.double_precision = bool(double_precision)
+        self._ck(self._lib.mdk_set_precision(self._h, int(self.double_precision)))
 
     def set_exclusions(self, bonded, scaling):
         def prep(a):
@@ -382,6 +395,8 @@ class EnsembleContext:
                 "reference package itself")
         self.ensemble = ensemble
         self.dev = Device(device)
+        if np.dtype(env.NUMPY_FLOAT) == np.float64 and hasattr(self.dev, 'set_precision'):
+            self.dev.set_precision(True)     # env.set_precision('DOUBLE'): float64 arithmetic, like the reference's switch
         topo, state = ensemble.topology, ensemble.state
         self._box_rev = None
         self._pos_rev = None

@@ -235,7 +235,7 @@ void mdk_destroy(mdk_ctx *c) {
     if (c->have_plans) { cufftDestroy(c->plan_r2c); cufftDestroy(c->plan_c2r); }
     c->q.release(); c->mass.release(); c->lj4.release(); c->excl.release(); c->p14.release(); c->excl_pairs.release();
     for (auto &b : c->bonded) { b.idx.release(); b.par.release(); }
-    c->rigid_trip.release(); c->rigid_flag.release();
+    c->rigid_trip.release(); c->rigid_flag.release(); c->q64.release(); c->lj64.release();
     c->x_cur.release(); c->x_prev.release(); c->vel.release(); c->f_prev.release();
     c->order.release(); c->inv_order.release(); c->xs.release(); c->xs_ref.release(); c->ljs.release();
     c->excl_s.release(); c->p14_s.release(); c->f_acc.release(); c->readback.release();
@@ -286,7 +286,9 @@ int mdk_set_atoms(mdk_ctx *c, int n, const float *charges, const float *masses) 
     NEED_CTX(c);
     if (n <= 0 || !charges || !masses) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_atoms: n=%d / NULL arrays", n);
     cudaSetDevice(c->device);
+    c->have_q64 = false;
     if (n != c->n) {
+        c->have_lj64 = false;
         c->have_pos = false; c->have_lj = false; c->wb = c->ws = 0;
         c->verlet_cached = c->langevin_cached = false;
         for (auto &b : c->bonded) b.n = 0;
@@ -317,6 +319,35 @@ int mdk_set_lj(mdk_ctx *c, const float *eps_sigma, float rc, float r_switch) {
     c->r_switch = (r_switch > 0 && r_switch < rc) ? r_switch : rc;
     c->have_lj = true;
     invalidate(c);
+    return MDK_OK;
+}
+
+int mdk_set_precision(mdk_ctx *c, int double_precision) {
+    NEED_CTX(c);
+    c->dprec = double_precision != 0;
+    c->verlet_cached = false; c->langevin_cached = false;
+    ++c->graph_epoch;
+    return MDK_OK;
+}
+
+int mdk_set_params_f64(mdk_ctx *c, const double *charges, const double *eps_sigma) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_set_params_f64 before mdk_set_atoms");
+    if (charges) {
+        MDK_CUDA(c, c->q64.reserve(c->n));
+        MDK_CUDA(c, cudaMemcpy(c->q64.p, charges, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice));
+        c->have_q64 = true;
+        double sq = 0, sq2 = 0;
+        for (int i = 0; i < c->n; ++i) { sq += charges[i]; sq2 += charges[i] * charges[i]; }
+        c->host_tmp.assign({sq, sq2});
+    }
+    if (eps_sigma) {
+        MDK_CUDA(c, c->lj64.reserve((size_t)4 * c->n));
+        MDK_CUDA(c, cudaMemcpy(c->lj64.p, eps_sigma, (size_t)4 * c->n * sizeof(double), cudaMemcpyHostToDevice));
+        c->have_lj64 = true;
+    }
+    c->verlet_cached = false; c->langevin_cached = false;
     return MDK_OK;
 }
 

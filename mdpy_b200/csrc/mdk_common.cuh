@@ -97,6 +97,11 @@ struct mdk_ctx {
     bool have_box = false;
     mdk::DevBuf<float> q, mass;          // [n]
     mdk::DevBuf<float4> lj4;             // [n] eps, sigma, eps14, sigma14
+    // DOUBLE precision (env.set_precision('DOUBLE'), mdpy/environment.py:23-42): float64 copies of the per-atom parameters;
+    // the pair, bonded and bare-Coulomb arithmetic then runs in float64 on the float64 positions (x_cur)
+    bool dprec = false;
+    mdk::DevBuf<double> q64, lj64;       // [n], [n,4]
+    bool have_q64 = false, have_lj64 = false;
     bool have_lj = false;
     float rc_lj = 0.f, r_switch = 0.f;
     mdk::DevBuf<int> excl, p14;          // [n, wb] / [n, ws], -1 padded, matrix ids
@@ -269,6 +274,7 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph);  // device work of a rebuild only 
 int nlist_ensure(mdk_ctx *c);                  // rebuild if flagged / invalid
 NlistView nlist_view(mdk_ctx *c);
 int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul);
+int pair_compute_f64(mdk_ctx *c, bool do_lj, bool do_coul);   // DOUBLE precision: plain float64 kernel over the same tile list
 int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int64_t *n_out, int production);
 int coulomb_bare(mdk_ctx *c);
 int pme_prepare(mdk_ctx *c);

@@ -46,7 +46,7 @@ struct DDState {
     int pme_rank = 0;
     bool local = false;
     int group_id = -1;
-    std::vector<int> blk;                       // [P + 1] first i-block of every rank (host copy)
+    std::vector<int> blk;                       // [P + 1] first tile slot of every rank (host copy): rank r owns slots [blk[r], blk[r+1])
     DevBuf<int> need, sendl;                    // halo: slots of other ranks this rank needs (ascending = grouped by
                                                 // owner) / own slots the peers need (grouped by peer)
     std::vector<int> need_cnt, need_off, send_cnt, send_off;
@@ -69,7 +69,7 @@ struct DDState {
     int64_t stat_exchanges = 0, stat_rebuilds = 0;
 };
 
-constexpr int PIN_ALL = 8 + 2 * (DD_MAXR + 1);     // pinned words: [0..7] flags, [8..] bounds / own counts, [PIN_ALL..] count matrix
+constexpr int PIN_ALL = 8 + 2 * (DD_MAXR + 1);        // pinned words: [0..7] flags, [8..] bounds / own counts, [PIN_ALL..] count matrix
 constexpr int PIN_WORDS = PIN_ALL + DD_MAXR * DD_MAXR + 8;
 using Group = std::vector<mdk_ctx *>;
 static std::map<int, Group> g_groups;
@@ -98,18 +98,14 @@ __global__ void k_dd_mark_excl(int n_pairs, const int2 *__restrict__ pairs, cons
     if (k >= own_lo && k < own_hi && (p < own_lo || p >= own_hi)) mark[p] = 1;     // the pair belongs to the owner of its first atom
 }
 
-__global__ void k_dd_mark_range(int lo, int hi, int *__restrict__ mark) {
-    for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) mark[k] = 1;
-}
-
-// cnt[r] = number of needed slots owned by rank r (need is ascending; rank r owns slots [32 blk[r], 32 blk[r+1]))
+// cnt[r] = number of needed slots owned by rank r (need is ascending; rank r owns slots [blk[r], blk[r+1]))
 __global__ void k_dd_need_counts(const int *__restrict__ need, const int *__restrict__ n_sel, const int *__restrict__ blk,
                                  int P, int *__restrict__ cnt) {
     const int r = threadIdx.x;
     if (r >= P) return;
     const int n = *n_sel;
     auto lb = [&](int v) { int lo = 0, hi = n; while (lo < hi) { int m = (lo + hi) >> 1; if (need[m] < v) lo = m + 1; else hi = m; } return lo; };
-    cnt[r] = lb(blk[r + 1] * TILE) - lb(blk[r] * TILE);
+    cnt[r] = lb(blk[r + 1]) - lb(blk[r]);
 }
 
 __global__ void k_dd_pack_x(int n, const int *__restrict__ list, const float4 *__restrict__ xs, float4 *__restrict__ out,
@@ -260,7 +256,7 @@ static int dd_gather_state(Group &g) {
         const size_t row = 9 * sizeof(double);
         for (int r = 0; r < P; ++r) {
             if (r == c->rank) continue;
-            const int rlo = std::min(d->blk[r] * TILE, c->n), rhi = std::min(d->blk[r + 1] * TILE, c->n);
+            const int rlo = d->blk[r], rhi = d->blk[r + 1];
             d->xf.push_back(Xfer{r, (size_t)lo * row, (size_t)(hi - lo) * row, (size_t)rlo * row, (size_t)(rhi - rlo) * row});
         }
     }
@@ -318,17 +314,12 @@ static int dd_rebuild(Group &g) {
         DDState *d = c->dd;
         MDK_TRY(nlist_rebuild(c));                // keys (domain-major) -> sort -> gathers -> bounds -> own lists (+ marks)
         // ownership of this rebuild
-        MDK_CUDA(c, cudaMemcpyAsync(d->pin + 8, c->dd_blk.p, 2 * (DD_MAXR + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MDK_CUDA(c, cudaMemcpyAsync(d->pin + 8, c->dd_blk.p, (DD_MAXR + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
         d->blk.assign(d->pin + 8, d->pin + 8 + P + 1);
-        c->own_lo = d->blk[c->rank] * TILE;
-        c->own_hi = d->blk[c->rank + 1] * TILE;
-        c->pme_lo = d->pin[8 + DD_MAXR + 1 + c->rank];
-        c->pme_hi = d->pin[8 + DD_MAXR + 1 + c->rank + 1];
-        // the few atoms of this domain that sit in the previous rank's last (straddling) i-block: spread / gathered
-        // here, integrated there — their positions come in and their mesh forces go back with the halo
-        if (c->pme_lo < c->own_lo)
-            k_dd_mark_range<<<1, 64, 0, c->stream>>>(c->pme_lo, c->own_lo, c->dd_mark.p);
+        c->own_lo = d->blk[c->rank];
+        c->own_hi = d->blk[c->rank + 1];
+        c->pme_lo = c->own_lo; c->pme_hi = c->own_hi;
         // halo: what the lists reference (marked by the builder) + the partners of the own bonded / excluded-pair terms
         static const int width[4] = {2, 3, 4, 4};
         for (int kind = 0; kind < 4; ++kind)
@@ -595,7 +586,7 @@ static int dd_gather_forces(Group &g) {
         const int lo = own_first(c), hi = own_end(c);
         for (int r = 0; r < P; ++r) {
             if (r == c->rank) continue;
-            const int rlo = std::min(d->blk[r] * TILE, c->n), rhi = std::min(d->blk[r + 1] * TILE, c->n);
+            const int rlo = d->blk[r], rhi = d->blk[r + 1];
             d->xf.push_back(Xfer{r, (size_t)lo * row, (size_t)(hi - lo) * row, (size_t)rlo * row, (size_t)(rhi - rlo) * row});
         }
     }

@@ -18,6 +18,8 @@
 // tests bit k (pair i = l, j-slot = (l + k) & 31).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "mdk_common.cuh"
 
 namespace mdk {
@@ -88,15 +90,15 @@ __global__ void k_cell_start(int n, int ncells, const unsigned *__restrict__ key
     cell_start[c] = lo;
 }
 
-// first i-block of every domain: a block that straddles a domain boundary belongs to the domain of its first atom
-// (blk[DD_MAXR + 1 + r] = the exact first tile slot of domain r: the atoms whose cell lies in the domain)
-__global__ void k_dd_bounds(DDGeom d, int n, int n_blocks, const int *__restrict__ cell_start, int *__restrict__ blk) {
+// first tile slot of every domain (the atoms whose cell lies in the domain are one contiguous range of the tile order);
+// blk[ndom] = n.  A rank owns exactly the atoms of its domain.  An i-block that straddles a domain boundary is listed
+// twice, once by each rank for its own lanes of the block (the other lanes are masked like the padding of a ragged
+// last block), so every rank's i-blocks stay spatially compact.
+__global__ void k_dd_bounds(DDGeom d, int n, const int *__restrict__ cell_start, int *__restrict__ blk) {
     const int ndom = d.pdim[0] * d.pdim[1] * d.pdim[2];
     const int r = threadIdx.x;
     if (r > ndom) return;
-    const int first = r == ndom ? n : cell_start[d.dom_base[r]];
-    blk[r] = r == 0 ? 0 : (r == ndom ? n_blocks : min(n_blocks, (first + TILE - 1) / TILE));
-    blk[DD_MAXR + 1 + r] = first;
+    blk[r] = r == ndom ? n : cell_start[d.dom_base[r]];
 }
 
 // tile-order gather of positions / charges / LJ parameters; also resets the displacement
@@ -162,16 +164,22 @@ __global__ void k_refresh_sorted(int n, const int *__restrict__ order, const dou
 }
 
 // one warp per i-block: periodic bounding box relative to the block's first atom
-__global__ void k_block_bbox(GridParams g, const float4 *__restrict__ xs, float4 *__restrict__ bbc,
+// (decomposed runs: over the lanes this rank owns — other ranks' blocks are skipped, a straddling block gets the box of
+// the own part)
+__global__ void k_block_bbox(GridParams g, const float4 *__restrict__ xs, const int *__restrict__ dd_blk, float4 *__restrict__ bbc,
                              float4 *__restrict__ bbh, int *__restrict__ bb_max) {
     int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (b >= g.n_blocks) return;
     int k = b * TILE + lane;
     bool valid = k < g.n;
-    float4 p = xs[valid ? k : b * TILE];
-    float rx = __shfl_sync(0xffffffffu, p.x, 0), ry = __shfl_sync(0xffffffffu, p.y, 0),
-          rz = __shfl_sync(0xffffffffu, p.z, 0);
+    if (g.dd_nranks > 1) valid = valid && k >= dd_blk[g.dd_rank] && k < dd_blk[g.dd_rank + 1];
+    const unsigned any = __ballot_sync(0xffffffffu, valid);
+    if (!any) return;
+    const int first = __ffs(any) - 1;
+    float4 p = xs[valid ? k : b * TILE + first];
+    float rx = __shfl_sync(0xffffffffu, p.x, first), ry = __shfl_sync(0xffffffffu, p.y, first),
+          rz = __shfl_sync(0xffffffffu, p.z, first);
     float d[3] = {min_image(p.x - rx, g.L[0], g.invL[0]), min_image(p.y - ry, g.L[1], g.invL[1]),
                   min_image(p.z - rz, g.L[2], g.invL[2])};
     float mn[3], mx[3];
@@ -304,8 +312,9 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
     // evaluate the same rule on the same global order, exactly one of them lists the pair, and the cross-domain
     // work is shared evenly whichever side of a boundary a block sits on.
     const bool multi = g.dd_nranks > 1;
-    const int blk_lo = multi ? dd_blk[g.dd_rank] : 0, blk_hi = multi ? dd_blk[g.dd_rank + 1] : g.n_blocks;
-    if (multi) { o.own_lo = blk_lo * TILE; o.own_hi = blk_hi * TILE; } else { o.mark = nullptr; }
+    const int own_lo = multi ? dd_blk[g.dd_rank] : 0, own_hi = multi ? dd_blk[g.dd_rank + 1] : g.n_blocks * TILE;
+    const int blk_lo = own_lo / TILE, blk_hi = (own_hi + TILE - 1) / TILE;      // the first / last one may be shared with a neighbour rank
+    if (multi) { o.own_lo = own_lo; o.own_hi = own_hi; } else { o.mark = nullptr; }
     // work item = (i-block, part): the candidate rows of a block are dealt round-robin to n_parts warps,
     // each emitting its own work units, so small systems still fill the machine during a rebuild
     for (int w = warp_global; w < (blk_hi - blk_lo) * n_parts; w += n_warps) {
@@ -318,12 +327,16 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
         // R + h <= L/2 on every axis is enough (pairs farther apart than R may then see a non-minimal image, but
         // both distances exceed the cutoff).  Blocks that break the bound are flagged and evaluated canonically.
         em.wide = (h.x > g.wide_lim[0] || h.y > g.wide_lim[1] || h.z > g.wide_lim[2]) ? 1 : 0;
-        em.i_valid = (b * TILE + lane) < g.n;
-        em.ragged = (b == g.n_blocks - 1) && (g.n & 31);
+        const int my_slot = b * TILE + lane;
+        em.i_valid = my_slot < g.n && my_slot >= own_lo && my_slot < own_hi;
+        em.ragged = ((b == g.n_blocks - 1) && (g.n & 31)) || b * TILE < own_lo || (b + 1) * TILE > own_hi;
         em.excl_s = excl_s; em.p14_s = p14_s; em.wb = wb; em.ws = ws; em.o = o;
         // i-atom positions of this block for the exact filter (ragged lanes repeat the first atom)
         __syncwarp();
-        s_xi[wid][lane] = xs[em.i_valid ? b * TILE + lane : b * TILE];
+        {   // i-atom positions for the exact filter; lanes this rank does not own repeat an own atom of the block
+            const unsigned vm = __ballot_sync(0xffffffffu, em.i_valid);
+            s_xi[wid][lane] = xs[em.i_valid ? my_slot : b * TILE + (vm ? __ffs(vm) - 1 : 0)];
+        }
         __syncwarp();
         em.begin();
         if (part == 0) {
@@ -366,7 +379,7 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                     // decomposed: inside the own domain only j > b counts (half shell by index), except the few slots
                     // at the start of the domain's range that sit in the previous rank's straddling block
                     int skip_lo = 0, skip_hi = 0;
-                    if (multi) { skip_lo = max(s, blk_lo * TILE); skip_hi = min(e, min(first_j, blk_hi * TILE)); }
+                    if (multi) { skip_lo = max(s, own_lo); skip_hi = min(e, min(first_j, own_hi)); }
                     for (int base = s; base < e; base += 32) {
                         if (base >= skip_lo && base + 32 <= skip_hi) continue;   // a whole stride of own atoms at or before this block
                         int j = base + lane;
@@ -375,7 +388,7 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                         bool cand = j < e;
                         if (multi && cand) {
                             const int bj = j >> 5;
-                            if (bj >= blk_lo && bj < blk_hi) cand = bj > b;
+                            if (j >= own_lo && j < own_hi) cand = bj > b;
                             else cand = ((b + bj) & 1) ? (bj < b) : (bj > b);
                         }
                         if (cand) {
@@ -536,7 +549,8 @@ static int nlist_plan(mdk_ctx *c) {
         for (; dom <= DD_MAXR; ++dom) d.dom_base[dom] = base;
         if (memcmp(&before, &d, sizeof(d)) != 0) ++c->graph_epoch;   // kernel arguments of captured rebuilds
     }
-    c->n_parts = (int)((4096 + c->n_blocks - 1) / c->n_blocks);
+    const int blocks_here = std::max(1, c->dd ? c->n_blocks / c->nranks : c->n_blocks);   // i-blocks this rank lists
+    c->n_parts = (int)((4096 + blocks_here - 1) / blocks_here);
     if (c->n_parts < 1) c->n_parts = 1;
     if (c->n_parts > 8) c->n_parts = 8;
     // work-unit granularity: enough units to fill the machine a few times over
@@ -561,7 +575,7 @@ static int nlist_plan(mdk_ctx *c) {
     MDK_CUDA(c, c->xs.reserve(c->n_pad)); MDK_CUDA(c, c->xs_ref.reserve(c->n_pad));
     MDK_CUDA(c, c->ljs.reserve(c->n_pad)); MDK_CUDA(c, c->f_acc.reserve((size_t)c->n_pad * 3));
     MDK_CUDA(c, c->bb_center.reserve(c->n_blocks)); MDK_CUDA(c, c->bb_half.reserve(c->n_blocks));
-    MDK_CUDA(c, c->dd_blk.reserve(2 * (DD_MAXR + 1)));
+    MDK_CUDA(c, c->dd_blk.reserve(DD_MAXR + 1));
     if (c->dd) MDK_CUDA(c, c->dd_mark.reserve(c->n_pad));
     MDK_CUDA(c, c->excl_s.reserve((size_t)n * (c->wb > 0 ? c->wb : 1)));
     MDK_CUDA(c, c->p14_s.reserve((size_t)n * (c->ws > 0 ? c->ws : 1)));
@@ -613,7 +627,7 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph) {
                                                 c->idx_tmp.p, c->order.p, n, 0, c->sort_end_bit, c->stream));
     k_cell_start<<<(int)((ncells + 1 + T - 1) / T), T, 0, c->stream>>>(n, (int)ncells, c->cell_key_sorted.p,
                                                                        c->cell_start.p);
-    k_dd_bounds<<<1, DD_MAXR + 1, 0, c->stream>>>(g.dd, n, c->n_blocks, c->cell_start.p, c->dd_blk.p);
+    k_dd_bounds<<<1, DD_MAXR + 1, 0, c->stream>>>(g.dd, n, c->cell_start.p, c->dd_blk.p);
     if (c->dd) MDK_CUDA(c, cudaMemsetAsync(c->dd_mark.p, 0, (size_t)c->n_pad * sizeof(int), c->stream));
     float sqrt_ke = c->have_coul ? (float)sqrt(c->k_e) : 0.f;
     k_gather_sorted<<<(c->n_pad + T - 1) / T, T, 0, c->stream>>>(n, c->n_pad, c->order.p, c->x_cur.p, c->q.p,
@@ -627,7 +641,7 @@ int nlist_enqueue(mdk_ctx *c, bool in_graph) {
                                                                       c->ws, c->p14_s.p);
     MDK_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 12 * sizeof(int), c->stream));
     MDK_CUDA(c, cudaMemsetAsync(c->flags.p + 1, 0, 2 * sizeof(int), c->stream));
-    k_block_bbox<<<(c->n_blocks * 32 + T - 1) / T, T, 0, c->stream>>>(g, c->xs.p, c->bb_center.p, c->bb_half.p,
+    k_block_bbox<<<(c->n_blocks * 32 + T - 1) / T, T, 0, c->stream>>>(g, c->xs.p, c->dd_blk.p, c->bb_center.p, c->bb_half.p,
                                                                     c->counters.p + 8);
     BuildOut o;
     o.units = c->units.p; o.chunk_j = c->chunk_j.p; o.chunk_mask = c->chunk_mask.p;

@@ -315,10 +315,132 @@ static PairParams make_pair_params(mdk_ctx *c, bool do_lj, bool do_coul) {
     return P;
 }
 
+// ---------------------------------------------------------------------------
+// DOUBLE precision (mdpy/environment.py:23-42 switches the reference's arithmetic type): the same tile list, the same
+// warp-per-unit rotation scheme and masks, float64 positions (x_cur, wrapped here), float64 parameters, libm erfc / exp.
+// Not tuned — it exists so that env.set_precision('DOUBLE') means float64 arithmetic, as in the reference.
+struct PairParams64 {
+    double L[3];
+    double rc2_lj, ron2, inv_ab3, rc2_c, alpha, sqrt_ke;
+    int n;
+    bool sw;
+};
+
+__global__ void __launch_bounds__(128)
+k_pair_f64(PairParams64 P, NlistView nl, const int *__restrict__ order, const double *__restrict__ x_cur,
+           const double *__restrict__ q64, const double *__restrict__ lj64, long long *__restrict__ f_acc,
+           long long *__restrict__ e_acc, int *__restrict__ cursor) {
+    __shared__ double s_x[4][32][4];
+    __shared__ double s_l[4][32][4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n_units = *nl.n_units;
+    auto load = [&](int slot, double x[4], double l[4]) {
+        x[0] = x[1] = x[2] = x[3] = 0.0; l[0] = l[1] = l[2] = l[3] = 0.0;
+        if (slot < P.n) {
+            const int a = order[slot];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { const double v = x_cur[3 * (size_t)a + d]; x[d] = v - P.L[d] * rint(v / P.L[d]); }
+            x[3] = q64 ? q64[a] * P.sqrt_ke : 0.0;
+            if (lj64) { l[0] = 2.0 * sqrt(lj64[4 * (size_t)a]); l[1] = 0.5 * lj64[4 * (size_t)a + 1];
+                        l[2] = 2.0 * sqrt(lj64[4 * (size_t)a + 2]); l[3] = 0.5 * lj64[4 * (size_t)a + 3]; }
+        }
+    };
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(cursor, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const int4 unit = nl.units[u];
+        const int ia = unit.x * TILE + lane;
+        double xi[4], li[4];
+        load(ia, xi, li);
+        double fi[3] = {0, 0, 0}, e_lj = 0, e_c = 0;
+        for (int cidx = 0; cidx < unit.z; ++cidx) {
+            const int chunk = unit.y + cidx;
+            const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
+            const int mslot = nl.chunk_mask[chunk];
+            const unsigned excl = mslot >= 0 ? nl.mask_excl[(size_t)mslot * 32 + lane] : 0u;
+            const unsigned m14 = mslot >= 0 ? nl.mask_14[(size_t)mslot * 32 + lane] : 0u;
+            double xj[4], lj[4];
+            load(j, xj, lj);
+            __syncwarp();
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { s_x[wid][lane][d] = xj[d]; s_l[wid][lane][d] = lj[d]; }
+            __syncwarp();
+            double fj[3] = {0, 0, 0};
+            for (int k = 0; k < 32; ++k) {
+                const int s = (lane + k) & 31;
+                double d[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { d[a] = s_x[wid][s][a] - xi[a]; d[a] -= P.L[a] * rint(d[a] / P.L[a]); }
+                const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                double g = 0.0;
+                if (!((excl >> k) & 1u)) {
+                    if (P.rc2_lj > 0 && r2 <= P.rc2_lj) {
+                        const bool is14 = (m14 >> k) & 1u;
+                        const double a4 = is14 ? li[2] * s_l[wid][s][2] : li[0] * s_l[wid][s][0];
+                        const double sg = is14 ? li[3] + s_l[wid][s][3] : li[1] + s_l[wid][s][1];
+                        const double s2 = sg * sg / r2, s6 = s2 * s2 * s2;
+                        const double t = a4 * s6, w = t * s6;
+                        double e = w - t, gl = (-12.0 * w + 6.0 * t) / r2;
+                        if (P.sw && r2 > P.ron2) {
+                            const double da = P.rc2_lj - r2;
+                            const double S = da * da * (P.rc2_lj + 2.0 * r2 - 3.0 * P.ron2) * P.inv_ab3;
+                            const double dS = 12.0 * P.inv_ab3 * da * (P.ron2 - r2);
+                            gl = gl * S + e * dS;
+                            e *= S;
+                        }
+                        e_lj += e; g += gl;
+                    }
+                    if (P.rc2_c > 0 && r2 <= P.rc2_c) {
+                        const double r = sqrt(r2), ar = P.alpha * r, qq = xi[3] * s_x[wid][s][3];
+                        const double ec = erfc(ar);
+                        e_c += qq * ec / r;
+                        g -= qq * (ec / r + 1.1283791670955126 * P.alpha * exp(-ar * ar)) / r2;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { fi[a] += g * d[a]; fj[a] -= g * d[a]; }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) fj[a] = __shfl_sync(0xffffffffu, fj[a], (lane + 1) & 31);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                if (fj[a] != 0.0) atomic_add_fix(&f_acc[3 * (size_t)j + a], to_fix(fj[a]));
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (fi[a] != 0.0) atomic_add_fix(&f_acc[3 * (size_t)ia + a], to_fix(fi[a]));
+        const long long vl = warp_sum_ll(to_fix(e_lj)), vc = warp_sum_ll(to_fix(e_c));
+        if (lane == 0 && vl) atomic_add_fix(&e_acc[MDK_E_LJ], vl);
+        if (lane == 0 && vc) atomic_add_fix(&e_acc[MDK_E_COUL_DIRECT], vc);
+    }
+}
+
+int pair_compute_f64(mdk_ctx *c, bool do_lj, bool do_coul) {
+    PhaseTimer pt(c, PH_PAIR);
+    PairParams64 P{};
+    for (int a = 0; a < 3; ++a) P.L[a] = c->box.Ld[a];
+    P.rc2_lj = do_lj ? (double)c->rc_lj * c->rc_lj : -1.0;
+    P.ron2 = (double)c->r_switch * c->r_switch;
+    P.sw = do_lj && c->r_switch < c->rc_lj;
+    if (P.sw) { const double a2 = P.rc2_lj, b2 = P.ron2; P.inv_ab3 = 1.0 / ((a2 - b2) * (a2 - b2) * (a2 - b2)); }
+    P.rc2_c = do_coul ? (double)c->rc_coul * c->rc_coul : -1.0;
+    P.alpha = c->alpha; P.sqrt_ke = sqrt(c->k_e); P.n = c->n;
+    MDK_CUDA(c, cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
+    k_pair_f64<<<c->sm_count * 8, 128, 0, c->stream>>>(P, nlist_view(c), c->order.p, c->x_cur.p, do_coul ? c->q64.p : nullptr,
+                                                      do_lj ? c->lj64.p : nullptr, c->f_acc.p, reinterpret_cast<long long *>(c->e_acc.p),
+                                                      c->counters.p + 3);
+    ++c->n_launches; ++c->n_pair_launches;
+    MDK_CUDA(c, cudaGetLastError());
+    return MDK_OK;
+}
+
 int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     if (!do_lj && !do_coul) return MDK_OK;
     if (do_lj && !c->have_lj) return fail(c, MDK_ERR_NOT_BOUND, "LJ term requested before mdk_set_lj");
     if (do_coul && !c->have_coul) return fail(c, MDK_ERR_NOT_BOUND, "Coulomb term requested before mdk_set_coulomb");
+    if (c->dprec && (!do_lj || c->have_lj64) && (!do_coul || c->have_q64)) return pair_compute_f64(c, do_lj, do_coul);
     PhaseTimer pt(c, PH_PAIR);
     PairParams P = make_pair_params(c, do_lj, do_coul);
     NlistView nl = nlist_view(c);

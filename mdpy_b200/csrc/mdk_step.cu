@@ -15,16 +15,23 @@ constexpr int BARE_T = 128;
 __global__ void __launch_bounds__(BARE_T)
 k_coulomb_bare(int n, const float4 *__restrict__ xs, const float *__restrict__ q, const int *__restrict__ order,
                double k_e, double Lx, double Ly, double Lz, long long *__restrict__ f_acc,
-               long long *__restrict__ e_acc) {
+               long long *__restrict__ e_acc, const double *__restrict__ x_cur, const double *__restrict__ q64) {
     __shared__ double4 sj[BARE_T];
     const int i = blockIdx.x * BARE_T + threadIdx.x;
     double xi = 0, yi = 0, zi = 0, qi = 0;
-    if (i < n) { float4 a = xs[i]; xi = a.x; yi = a.y; zi = a.z; qi = k_e * (double)q[order[i]]; }
+    // DOUBLE precision: float64 positions / charges of the state instead of the float32 tile-order copy
+    auto fetch = [&](int k) {
+        const int a = order[k];
+        if (x_cur) return make_double4(x_cur[3 * (size_t)a], x_cur[3 * (size_t)a + 1], x_cur[3 * (size_t)a + 2], q64[a]);
+        const float4 v = xs[k];
+        return make_double4(v.x, v.y, v.z, (double)q[a]);
+    };
+    if (i < n) { const double4 a = fetch(i); xi = a.x; yi = a.y; zi = a.z; qi = k_e * a.w; }
     double fx = 0, fy = 0, fz = 0, e = 0;
     for (int base = 0; base < n; base += BARE_T) {
         int j = base + threadIdx.x;
         double4 v = make_double4(0, 0, 0, 0);
-        if (j < n) { float4 b = xs[j]; v = make_double4(b.x, b.y, b.z, (double)q[order[j]]); }
+        if (j < n) v = fetch(j);
         __syncthreads();
         sj[threadIdx.x] = v;
         __syncthreads();
@@ -55,19 +62,27 @@ k_coulomb_bare(int n, const float4 *__restrict__ xs, const float *__restrict__ q
 __global__ void k_coulomb_bare_excl(int n, int wb, const int *__restrict__ excl_s, const float4 *__restrict__ xs,
                                     const float *__restrict__ q, const int *__restrict__ order, double k_e,
                                     double Lx, double Ly, double Lz, long long *__restrict__ f_acc,
-                                    long long *__restrict__ e_acc) {
+                                    long long *__restrict__ e_acc, const double *__restrict__ x_cur, const double *__restrict__ q64) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
     if (t < n * wb) {
         int k = t / wb;
         int p = excl_s[t];
         if (p > k) {
-            float4 a = xs[k], b = xs[p];
-            double dx = (double)b.x - a.x, dy = (double)b.y - a.y, dz = (double)b.z - a.z;
+            double4 a, b;
+            if (x_cur) {
+                const size_t ia = (size_t)order[k], ib = (size_t)order[p];
+                a = make_double4(x_cur[3 * ia], x_cur[3 * ia + 1], x_cur[3 * ia + 2], 0.0);
+                b = make_double4(x_cur[3 * ib], x_cur[3 * ib + 1], x_cur[3 * ib + 2], 0.0);
+            } else {
+                const float4 fa = xs[k], fb = xs[p];
+                a = make_double4(fa.x, fa.y, fa.z, 0.0); b = make_double4(fb.x, fb.y, fb.z, 0.0);
+            }
+            double dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
             dx -= Lx * rint(dx / Lx); dy -= Ly * rint(dy / Ly); dz -= Lz * rint(dz / Lz);
             double r2 = dx * dx + dy * dy + dz * dz;
             double rinv = rsqrt(r2);
-            double qq = k_e * (double)q[order[k]] * (double)q[order[p]];
+            double qq = q64 ? k_e * q64[order[k]] * q64[order[p]] : k_e * (double)q[order[k]] * (double)q[order[p]];
             e = -qq * rinv;
             double g = qq * rinv * rinv * rinv;  // minus the pair's dE/dr / r
             atomic_add_fix(&f_acc[3 * (size_t)k + 0], to_fix(g * dx));
@@ -86,14 +101,15 @@ int coulomb_bare(mdk_ctx *c) {
     if (!c->have_coul) return fail(c, MDK_ERR_NOT_BOUND, "Coulomb term requested before mdk_set_coulomb");
     PhaseTimer pt(c, PH_BARE);
     long long *e_acc = reinterpret_cast<long long *>(c->e_acc.p);
+    const double *xd = (c->dprec && c->have_q64) ? c->x_cur.p : nullptr, *qd = xd ? c->q64.p : nullptr;
     k_coulomb_bare<<<(c->n + BARE_T - 1) / BARE_T, BARE_T, 0, c->stream>>>(
-        c->n, c->xs.p, c->q.p, c->order.p, c->k_e, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->f_acc.p, e_acc);
+        c->n, c->xs.p, c->q.p, c->order.p, c->k_e, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2], c->f_acc.p, e_acc, xd, qd);
     ++c->n_launches;
     if (c->wb > 0) {
         int total = c->n * c->wb;
         k_coulomb_bare_excl<<<(total + 255) / 256, 256, 0, c->stream>>>(
             c->n, c->wb, c->excl_s.p, c->xs.p, c->q.p, c->order.p, c->k_e, c->box.Ld[0], c->box.Ld[1],
-            c->box.Ld[2], c->f_acc.p, e_acc);
+            c->box.Ld[2], c->f_acc.p, e_acc, xd, qd);
         ++c->n_launches;
     }
     MDK_CUDA(c, cudaGetLastError());
@@ -112,8 +128,25 @@ __device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 
 struct BoxF { double L[3]; };
-__device__ __forceinline__ V3 mi_vec(float4 a, float4 b, const BoxF &bx) {  // b - a, minimum image
-    double dx = (double)b.x - (double)a.x, dy = (double)b.y - (double)a.y, dz = (double)b.z - (double)a.z;
+// where the O(N) terms read positions (and the scaled charge) of a tile slot: the float32 tile-order copy, or — DOUBLE
+// precision — the float64 state itself
+struct P4 { double x, y, z, w; };
+struct PosSrc {
+    const float4 *xs;
+    const double *x_cur, *q64;
+    const int *order;
+    double sqrt_ke;
+    __device__ __forceinline__ P4 operator()(int slot) const {
+        if (x_cur) {
+            const size_t a = (size_t)order[slot];
+            return P4{x_cur[3 * a], x_cur[3 * a + 1], x_cur[3 * a + 2], q64 ? q64[a] * sqrt_ke : 0.0};
+        }
+        const float4 v = xs[slot];
+        return P4{v.x, v.y, v.z, v.w};
+    }
+};
+__device__ __forceinline__ V3 mi_vec(P4 a, P4 b, const BoxF &bx) {  // b - a, minimum image
+    double dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
     return {dx - bx.L[0] * rint(dx / bx.L[0]), dy - bx.L[1] * rint(dy / bx.L[1]), dz - bx.L[2] * rint(dz / bx.L[2])};
 }
 __device__ __forceinline__ void add_force(long long *f_acc, int slot, V3 f) {
@@ -132,13 +165,13 @@ __device__ __forceinline__ void block_energy(double e, long long *e_acc, int whi
 // A term belongs to the rank that owns its first atom (tile slot in [own_lo, own_hi)); every rank walks the whole
 // term list and skips the others' terms.
 __device__ __forceinline__ double term_bond(int t, int own_lo, int own_hi, int nb, const int *__restrict__ idx, const float *__restrict__ par,
-        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
+        const int *__restrict__ inv_order, const PosSrc &xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s1 = t < nb ? inv_order[idx[2 * t]] : -1;
     if (s1 >= own_lo && s1 < own_hi) {
         int s2 = inv_order[idx[2 * t + 1]];
         double k = par[2 * t], r0 = par[2 * t + 1];
-        V3 d = mi_vec(xs[s1], xs[s2], bx);
+        V3 d = mi_vec(xs(s1), xs(s2), bx);
         double r = sqrt(dot(d, d));
         double dr = r - r0;
         e = (k * dr * dr);
@@ -151,13 +184,13 @@ __device__ __forceinline__ double term_bond(int t, int own_lo, int own_hi, int n
 
 // E = k (theta - theta0)^2 + k_ub (r13 - r_ub)^2   (charmm_angle_constraint.py:55-96)
 __device__ __forceinline__ double term_angle(int t, int own_lo, int own_hi, int na, const int *__restrict__ idx, const float *__restrict__ par,
-        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
+        const int *__restrict__ inv_order, const PosSrc &xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s1 = t < na ? inv_order[idx[3 * t]] : -1;
     if (s1 >= own_lo && s1 < own_hi) {
         int s2 = inv_order[idx[3 * t + 1]], s3 = inv_order[idx[3 * t + 2]];
         double k = par[4 * t], th0 = par[4 * t + 1], ku = par[4 * t + 2], u0 = par[4 * t + 3];
-        float4 p1 = xs[s1], p2 = xs[s2], p3 = xs[s3];
+        P4 p1 = xs(s1), p2 = xs(s2), p3 = xs(s3);
         V3 r21 = mi_vec(p2, p1, bx), r23 = mi_vec(p2, p3, bx);
         double l21 = sqrt(dot(r21, r21)), l23 = sqrt(dot(r23, r23));
         double ct = dot(r21, r23) / (l21 * l23);
@@ -188,7 +221,7 @@ __device__ __forceinline__ double term_angle(int t, int own_lo, int own_hi, int 
 
 // Torsion geometry shared by dihedrals and impropers: phi by the reference's atan2
 // convention (utils/geometry.py:84-96), analytic gradient (Blondel & Karplus form).
-__device__ __forceinline__ double torsion(float4 p1, float4 p2, float4 p3, float4 p4, const BoxF &bx, V3 &g1,
+__device__ __forceinline__ double torsion(P4 p1, P4 p2, P4 p3, P4 p4, const BoxF &bx, V3 &g1,
                                          V3 &g2, V3 &g3, V3 &g4) {
     V3 r1 = mi_vec(p1, p2, bx), r2 = mi_vec(p2, p3, bx), r3 = mi_vec(p3, p4, bx);
     V3 n1 = cross(r1, r2), n2 = cross(r2, r3);
@@ -208,7 +241,7 @@ __device__ __forceinline__ double torsion(float4 p1, float4 p2, float4 p3, float
 // E = k (1 + cos(n phi - delta))   (charmm_dihedral_constraint.py:59-95; the force is the
 // analytic gradient of this energy — the reference's `-k (1 - n sin(..))` at :80 is not).
 __device__ __forceinline__ double term_dihedral(int t, int own_lo, int own_hi, int nd, const int *__restrict__ idx, const float *__restrict__ par,
-        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
+        const int *__restrict__ inv_order, const PosSrc &xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s0 = t < nd ? inv_order[idx[4 * t]] : -1;
     if (s0 >= own_lo && s0 < own_hi) {
@@ -216,7 +249,7 @@ __device__ __forceinline__ double term_dihedral(int t, int own_lo, int own_hi, i
         for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
         double k = par[3 * t], nn = par[3 * t + 1], delta = par[3 * t + 2];
         V3 g1, g2, g3, g4;
-        double phi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
+        double phi = torsion(xs(s[0]), xs(s[1]), xs(s[2]), xs(s[3]), bx, g1, g2, g3, g4);
         double arg = nn * phi - delta;
         e = (k * (1. + cos(arg)));
         double dEdphi = -k * nn * sin(arg);
@@ -230,7 +263,7 @@ __device__ __forceinline__ double term_dihedral(int t, int own_lo, int own_hi, i
 
 // E = k (psi - psi0)^2   (charmm_improper_constraint.py:57-94)
 __device__ __forceinline__ double term_improper(int t, int own_lo, int own_hi, int ni, const int *__restrict__ idx, const float *__restrict__ par,
-        const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx, long long *__restrict__ f_acc) {
+        const int *__restrict__ inv_order, const PosSrc &xs, const BoxF &bx, long long *__restrict__ f_acc) {
     double e = 0.0;
     int s0 = t < ni ? inv_order[idx[4 * t]] : -1;
     if (s0 >= own_lo && s0 < own_hi) {
@@ -238,7 +271,7 @@ __device__ __forceinline__ double term_improper(int t, int own_lo, int own_hi, i
         for (int a = 0; a < 4; ++a) s[a] = inv_order[idx[4 * t + a]];
         double k = par[2 * t], psi0 = par[2 * t + 1];
         V3 g1, g2, g3, g4;
-        double psi = torsion(xs[s[0]], xs[s[1]], xs[s[2]], xs[s[3]], bx, g1, g2, g3, g4);
+        double psi = torsion(xs(s[0]), xs(s[1]), xs(s[2]), xs(s[3]), bx, g1, g2, g3, g4);
         double d = psi - psi0;
         e = (k * d * d);
         double dE = 2. * k * d;
@@ -267,17 +300,17 @@ __device__ __forceinline__ double erf_small(double x) {
 // skips; remove -k_e q_i q_j erf(alpha r)/r for each of them.  One thread per excluded pair (a < b, matrix ids; the
 // compact list mdk_set_exclusions builds from the -1-padded bonded_particles table); owner = the owner of atom a.
 __device__ __forceinline__ double term_excl(int t, int own_lo, int own_hi, int n_pairs, const int2 *__restrict__ pairs,
-                                            const int *__restrict__ inv_order, const float4 *__restrict__ xs, const BoxF &bx,
+                                            const int *__restrict__ inv_order, const PosSrc &xs, const BoxF &bx,
                                             double alpha, long long *__restrict__ f_acc) {
     if (t >= n_pairs) return 0.0;
     const int2 pr = pairs[t];
     const int k = inv_order[pr.x];
     if (k < own_lo || k >= own_hi) return 0.0;
     const int p = inv_order[pr.y];
-    const float4 a = xs[k], b = xs[p];
+    const P4 a = xs(k), b = xs(p);
     const V3 d = mi_vec(a, b, bx);
     const double r2 = dot(d, d), r = sqrt(r2);
-    const double qq = (double)a.w * (double)b.w;
+    const double qq = a.w * b.w;
     const double ar = alpha * r, erf_ar = erf_small(ar);
     // dE/dr = -qq (2 alpha/sqrt(pi) exp(-a^2 r^2)/r - erf/r^2);  F_i = dE/dr d/r
     const double g = -qq * (1.1283791670955126 * alpha * exp(-ar * ar) / r - erf_ar / r2) / r;
@@ -299,7 +332,7 @@ struct AuxTable {
 constexpr int AUX_T = 128;
 
 __global__ void __launch_bounds__(AUX_T)
-k_aux_terms(AuxTable tb, int own_lo, int own_hi, const int *__restrict__ inv_order, const float4 *__restrict__ xs, BoxF bx,
+k_aux_terms(AuxTable tb, int own_lo, int own_hi, const int *__restrict__ inv_order, PosSrc xs, BoxF bx,
             double alpha, long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
     int kind = 0;
     while (kind < 4 && (int)blockIdx.x >= tb.blk_off[kind + 1]) ++kind;
@@ -338,7 +371,9 @@ int bonded_compute(mdk_ctx *c, unsigned terms) {
     tb.blk_off[5] = blocks;
     if (blocks == 0) return MDK_OK;
     const int lo = own_first(c), hi = c->own_hi < 0 ? c->n_pad : c->own_hi;
-    k_aux_terms<<<blocks, AUX_T, 0, c->stream>>>(tb, lo, hi, c->inv_order.p, c->xs.p, bx, c->alpha, c->f_acc.p, e_acc);
+    PosSrc ps{c->xs.p, nullptr, nullptr, c->order.p, sqrt(c->k_e)};
+    if (c->dprec && c->have_q64) { ps.x_cur = c->x_cur.p; ps.q64 = c->q64.p; }
+    k_aux_terms<<<blocks, AUX_T, 0, c->stream>>>(tb, lo, hi, c->inv_order.p, ps, bx, c->alpha, c->f_acc.p, e_acc);
     ++c->n_launches;
     MDK_CUDA(c, cudaGetLastError());
     return MDK_OK;

@@ -46,7 +46,7 @@ def close(p, q):
     dx = p[2] - q[2]; dx -= 60.0 * np.round(dx / 60.0)
     df = np.sqrt(((p[0] - q[0]) ** 2).sum() / (q[0] ** 2).sum())
     scale = max(abs(q[1]), abs(q[3]), 1.0)
-    return (bool(df < 1e-6), bool(abs(p[1] - q[1]) < 1e-6 * scale), bool(np.abs(dx).max() < 1e-3), bool(abs(p[3] - q[3]) < 1e-4 * scale)), \
+    return (bool(df < 5e-6), bool(abs(p[1] - q[1]) < 1e-6 * scale), bool(np.abs(dx).max() < 2e-3), bool(abs(p[3] - q[3]) < 1e-4 * scale)), \
         float(df), float(np.abs(dx).max())
 res = {}
 a = run(False)

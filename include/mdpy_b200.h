@@ -243,6 +243,11 @@ MDK_API int mdk_dd_step_langevin_group(mdk_ctx *const *ctxs, int n, double dt, d
 /* out8: own tile slots [lo, hi), halo atoms received per step, own atoms sent per step, exchanges so far, list
  * rebuilds, PME sub-mesh points of this rank, ranks. */
 MDK_API int mdk_dd_stats(mdk_ctx *ctx, int64_t *out8);
+/* Phase trace of the decomposed step (measurement hook): on != 0 makes every phase of the following calls end with a stream
+ * synchronisation and accumulates its wall time; out16 (may be NULL) receives the sums so far in ms: halo positions,
+ * rebuild (state gather / sort + lists / halo lists), O(N) terms + spreading, sub-meshes in, pair kernel, potential boxes out,
+ * gather, halo forces, update, end of call, [12] = steps counted. */
+MDK_API int mdk_dd_trace(mdk_ctx *ctx, int on, double *out16);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64', 'mdk_dd_trace',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -95,6 +95,7 @@ def load_library():
         'mdk_dd_compute_group': (i32, [vp, i32, C.c_uint, vp]),
         'mdk_dd_step_langevin_group': (i32, [vp, i32, f64, f64, f64, u64, i32, C.c_uint, vp]),
         'mdk_dd_stats': (i32, [vp, vp]),
+        'mdk_dd_trace': (i32, [vp, i32, vp]),
         'mdk_set_rigid_waters': (i32, [vp, i32, vp, f64, f64]),
         'mdk_set_precision': (i32, [vp, i32]),
         'mdk_set_params_f64': (i32, [vp, vp, vp]),
@@ -217,6 +218,14 @@ class Device:
         """Spatial domain decomposition (mdk_dd_init): this context becomes rank `rank` of `nranks`, owning one
         domain of the px x py x pz grid.  local_group >= 0: in-process group on one device (tests)."""
         self._ck(self._lib.mdk_dd_init(self._h, int(rank), int(nranks), int(grid[0]), int(grid[1]), int(grid[2]), int(local_group)))
+
+    def dd_trace(self, on=True):
+        """mdk_dd_trace: returns the per-phase wall times (ms) accumulated so far and switches the trace on / off."""
+        out = np.zeros(16, dtype=np.float64)
+        self._ck(self._lib.mdk_dd_trace(self._h, int(bool(on)), _ptr(out)))
+        keys = ['halo_positions', 'rebuild_state_gather', 'rebuild_sort_lists', 'rebuild_halo_lists', 'aux_spread', 'mesh_in', 'pair',
+                'mesh_out', 'gather', 'halo_forces', 'update', 'call_end', 'steps']
+        return dict(zip(keys, out.tolist()))
 
     def dd_stats(self):
         out = np.zeros(8, dtype=np.int64)

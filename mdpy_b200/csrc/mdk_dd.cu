@@ -33,6 +33,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 
 #include "mdk_common.cuh"
@@ -67,7 +68,14 @@ struct DDState {
     char *rbuf = nullptr;
     std::vector<Xfer> xf;
     int64_t stat_exchanges = 0, stat_rebuilds = 0;
+    // trace (mdk_dd_trace): with trace on, every phase ends with a stream synchronisation and its wall time is added up
+    bool trace = false;
+    double t_phase[16] = {0};
+    std::chrono::steady_clock::time_point t_mark;
 };
+enum { TP_HALO_X = 0, TP_REBUILD_GATHER, TP_REBUILD_NLIST, TP_REBUILD_LISTS, TP_AUX_SPREAD, TP_MESH_IN, TP_PAIR, TP_MESH_OUT, TP_GATHER,
+       TP_HALO_F, TP_UPDATE, TP_CALL_END, TP_STEPS };
+
 
 constexpr int PIN_ALL = 8 + 2 * (DD_MAXR + 1);        // pinned words: [0..7] flags, [8..] bounds / own counts, [PIN_ALL..] count matrix
 constexpr int PIN_WORDS = PIN_ALL + DD_MAXR * DD_MAXR + 8;
@@ -199,6 +207,20 @@ __global__ void k_dd_grid_convert(size_t total, long long *__restrict__ fix, flo
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// phase trace
+static void trace_mark(Group &g) {
+    for (mdk_ctx *c : g) if (c->dd->trace) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_pme); cudaStreamSynchronize(c->s_aux); c->dd->t_mark = std::chrono::steady_clock::now(); }
+}
+static void trace_add(Group &g, int phase) {
+    for (mdk_ctx *c : g) if (c->dd->trace) {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_pme); cudaStreamSynchronize(c->s_aux);
+        const auto now = std::chrono::steady_clock::now();
+        c->dd->t_phase[phase] += std::chrono::duration<double, std::milli>(now - c->dd->t_mark).count();
+        c->dd->t_mark = now;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // group plumbing
 static void gsync(Group &g) {
     if (g[0]->dd->local) cudaDeviceSynchronize();     // all members share one device
@@ -307,12 +329,15 @@ static BoxArg box_arg(const mdk_ctx *c, const SubBox &b) {
 // ---------------------------------------------------------------------------------------------------------
 // rebuild: global sort on every rank, own lists, halo lists
 static int dd_rebuild(Group &g) {
+    trace_mark(g);
     MDK_TRY(dd_gather_state(g));
+    trace_add(g, TP_REBUILD_GATHER);
     const int P = g[0]->nranks;
     for (mdk_ctx *c : g) {
         each_set_device(c);
         DDState *d = c->dd;
         MDK_TRY(nlist_rebuild(c));                // keys (domain-major) -> sort -> gathers -> bounds -> own lists (+ marks)
+        if (d->trace) { Group one{c}; trace_add(one, TP_REBUILD_NLIST); }
         // ownership of this rebuild
         MDK_CUDA(c, cudaMemcpyAsync(d->pin + 8, c->dd_blk.p, (DD_MAXR + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MDK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -385,6 +410,7 @@ static int dd_rebuild(Group &g) {
         ++c->dd->stat_rebuilds;
     }
     gsync(g);
+    trace_add(g, TP_REBUILD_LISTS);
     return MDK_OK;
 }
 
@@ -434,12 +460,15 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
         return fail(g[0], MDK_ERR_BAD_ARG, "the all-pairs reference Coulomb sum (MDK_TERM_COUL_BARE) is not domain decomposed");
     bool rebuild = false;
     for (mdk_ctx *c : g) rebuild = rebuild || !c->nlist_valid || !c->xs_current;
+    trace_mark(g);
     if (!rebuild) {
         bool fresh = true;
         for (mdk_ctx *c : g) fresh = fresh && c->dd->fresh;
         if (!fresh) MDK_TRY(dd_halo_positions(g, &rebuild));
     }
+    trace_add(g, TP_HALO_X);
     if (rebuild) MDK_TRY(dd_rebuild(g));
+    trace_mark(g);
     if (rebuild || clear)
         for (mdk_ctx *c : g) { each_set_device(c); MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream)); }
     const bool pme = terms & MDK_TERM_PME_RECIP;
@@ -482,7 +511,9 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
             }
         }
     }
+    trace_add(g, TP_AUX_SPREAD);
     if (pme && P > 1) MDK_TRY(group_exchange(g));
+    trace_add(g, TP_MESH_IN);
     for (mdk_ctx *c : g) {
         each_set_device(c);
         DDState *d = c->dd;
@@ -522,7 +553,9 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
             }
         }
     }
+    trace_add(g, TP_PAIR);
     if (pme && P > 1) MDK_TRY(group_exchange(g));
+    trace_add(g, TP_MESH_OUT);
     for (mdk_ctx *c : g) {
         each_set_device(c);
         DDState *d = c->dd;
@@ -546,6 +579,7 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
             if (r != c->rank && (d->need_cnt[r] || d->send_cnt[r]))
                 d->xf.push_back(Xfer{r, d->need_off[r] * row, d->need_cnt[r] * row, d->send_off[r] * row, d->send_cnt[r] * row});
     }
+    trace_add(g, TP_GATHER);
     MDK_TRY(group_exchange(g));
     for (mdk_ctx *c : g) {
         each_set_device(c);
@@ -555,6 +589,7 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
         MDK_CUDA(c, cudaGetLastError());
     }
     gsync(g);
+    trace_add(g, TP_HALO_F);
     return MDK_OK;
 }
 
@@ -646,13 +681,18 @@ static int dd_langevin_group(Group &g, double dt, double kT, double gamma, uint6
     for (int s = 0; s < nsteps; ++s) {
         MDK_TRY(dd_forces(g, terms, false));          // f(x_n+1)
         const bool more = s + 1 < nsteps;
+        trace_mark(g);
         MDK_TRY(update(more ? 3 : 1));                // mode 3 leaves the own accumulator rows clean for the next step
+        trace_add(g, TP_UPDATE);
         if (more) for (mdk_ctx *c : g) ++c->langevin_step;
+        for (mdk_ctx *c : g) c->dd->t_phase[TP_STEPS] += 1.0;
     }
+    trace_mark(g);
     // the call hands back a complete state on every rank (positions, velocities, forces of the last evaluation)
     MDK_TRY(dd_gather_state(g));
     MDK_TRY(dd_gather_forces(g));
     for (mdk_ctx *c : g) { each_set_device(c); MDK_TRY(energies_enqueue(c)); }
+    trace_add(g, TP_CALL_END);
     if (defer_energies && !g[0]->dd->local) return MDK_OK;     // the caller synchronises once, after queueing its downloads
     for (mdk_ctx *c : g) MDK_CUDA(c, cudaStreamSynchronize(c->stream));
     if (g[0]->dd->local) {
@@ -767,6 +807,18 @@ int mdk_dd_step_langevin_group(mdk_ctx *const *ctxs, int n, double dt, double kT
     for (mdk_ctx *c : g) { cudaSetDevice(c->device); prepare_pme_constants(c); }
     MDK_TRY(dd_langevin_group(g, dt, kT, gamma, seed, nsteps, terms, false));
     if (energies) memcpy(energies, g[0]->last_e, sizeof(g[0]->last_e));
+    return MDK_OK;
+}
+
+/* Phase trace of the decomposed step.  on != 0: every phase of the following calls ends with a stream synchronisation and
+ * its wall time is accumulated; out16 (may be NULL) receives the sums in ms — [0] halo positions (+ flag read-back),
+ * [1] rebuild: state all-gather, [2] rebuild: sort + own lists, [3] rebuild: halo lists, [4] O(N) terms + spreading,
+ * [5] sub-meshes to the mesh rank, [6] pair kernel (+ mesh chain on the mesh rank), [7] potential boxes back,
+ * [8] gather, [9] halo forces, [10] update, [11] end of call (state / force gathers, energies), [12] steps counted. */
+int mdk_dd_trace(mdk_ctx *c, int on, double *out16) {
+    if (!c || !c->dd) return MDK_ERR_BAD_ARG;
+    if (out16) memcpy(out16, c->dd->t_phase, sizeof(c->dd->t_phase));
+    if (on != (c->dd->trace ? 1 : 0)) { memset(c->dd->t_phase, 0, sizeof(c->dd->t_phase)); c->dd->trace = on != 0; }
     return MDK_OK;
 }
 

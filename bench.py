@@ -71,7 +71,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '150'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -104,6 +104,12 @@ class ClockSampler:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+class NoSampler:
+    def __enter__(self): return self
+    def __exit__(self, *a): pass
+    def summary(self): return dict(sm_mhz=None, sm_max_mhz=None, reasons=['not sampled on this rank'])
 
 
 def ns_per_day(steps, seconds, dt_fs):
@@ -440,7 +446,9 @@ def run_b200(args, cfg):
     # ---- timed region.  The clock sampler runs from >= 1 s before the first timed repetition to after the last
     # one, and the GPU does the same steps (untimed) during the pre-roll, so every clock sample is taken under
     # the load that is being timed — however short K steps are.
-    with ClockSampler(local) as clocks:
+    # (one sampler for the job — rank 0's GPU: eight nvidia-smi pollers take the driver lock often enough to slow the
+    # host-launched decomposed step)
+    with (ClockSampler(local) if rank == 0 else NoSampler()) as clocks:
         t_pre = time.perf_counter()
         while time.perf_counter() - t_pre < 1.2:
             w.step(max(args.steps, 20))

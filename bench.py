@@ -440,7 +440,10 @@ def run_b200(args, cfg):
     # ---- multi-GPU: join the communicator, shard the work ----
     grid = (1, 1, 1)
     if world > 1:
-        grid = multigpu.attach(w.ctx, dist, rank, world)   # one spatial domain per rank, halo exchange per step
+        # one spatial domain per rank, halo exchange per step; the mesh rank's domain is smaller by what its mesh chain costs
+        # (single-GPU profile: FFT + influence function, plus the sub-mesh conversions it does for the other ranks)
+        weights = multigpu.domain_weights(world, ph1['pair_ms'], 1.8 * ph1['fft_ms'])
+        grid = multigpu.attach(w.ctx, dist, rank, world, weights=weights)
     w.integ.integrate(w.ens, max(args.warmup, 3))
 
     # ---- timed region.  The clock sampler runs from >= 1 s before the first timed repetition to after the last
@@ -511,7 +514,7 @@ def run_b200(args, cfg):
                     'spatial domain decomposition %d x %d x %d, one domain per rank: halo positions out / halo forces back by grouped '
                     'ncclSend / ncclRecv every step, owner-only integration, PME sub-meshes to / from the mesh rank, state all-gather at '
                     'list rebuilds' % grid,
-                    domain_decomposition=None if world == 1 else dict(grid=list(grid), **dev.dd_stats()),
+                    domain_decomposition=None if world == 1 else dict(grid=list(grid), weights=np.round(weights, 3).tolist(), **dev.dd_stats()),
                     l2='steady-state MD trajectory: every step consumes the previous step\'s output, nothing is re-timed '
                        'on a repeated input; working set %.1f MB (> L2 for this box: %s); l2_flushed_ms_per_step gives the same '
                        'step with a 256 MB L2 flush before it' % ((190.0 * n + 20.0 * K) / 1e6, (190.0 * n + 20.0 * K) > 126e6)),

@@ -242,6 +242,10 @@ MDK_API int mdk_dd_step_langevin_group(mdk_ctx *const *ctxs, int n, double dt, d
                                int nsteps, unsigned terms, double *energies);
 /* out8: own tile slots [lo, hi), halo atoms received per step, own atoms sent per step, exchanges so far, list
  * rebuilds, PME sub-mesh points of this rank, ranks. */
+/* Relative pair-work share of every rank's domain (nranks doubles, the same on all ranks; NULL = equal).  The domains are a
+ * recursive bisection of the cell grid (x, then y inside each x slab, then z inside each column) whose volumes follow the
+ * weights: the rank that also runs the PME mesh chain gets a smaller domain. */
+MDK_API int mdk_dd_set_weights(mdk_ctx *ctx, const double *weights);
 MDK_API int mdk_dd_stats(mdk_ctx *ctx, int64_t *out8);
 /* Phase trace of the decomposed step (measurement hook): on != 0 makes every phase of the following calls end with a stream
  * synchronisation and accumulates its wall time; out16 (may be NULL) receives the sums so far in ms: halo positions,

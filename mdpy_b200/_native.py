@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64', 'mdk_dd_trace',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64', 'mdk_dd_trace', 'mdk_dd_set_weights',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -96,6 +96,7 @@ def load_library():
         'mdk_dd_step_langevin_group': (i32, [vp, i32, f64, f64, f64, u64, i32, C.c_uint, vp]),
         'mdk_dd_stats': (i32, [vp, vp]),
         'mdk_dd_trace': (i32, [vp, i32, vp]),
+        'mdk_dd_set_weights': (i32, [vp, vp]),
         'mdk_set_rigid_waters': (i32, [vp, i32, vp, f64, f64]),
         'mdk_set_precision': (i32, [vp, i32]),
         'mdk_set_params_f64': (i32, [vp, vp, vp]),
@@ -218,6 +219,14 @@ class Device:
         """Spatial domain decomposition (mdk_dd_init): this context becomes rank `rank` of `nranks`, owning one
         domain of the px x py x pz grid.  local_group >= 0: in-process group on one device (tests)."""
         self._ck(self._lib.mdk_dd_init(self._h, int(rank), int(nranks), int(grid[0]), int(grid[1]), int(grid[2]), int(local_group)))
+
+    def dd_set_weights(self, weights):
+        """mdk_dd_set_weights: relative pair-work share of every rank's domain (None = equal)."""
+        if weights is None:
+            self._ck(self._lib.mdk_dd_set_weights(self._h, None))
+        else:
+            w = np.ascontiguousarray(weights, dtype=np.float64)
+            self._ck(self._lib.mdk_dd_set_weights(self._h, _ptr(w)))
 
     def dd_trace(self, on=True):
         """mdk_dd_trace: returns the per-phase wall times (ms) accumulated so far and switches the trace on / off."""
@@ -506,7 +515,7 @@ class LocalGroup:
     transfers done by device-to-device copies.  For tests on a single-GPU box."""
     _next_id = 0
 
-    def __init__(self, ensembles, grid):
+    def __init__(self, ensembles, grid, weights=None):
         self.ensembles = list(ensembles)
         self.ctxs = [context_of(e) for e in self.ensembles]
         n = len(self.ctxs)
@@ -516,6 +525,8 @@ class LocalGroup:
         LocalGroup._next_id += 1
         for r, ctx in enumerate(self.ctxs):
             ctx.dev.dd_init(r, n, grid, local_group=self.group_id)
+            if weights is not None:
+                ctx.dev.dd_set_weights(weights)
             ctx._pos_rev = None
         self._lib = self.ctxs[0].dev._lib
         self._handles = (C.c_void_p * n)(*[ctx.dev._h for ctx in self.ctxs])

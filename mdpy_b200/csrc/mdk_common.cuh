@@ -51,10 +51,15 @@ struct Box {
 // domain (pdim = 1,1,1) reproduces the plain x-fastest numbering.
 constexpr int DD_MAXP = 4;                 // domains per axis
 constexpr int DD_MAXR = DD_MAXP * DD_MAXP * DD_MAXP;
+// The cuts are a recursive bisection: planes across x, then across y inside every x slab, then across z inside every
+// (x, y) column — so the domain volumes can follow per-rank work weights (the rank that also runs the PME mesh gets a
+// smaller domain) while every domain stays a box.
 struct DDGeom {
     int pdim[3];
-    int cut[3][DD_MAXP + 1];               // domain d along axis a covers cells [cut[a][d], cut[a][d+1])
-    int dom_base[DD_MAXR + 1];             // first cell key of each domain, [ndom] = number of cells
+    int cut0[DD_MAXP + 1];                       // x: domain dx covers cells [cut0[dx], cut0[dx+1])
+    int cut1[DD_MAXP][DD_MAXP + 1];              // y inside x slab dx
+    int cut2[DD_MAXP][DD_MAXP][DD_MAXP + 1];     // z inside column (dx, dy)
+    int dom_base[DD_MAXR + 1];                   // first cell key of each domain, [ndom] = number of cells
 };
 
 // kernel-side view of the tile list
@@ -168,8 +173,11 @@ struct mdk_ctx {
     int rank = 0, nranks = 1;
     mdk::DDState *dd = nullptr;               // spatial domain decomposition (mdk_dd.cu); null = single domain
     mdk::DDGeom dd_geom{};                    // cell numbering (one domain unless dd is set)
+    double dd_weight[mdk::DD_MAXR] = {0};     // relative pair-work share of every rank's domain (0 = equal)
     mdk::DevBuf<int> dd_blk;                  // [ndom + 1] first i-block of each domain (device; written by every rebuild)
     mdk::DevBuf<int> dd_mark;                 // [n_pad] 1 = tile slot referenced by this rank's work but owned by another
+    mdk::DevBuf<int> aux_sel[5];              // decomposed runs: indices of the bonded terms / excluded pairs this rank owns (per kind)
+    int aux_sel_n[5] = {-1, -1, -1, -1, -1};  // -1 = no selection (walk the whole list)
     int own_lo = 0, own_hi = -1;              // tile slots this rank owns (integrates, owns the terms of); -1 = all
     int pme_lo = 0, pme_hi = -1;              // tile slots this rank spreads / gathers on the PME mesh: the atoms whose CELL lies in
                                               // its domain (own slots are whole i-blocks; the block that straddles a domain boundary

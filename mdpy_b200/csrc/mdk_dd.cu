@@ -52,7 +52,7 @@ struct DDState {
                                                 // owner) / own slots the peers need (grouped by peer)
     std::vector<int> need_cnt, need_off, send_cnt, send_off;
     int n_need = 0, n_send = 0;
-    DevBuf<int> cnt_dev, cnt_all, n_sel;
+    DevBuf<int> cnt_dev, cnt_all, n_sel, sel_cnt;
     DevBuf<unsigned char> sel_tmp;
     DevBuf<float4> xs_send, xs_recv;            // + one header element per peer at the end
     DevBuf<long long> f_send, f_recv;
@@ -105,6 +105,12 @@ __global__ void k_dd_mark_excl(int n_pairs, const int2 *__restrict__ pairs, cons
     const int k = inv_order[pairs[t].x], p = inv_order[pairs[t].y];
     if (k >= own_lo && k < own_hi && (p < own_lo || p >= own_hi)) mark[p] = 1;     // the pair belongs to the owner of its first atom
 }
+
+// predicate of the own-term selection: the term's (pair's) first atom sits in an own tile slot
+struct OwnTerm {
+    const int *idx; const int *inv_order; int w, lo, hi;
+    __device__ bool operator()(int t) const { const int s = inv_order[idx[(size_t)t * w]]; return s >= lo && s < hi; }
+};
 
 // cnt[r] = number of needed slots owned by rank r (need is ascending; rank r owns slots [blk[r], blk[r+1]))
 __global__ void k_dd_need_counts(const int *__restrict__ need, const int *__restrict__ n_sel, const int *__restrict__ blk,
@@ -304,11 +310,13 @@ static void dd_mesh_boxes(mdk_ctx *c) {
     d->box_off.assign(P + 1, 0);
     for (int r = 0; r < P; ++r) {
         const int dom[3] = {r % gm.pdim[0], (r / gm.pdim[0]) % gm.pdim[1], r / (gm.pdim[0] * gm.pdim[1])};
+        const int cell_lo[3] = {gm.cut0[dom[0]], gm.cut1[dom[0]][dom[1]], gm.cut2[dom[0]][dom[1]][dom[2]]};
+        const int cell_hi[3] = {gm.cut0[dom[0] + 1], gm.cut1[dom[0]][dom[1] + 1], gm.cut2[dom[0]][dom[1]][dom[2] + 1]};
         SubBox &b = d->box[r];
         b.pts = 1;
         for (int a = 0; a < 3; ++a) {
             const double w = c->cellw[a], L = c->box.Ld[a];
-            const double x0 = gm.cut[a][dom[a]] * w - 0.5 * c->skin - 0.05 * w, x1 = gm.cut[a][dom[a] + 1] * w + 0.5 * c->skin + 0.05 * w;
+            const double x0 = cell_lo[a] * w - 0.5 * c->skin - 0.05 * w, x1 = cell_hi[a] * w + 0.5 * c->skin + 0.05 * w;
             const int m = c->pme_n[a];
             int lo = (int)floor(x0 / L * m) - c->pme_order, hi = (int)floor(x1 / L * m) + 2;   // mesh index of x = -L/2 is 0
             int n = hi - lo + 1;
@@ -364,6 +372,25 @@ static int dd_rebuild(Group &g) {
         k_dd_need_counts<<<1, DD_MAXR, 0, c->stream>>>(d->need.p, d->n_sel.p, c->dd_blk.p, P, d->cnt_dev.p);
         c->n_launches += 6;
         MDK_CUDA(c, cudaMemcpyAsync(d->pin + 8, d->cnt_dev.p, P * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        // the bonded terms / excluded pairs this rank owns, as index lists: the O(N) kernel then walks its share only
+        {
+            MDK_CUDA(c, d->sel_cnt.reserve(8));
+            const int nk[5] = {c->bonded[0].n, c->bonded[1].n, c->bonded[2].n, c->bonded[3].n, c->n_excl_pairs};
+            const int *ix[5] = {c->bonded[0].idx.p, c->bonded[1].idx.p, c->bonded[2].idx.p, c->bonded[3].idx.p,
+                                reinterpret_cast<const int *>(c->excl_pairs.p)};
+            for (int k = 0; k < 5; ++k) {
+                c->aux_sel_n[k] = -1;
+                if (nk[k] <= 0) continue;
+                MDK_CUDA(c, c->aux_sel[k].reserve(nk[k]));
+                OwnTerm pred{ix[k], c->inv_order.p, k == 4 ? 2 : width[k], c->own_lo, c->own_hi};
+                size_t tmp2 = 0;
+                cub::DeviceSelect::If(nullptr, tmp2, ids, c->aux_sel[k].p, d->sel_cnt.p + k, nk[k], pred, c->stream);
+                MDK_CUDA(c, d->sel_tmp.reserve(tmp2));
+                MDK_CUDA(c, cub::DeviceSelect::If(d->sel_tmp.p, tmp2, ids, c->aux_sel[k].p, d->sel_cnt.p + k, nk[k], pred, c->stream));
+                c->aux_sel_n[k] = -2;      // count follows with the read-back below
+            }
+            MDK_CUDA(c, cudaMemcpyAsync(d->pin + PIN_WORDS - 8, d->sel_cnt.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        }
     }
     // counts: need_cnt[o] of every rank -> send_cnt[r] = need_cnt of rank r for me
     if (!g[0]->dd->local) {
@@ -390,6 +417,8 @@ static int dd_rebuild(Group &g) {
             d->send_off[r + 1] = d->send_off[r] + d->send_cnt[r];
         }
         d->n_need = d->need_off[P]; d->n_send = d->send_off[P];
+        for (int k = 0; k < 5; ++k)
+            if (c->aux_sel_n[k] == -2) c->aux_sel_n[k] = d->pin[PIN_WORDS - 8 + k];
         MDK_CUDA(c, d->sendl.reserve(d->n_send + 1));
         MDK_CUDA(c, d->xs_send.reserve(d->n_send + P)); MDK_CUDA(c, d->xs_recv.reserve(d->n_need + P));
         MDK_CUDA(c, d->f_send.reserve(3 * (size_t)d->n_need + 3)); MDK_CUDA(c, d->f_recv.reserve(3 * (size_t)d->n_send + 3));
@@ -730,6 +759,8 @@ void dd_destroy(mdk_ctx *c) {
             if (!any) g_groups.erase(it);
         }
     }
+    d->sel_cnt.release();
+    for (int k = 0; k < 5; ++k) { c->aux_sel[k].release(); c->aux_sel_n[k] = -1; }
     d->need.release(); d->sendl.release(); d->cnt_dev.release(); d->cnt_all.release(); d->n_sel.release(); d->sel_tmp.release();
     d->xs_send.release(); d->xs_recv.release(); d->f_send.release(); d->f_recv.release(); d->st_buf.release();
     d->m_send.release(); d->m_recv.release();
@@ -815,6 +846,17 @@ int mdk_dd_step_langevin_group(mdk_ctx *const *ctxs, int n, double dt, double kT
  * [1] rebuild: state all-gather, [2] rebuild: sort + own lists, [3] rebuild: halo lists, [4] O(N) terms + spreading,
  * [5] sub-meshes to the mesh rank, [6] pair kernel (+ mesh chain on the mesh rank), [7] potential boxes back,
  * [8] gather, [9] halo forces, [10] update, [11] end of call (state / force gathers, energies), [12] steps counted. */
+/* Relative pair-work share of every rank's domain (nranks doubles; NULL = equal): the domain volumes follow the weights, so a
+ * rank with extra duties (the PME mesh rank) can be given a smaller domain.  Every rank must pass the same weights. */
+int mdk_dd_set_weights(mdk_ctx *c, const double *weights) {
+    if (!c || !c->dd) return MDK_ERR_BAD_ARG;
+    for (int r = 0; r < DD_MAXR; ++r) c->dd_weight[r] = (weights && r < c->nranks) ? weights[r] : 0.0;
+    for (int r = 0; weights && r < c->nranks; ++r)
+        if (!(weights[r] > 0)) return fail(c, MDK_ERR_BAD_ARG, "mdk_dd_set_weights: weight %d = %g is not positive", r, weights[r]);
+    c->nlist_valid = false;
+    return MDK_OK;
+}
+
 int mdk_dd_trace(mdk_ctx *c, int on, double *out16) {
     if (!c || !c->dd) return MDK_ERR_BAD_ARG;
     if (out16) memcpy(out16, c->dd->t_phase, sizeof(c->dd->t_phase));

@@ -36,12 +36,16 @@ struct GridParams {
     int dd_rank, dd_nranks;   // nranks > 1: this rank builds the lists of its own domain's i-blocks only
 };
 
-// domain index and first / one-past-last cell of the domain that holds cell c along one axis
-__host__ __device__ __forceinline__ int dd_axis_domain(const DDGeom &d, int a, int c, int &lo, int &hi) {
+// index of the interval of a cut array that holds cell c; lo / hi = its first / one-past-last cell
+__host__ __device__ __forceinline__ int dd_find(const int *cut, int p, int c, int &lo, int &hi) {
     int k = 0;
-    while (k + 1 < d.pdim[a] && c >= d.cut[a][k + 1]) ++k;
-    lo = d.cut[a][k]; hi = d.cut[a][k + 1];
+    while (k + 1 < p && c >= cut[k + 1]) ++k;
+    lo = cut[k]; hi = cut[k + 1];
     return k;
+}
+// x slab of cell column cx (the list builder walks rows in pieces that stay inside one slab)
+__host__ __device__ __forceinline__ int dd_axis_domain(const DDGeom &d, int a, int c, int &lo, int &hi) {
+    return dd_find(d.cut0, d.pdim[0], c, lo, hi);   // only axis 0 is asked for
 }
 // key of cell (cx, cy, cz): cells of one domain are contiguous, x fastest.  Along an axis that is cut, the walk
 // is a serpentine (x runs backwards on every other row, y on every other plane), so that consecutive cells — and
@@ -49,7 +53,9 @@ __host__ __device__ __forceinline__ int dd_axis_domain(const DDGeom &d, int a, i
 // uncut axis the periodic wrap already makes the row end and the next row's start neighbours.
 __host__ __device__ __forceinline__ int dd_cell_key(const DDGeom &d, int cx, int cy, int cz) {
     int lx, hx, ly, hy, lz, hz;
-    const int dx = dd_axis_domain(d, 0, cx, lx, hx), dy = dd_axis_domain(d, 1, cy, ly, hy), dz = dd_axis_domain(d, 2, cz, lz, hz);
+    const int dx = dd_find(d.cut0, d.pdim[0], cx, lx, hx);
+    const int dy = dd_find(d.cut1[dx], d.pdim[1], cy, ly, hy);
+    const int dz = dd_find(d.cut2[dx][dy], d.pdim[2], cz, lz, hz);
     const int dom = (dz * d.pdim[1] + dy) * d.pdim[0] + dx;
     const int nx = hx - lx, ny = hy - ly, pz = cz - lz;
     int py = cy - ly, px = cx - lx;
@@ -527,25 +533,61 @@ static int nlist_plan(mdk_ctx *c) {
         ncells *= nc;
     }
     c->n_cells = ncells;
-    // cell numbering: one domain, or the domain grid of mdk_dd_init (cuts at equal cell counts per axis)
+    // cell numbering: one domain, or the domain grid of mdk_dd_init — recursive bisection of the cell grid by the ranks'
+    // work weights (equal weights: equal cell counts)
     {
         DDGeom &d = c->dd_geom;
         const DDGeom before = d;
+        int p[3];
         for (int a = 0; a < 3; ++a) {
-            int p = c->dd ? d.pdim[a] : 1;
-            if (p < 1) p = 1;
-            if (p > c->ncell[a]) return fail(c, MDK_ERR_BAD_ARG, "domain grid %d along axis %d exceeds the %d cells of the box", p, a, c->ncell[a]);
-            d.pdim[a] = p;
-            for (int k = 0; k <= p; ++k) d.cut[a][k] = (int)((long long)k * c->ncell[a] / p);
-            for (int k = p + 1; k <= DD_MAXP; ++k) d.cut[a][k] = c->ncell[a];
+            p[a] = c->dd ? d.pdim[a] : 1;
+            if (p[a] < 1) p[a] = 1;
+            if (p[a] > c->ncell[a]) return fail(c, MDK_ERR_BAD_ARG, "domain grid %d along axis %d exceeds the %d cells of the box", p[a], a, c->ncell[a]);
+            d.pdim[a] = p[a];
+        }
+        auto weight = [&](int dx, int dy, int dz) {
+            const double w = c->dd ? c->dd_weight[(dz * p[1] + dy) * p[0] + dx] : 1.0;
+            return w > 0 ? w : 1.0;
+        };
+        // cut `cells` cells into n intervals proportional to w[0..n), every interval at least one cell
+        auto split = [&](int cells, int n, const double *w, int *cut) {
+            double tot = 0; for (int k = 0; k < n; ++k) tot += w[k];
+            double acc = 0;
+            cut[0] = 0;
+            for (int k = 1; k < n; ++k) {
+                acc += w[k - 1];
+                int v = (int)floor(cells * acc / tot + 0.5);
+                if (v < cut[k - 1] + 1) v = cut[k - 1] + 1;
+                if (v > cells - (n - k)) v = cells - (n - k);
+                cut[k] = v;
+            }
+            for (int k = n; k <= DD_MAXP; ++k) cut[k] = cells;
+        };
+        double wx[DD_MAXP] = {0};
+        for (int dx = 0; dx < p[0]; ++dx)
+            for (int dy = 0; dy < p[1]; ++dy)
+                for (int dz = 0; dz < p[2]; ++dz) wx[dx] += weight(dx, dy, dz);
+        split(c->ncell[0], p[0], wx, d.cut0);
+        for (int dx = 0; dx < DD_MAXP; ++dx) {
+            double wy[DD_MAXP] = {0};
+            for (int dy = 0; dy < p[1]; ++dy)
+                for (int dz = 0; dz < p[2]; ++dz) wy[dy] += dx < p[0] ? weight(dx, dy, dz) : 1.0;
+            split(c->ncell[1], p[1], wy, d.cut1[dx]);
+            for (int dy = 0; dy < DD_MAXP; ++dy) {
+                double wz[DD_MAXP] = {0};
+                for (int dz = 0; dz < p[2]; ++dz) wz[dz] = (dx < p[0] && dy < p[1]) ? weight(dx, dy, dz) : 1.0;
+                split(c->ncell[2], p[2], wz, d.cut2[dx][dy]);
+            }
         }
         int base = 0, dom = 0;
-        for (int dz = 0; dz < d.pdim[2]; ++dz)
-            for (int dy = 0; dy < d.pdim[1]; ++dy)
-                for (int dx = 0; dx < d.pdim[0]; ++dx) {
-                    d.dom_base[dom++] = base;
-                    base += (d.cut[0][dx + 1] - d.cut[0][dx]) * (d.cut[1][dy + 1] - d.cut[1][dy]) * (d.cut[2][dz + 1] - d.cut[2][dz]);
-                }
+        int size[DD_MAXR] = {0};
+        for (int dz = 0; dz < p[2]; ++dz)
+            for (int dy = 0; dy < p[1]; ++dy)
+                for (int dx = 0; dx < p[0]; ++dx)
+                    size[(dz * p[1] + dy) * p[0] + dx] = (d.cut0[dx + 1] - d.cut0[dx]) * (d.cut1[dx][dy + 1] - d.cut1[dx][dy]) *
+                                                         (d.cut2[dx][dy][dz + 1] - d.cut2[dx][dy][dz]);
+        const int ndom = p[0] * p[1] * p[2];
+        for (dom = 0; dom < ndom; ++dom) { d.dom_base[dom] = base; base += size[dom]; }
         for (; dom <= DD_MAXR; ++dom) d.dom_base[dom] = base;
         if (memcmp(&before, &d, sizeof(d)) != 0) ++c->graph_epoch;   // kernel arguments of captured rebuilds
     }

@@ -328,6 +328,7 @@ struct AuxTable {
     const int *idx[4];
     const float *par[4];
     const int2 *pairs;
+    const int *sel[5];       // decomposed runs: the terms this rank owns (indices into the full lists), or null
 };
 constexpr int AUX_T = 128;
 
@@ -336,7 +337,12 @@ k_aux_terms(AuxTable tb, int own_lo, int own_hi, const int *__restrict__ inv_ord
             double alpha, long long *__restrict__ f_acc, long long *__restrict__ e_acc) {
     int kind = 0;
     while (kind < 4 && (int)blockIdx.x >= tb.blk_off[kind + 1]) ++kind;
-    const int t = ((int)blockIdx.x - tb.blk_off[kind]) * AUX_T + threadIdx.x;
+    int t = ((int)blockIdx.x - tb.blk_off[kind]) * AUX_T + threadIdx.x;
+    int nk = tb.n[kind];
+    if (tb.sel[kind]) {           // n[kind] counts the selection: map to the term's index in the full list
+        if (t < nk) { t = tb.sel[kind][t]; nk = t + 1; } else { t = 0; nk = 0; }
+    }
+    tb.n[kind] = nk;
     double e = 0.0;
     int slot = MDK_E_BOND;
     switch (kind) {
@@ -359,12 +365,16 @@ int bonded_compute(mdk_ctx *c, unsigned terms) {
     AuxTable tb{};
     int blocks = 0;
     for (int k = 0; k < 4; ++k) {
-        tb.n[k] = (terms & bit[k]) ? c->bonded[k].n : 0;
+        const bool sel = c->dd && c->aux_sel_n[k] >= 0;
+        tb.n[k] = (terms & bit[k]) ? (sel ? c->aux_sel_n[k] : c->bonded[k].n) : 0;
+        tb.sel[k] = sel ? c->aux_sel[k].p : nullptr;
         tb.idx[k] = c->bonded[k].idx.p; tb.par[k] = c->bonded[k].par.p;
         tb.blk_off[k] = blocks;
         blocks += (tb.n[k] + AUX_T - 1) / AUX_T;
     }
-    tb.n[4] = (terms & MDK_TERM_PME_RECIP) ? c->n_excl_pairs : 0;
+    const bool sel4 = c->dd && c->aux_sel_n[4] >= 0;
+    tb.n[4] = (terms & MDK_TERM_PME_RECIP) ? (sel4 ? c->aux_sel_n[4] : c->n_excl_pairs) : 0;
+    tb.sel[4] = sel4 ? c->aux_sel[4].p : nullptr;
     tb.pairs = c->excl_pairs.p;
     tb.blk_off[4] = blocks;
     blocks += (tb.n[4] + AUX_T - 1) / AUX_T;

@@ -41,9 +41,24 @@ def broadcast_unique_id(dist, dev, rank):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach(ctx, dist, rank, world, grid=None):
+def domain_weights(world, pair_ms, mesh_ms):
+    """Relative pair-work share of every rank's domain such that all ranks finish together when the LAST rank also runs
+    the PME mesh chain (mesh_ms; FFTs, influence function, sub-mesh traffic) next to its share of the pair work
+    (pair_ms = the single-GPU pair-kernel time):  pair_ms * w_r / world + extra_r = T.  The mesh rank never drops below
+    a fifth of an equal share (its domain must still hold cells)."""
+    if world == 1:
+        return np.ones(1)
+    share = pair_ms / world
+    T = share + mesh_ms / world
+    w = np.full(world, T / share)
+    w[-1] = max((T - mesh_ms) / share, 0.2)
+    return w / w.mean()
+
+
+def attach(ctx, dist, rank, world, grid=None, weights=None):
     """Join this rank's device context to the job: NCCL communicator + its domain of the grid.  Afterwards
-    Ensemble.update / LangevinIntegrator.integrate on this ensemble are collective calls."""
+    Ensemble.update / LangevinIntegrator.integrate on this ensemble are collective calls.  weights: relative pair-work
+    share of every rank's domain (domain_weights); they are broadcast from rank 0 so that all ranks cut the same domains."""
     import os
     import sys
     dev = ctx.dev
@@ -61,6 +76,8 @@ def attach(ctx, dist, rank, world, grid=None):
         os.dup2(saved, 1)
         os.close(saved)
     dev.dd_init(rank, world, grid)
+    if weights is not None:
+        dev.dd_set_weights(broadcast_array(dist, np.asarray(weights, dtype=np.float64), rank))
     ctx._pos_rev = None          # the next call re-uploads the State: every rank starts from the same complete state
     ctx.domain_grid = grid
     return grid

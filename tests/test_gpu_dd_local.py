@@ -108,3 +108,22 @@ def test_decomposed_pair_sets_partition_the_single_domain_set(single):
     assert share.max() < 1.25 * share.min(), share                            # the seam pairs are shared out evenly
     for c in group.ctxs:
         c.dev.close()
+
+
+def test_weighted_domains_shrink_the_mesh_rank_and_change_nothing_else(single):
+    """mdk_dd_set_weights: the domains are a recursive bisection whose volumes follow the ranks' work weights (the rank
+    that also runs the PME mesh chain gets less pair work); forces and energies are those of the single domain."""
+    s = single['system']
+    weights = [1.1, 1.1, 1.1, 1.1, 1.1, 1.1, 1.1, 0.3]
+    group = _native.LocalGroup([make_ensemble(s) for _ in range(8)], (2, 2, 2), weights=weights)
+    e0, forces = group.compute()
+    assert rel_rms(forces[0], single['f0']) < 5e-6 and rel_rms(forces[7], single['f0']) < 5e-6
+    assert np.abs(e0[:10] - single['e0'][:10]).max() < 1e-6 * np.abs(single['e0'][:10]).sum()
+    stats = [c.dev.dd_stats() for c in group.ctxs]
+    sizes = np.array([st['own_hi'] - st['own_lo'] for st in stats])
+    assert sizes.sum() == s.num_particles
+    assert sizes[7] < 0.6 * sizes[:7].mean(), sizes            # cut at cell granularity: 8 cells per axis here
+    e = group.step_langevin(0.5, KT, 0.05, 5, 30)
+    assert np.isfinite(e).all()
+    for c in group.ctxs:
+        c.dev.close()

@@ -93,6 +93,7 @@ struct mdk_ctx {
     cudaStream_t s_pme = nullptr, s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_pme = nullptr, ev_aux = nullptr;
     bool concurrent = true;
+    bool pair_v5 = true;                      // filter-then-compute pair kernel (option 8; 0 = the rotation-ring kernel)
     int pair_blocks_per_sm = 4;               // persistent k_pair blocks per SM (4 fill the register file; fewer leave room for the side-stream kernels)
     std::string err;
 

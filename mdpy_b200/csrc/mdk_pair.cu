@@ -247,6 +247,231 @@ __device__ __forceinline__ void pair_unit(const PairParams &P, const NlistView &
     }
 }
 
+// ---------------------------------------------------------------------------
+// Filter-then-compute variant of the unit body ("v5").  The rotation scheme above evaluates the whole interaction
+// for the warp whenever ANY lane's slot is inside the cutoff; with 20-30 % of the slots inside, 40 % of the lanes do
+// useful work in the expensive part.  Here a chunk goes through three passes:
+//   1. filter   lane l (i-atom l) computes r^2 against all 32 staged j (broadcast LDS, 10 instructions per slot) and
+//               keeps a bit mask of the slots inside the cutoff (exclusions removed);
+//   2. compute  every lane walks ITS OWN set bits: full interaction for that pair, i-force and energies accumulate in
+//               registers, the scalar g = (dE/dr)/r goes to a shared 32 x 32 table;
+//   3. scatter  the mask is transposed (5 shuffle stages); lane s (j-atom s) walks the i-atoms that interact with it,
+//               reads g from the table, rebuilds d from the staged positions and accumulates the j-force in registers.
+// Trip counts are max over lanes of the bit counts (~16 at 30 % density instead of 32), nothing goes through atomics
+// or changes summation order from run to run: forces stay bitwise reproducible.  The cutoff decision of the SHIFT
+// variant is re-taken on the canonical expression in pass 2 for slots within the band (table entry 0 if it fails).
+constexpr int G_STRIDE = 33;     // skewed rows: bank = (l + s) mod 32
+
+__device__ __forceinline__ unsigned transpose32(unsigned x, const int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned k = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned other = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? (((other >> j) & k) | (x & ~k)) : ((x & k) | ((other & k) << j));
+    }
+    return x;
+}
+
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool EMIT>
+__device__ __forceinline__ void pair_unit_v5(const PairParams &P, const NlistView &nl, const int4 unit, const float4 *__restrict__ xs,
+                                             const float4 *__restrict__ ljs, const float4 *__restrict__ bbc,
+                                             long long *__restrict__ f_acc, float4 *__restrict__ s_x, float4 *__restrict__ s_lj,
+                                             float4 *__restrict__ s_xi, float *__restrict__ s_g, const int lane,
+                                             long long &e_lj_tot, long long &e_c_tot, const EmitOut &em) {
+    const int ia = unit.x * TILE + lane;
+    float4 xi = xs[ia];
+    const float4 li = ljs[ia];
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (SHIFT) {
+        const float4 c = bbc[unit.x];
+        cx = c.x; cy = c.y; cz = c.z;
+        xi.x = min_image(xi.x - cx, P.L[0], P.invL[0]);
+        xi.y = min_image(xi.y - cy, P.L[1], P.invL[1]);
+        xi.z = min_image(xi.z - cz, P.L[2], P.invL[2]);
+    }
+    __syncwarp();
+    s_xi[lane] = xi;
+    float fix = 0.f, fiy = 0.f, fiz = 0.f;
+    float e_lj = 0.f, e_c = 0.f;
+
+    for (int cidx = 0; cidx < unit.z; ++cidx) {
+        const int chunk = unit.y + cidx;
+        const int j = nl.chunk_j[(size_t)chunk * 32 + lane];
+        const int mslot = nl.chunk_mask[chunk];
+        float4 xj_own = xs[j];
+        if (SHIFT) {
+            xj_own.x = min_image(xj_own.x - cx, P.L[0], P.invL[0]);
+            xj_own.y = min_image(xj_own.y - cy, P.L[1], P.invL[1]);
+            xj_own.z = min_image(xj_own.z - cz, P.L[2], P.invL[2]);
+        }
+        __syncwarp();
+        s_x[lane] = xj_own;
+        if (DO_LJ) s_lj[lane] = ljs[j];
+        unsigned excl = 0u, m14 = 0u;
+        if (mslot >= 0) {     // stored rotated for the ring kernel (bit k <-> slot (lane + k) & 31): un-rotate
+            const unsigned er = nl.mask_excl[(size_t)mslot * 32 + lane];
+            excl = __funnelshift_l(er, er, lane);
+            if (DO_LJ) { const unsigned mr = nl.mask_14[(size_t)mslot * 32 + lane]; m14 = __funnelshift_l(mr, mr, lane); }
+        }
+        __syncwarp();
+        // ---- pass 1: filter
+        unsigned m = 0u;
+        const float lim = SHIFT ? P.max_hi : P.rc2_max;
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl) {
+            const float4 xj = s_x[sl];
+            float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+            if (!SHIFT) {
+                dx = min_image(dx, P.L[0], P.invL[0]);
+                dy = min_image(dy, P.L[1], P.invL[1]);
+                dz = min_image(dz, P.L[2], P.invL[2]);
+            }
+            if (dist2(dx, dy, dz) <= lim) m |= 1u << sl;
+        }
+        m &= ~excl;
+        // ---- pass 2: the interaction for the surviving pairs of this lane
+        unsigned mm = m;
+        while (__any_sync(0xffffffffu, mm != 0u)) {
+            if (mm) {
+                const int sl = __ffs(mm) - 1;
+                mm &= mm - 1u;
+                const float4 xj = s_x[sl];
+                float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+                if (!SHIFT) {
+                    dx = min_image(dx, P.L[0], P.invL[0]);
+                    dy = min_image(dy, P.L[1], P.invL[1]);
+                    dz = min_image(dz, P.L[2], P.invL[2]);
+                }
+                const float r2 = dist2(dx, dy, dz);
+                float r2d = r2;
+                bool in = true;
+                if (SHIFT) {
+                    bool near = r2 > P.max_lo;
+                    if (!ONECUT) near = near || (r2 > P.lj_lo && r2 <= P.lj_hi) || (r2 > P.c_lo && r2 <= P.c_hi);
+                    if (near) {
+                        r2d = canonical_r2(P.L[0], P.L[1], P.L[2], P.invL[0], P.invL[1], P.invL[2], xs, ia, nl.chunk_j[(size_t)chunk * 32 + sl]);
+                        in = r2d <= P.rc2_max;
+                    }
+                }
+                float g = 0.f;
+                if (in) {
+                    if (EMIT) {
+                        const unsigned long long pos = atomicAdd(em.count, 1ull);
+                        if (pos < em.cap) {
+                            const int a = em.order[ia], b = em.order[nl.chunk_j[(size_t)chunk * 32 + sl]];
+                            em.out_i[pos] = a < b ? a : b;
+                            em.out_j[pos] = a < b ? b : a;
+                        }
+                    }
+                    const float rinv = rsqrt_approx(r2);
+                    const float r2inv = rinv * rinv;
+                    if (DO_LJ) {
+                        if (ONECUT || r2d <= P.rc2_lj) {
+                            const float4 lj = s_lj[sl];
+                            float a = li.x * lj.x, sg = li.y + lj.y;             // 4 eps_ij, sigma_ij
+                            if ((m14 >> sl) & 1u) { a = li.z * lj.z; sg = li.w + lj.w; }
+                            const float s2 = sg * sg * r2inv;
+                            const float s6 = s2 * s2 * s2;
+                            const float t = a * s6, w = t * s6;
+                            float e = w - t;
+                            float gl = fmaf(-12.f, w, 6.f * t) * r2inv;
+                            if (SWITCH) {
+                                if (r2 > P.ron2) {
+                                    const float da = P.rc2_lj - r2;
+                                    const float S = da * da * fmaf(2.f, r2, P.sw_c0) * P.inv_ab3;
+                                    const float dS = P.sw_12inv * da * (P.ron2 - r2);
+                                    gl = fmaf(gl, S, e * dS);
+                                    e *= S;
+                                }
+                            }
+                            if (ENERGY) e_lj += e;
+                            g = gl;
+                        }
+                    }
+                    if (DO_COUL) {
+                        if (ONECUT || r2d <= P.rc2_c) {
+                            const float u = xi.w * xj.w * ex2_approx(-P.alpha2_log2e * r2);
+                            const float v = erfcx_poly(P.alpha * (r2 * rinv)) * rinv;
+                            if (ENERGY) e_c = fmaf(u, v, e_c);
+                            g = fmaf(-u, (v + P.two_alpha_over_sqrtpi) * r2inv, g);
+                        }
+                    }
+                    fix = fmaf(g, dx, fix); fiy = fmaf(g, dy, fiy); fiz = fmaf(g, dz, fiz);
+                }
+                s_g[lane * G_STRIDE + sl] = g;
+            }
+        }
+        __syncwarp();
+        // ---- pass 3: the same pairs seen from the j side
+        unsigned mt = transpose32(m, lane);
+        float fjx = 0.f, fjy = 0.f, fjz = 0.f;
+        while (__any_sync(0xffffffffu, mt != 0u)) {
+            if (mt) {
+                const int il = __ffs(mt) - 1;
+                mt &= mt - 1u;
+                const float g = s_g[il * G_STRIDE + lane];
+                const float4 xo = s_xi[il];
+                float dx = xj_own.x - xo.x, dy = xj_own.y - xo.y, dz = xj_own.z - xo.z;
+                if (!SHIFT) {
+                    dx = min_image(dx, P.L[0], P.invL[0]);
+                    dy = min_image(dy, P.L[1], P.invL[1]);
+                    dz = min_image(dz, P.L[2], P.invL[2]);
+                }
+                fjx = fmaf(-g, dx, fjx); fjy = fmaf(-g, dy, fjy); fjz = fmaf(-g, dz, fjz);
+            }
+        }
+        if (fjx != 0.f || fjy != 0.f || fjz != 0.f) {
+            atomic_add_fix(&f_acc[3 * (size_t)j + 0], to_fix(fjx));
+            atomic_add_fix(&f_acc[3 * (size_t)j + 1], to_fix(fjy));
+            atomic_add_fix(&f_acc[3 * (size_t)j + 2], to_fix(fjz));
+        }
+    }
+    if (fix != 0.f || fiy != 0.f || fiz != 0.f) {
+        atomic_add_fix(&f_acc[3 * (size_t)ia + 0], to_fix(fix));
+        atomic_add_fix(&f_acc[3 * (size_t)ia + 1], to_fix(fiy));
+        atomic_add_fix(&f_acc[3 * (size_t)ia + 2], to_fix(fiz));
+    }
+    if (ENERGY) {
+        e_lj_tot += to_fix((double)e_lj);
+        e_c_tot += to_fix((double)e_c);
+    }
+}
+
+template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool EMIT = false>
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+k_pair5(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
+        const float4 *__restrict__ bbc, long long *__restrict__ f_acc, long long *__restrict__ e_acc,
+        int *__restrict__ cursor, EmitOut em) {
+    __shared__ float4 s_x[PAIR_WARPS][32];
+    __shared__ float4 s_lj[PAIR_WARPS][32];
+    __shared__ float4 s_xi[PAIR_WARPS][32];
+    __shared__ float s_g[PAIR_WARPS][32 * G_STRIDE];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n_units = *nl.n_units;
+    long long e_lj_tot = 0, e_c_tot = 0;
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(cursor, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const int4 unit = nl.units[u];
+        if (SHIFT && unit.w)
+            pair_unit_v5<DO_LJ, DO_COUL, SWITCH, false, ONECUT, ENERGY, EMIT>(P, nl, unit, xs, ljs, bbc, f_acc, s_x[wid], s_lj[wid], s_xi[wid],
+                                                                             s_g[wid], lane, e_lj_tot, e_c_tot, em);
+        else
+            pair_unit_v5<DO_LJ, DO_COUL, SWITCH, SHIFT, ONECUT, ENERGY, EMIT>(P, nl, unit, xs, ljs, bbc, f_acc, s_x[wid], s_lj[wid], s_xi[wid],
+                                                                             s_g[wid], lane, e_lj_tot, e_c_tot, em);
+    }
+    if (ENERGY && DO_LJ) {
+        long long v = warp_sum_ll(e_lj_tot);
+        if (lane == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_LJ], v);
+    }
+    if (ENERGY && DO_COUL) {
+        long long v = warp_sum_ll(e_c_tot);
+        if (lane == 0 && v != 0) atomic_add_fix(&e_acc[MDK_E_COUL_DIRECT], v);
+    }
+}
+
 template <bool DO_LJ, bool DO_COUL, bool SWITCH, bool SHIFT, bool ONECUT, bool ENERGY, bool EMIT = false>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *__restrict__ ljs,
@@ -459,8 +684,14 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     // it 18 % slower than the energy-carrying one, so that combination keeps ENERGY on)
     const bool energy = !c->in_capture || c->graph_energy || c->capture_energy || sw;   // the inner steps of a graph run never report energies
 #define LAUNCH(LJ, CO, SW, SH, OC, EN)                                                                          \
-    k_pair<LJ, CO, SW, SH, OC, EN><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
-                                                             c->e_acc.p, cursor, EmitOut{})
+    do {                                                                                                          \
+        if (c->pair_v5)                                                                                           \
+            k_pair5<LJ, CO, SW, SH, OC, EN><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
+                                                                    c->e_acc.p, cursor, EmitOut{});                \
+        else                                                                                                      \
+            k_pair<LJ, CO, SW, SH, OC, EN><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, c->f_acc.p, \
+                                                                   c->e_acc.p, cursor, EmitOut{});                 \
+    } while (0)
 #define PICK_EN(LJ, CO, SW, SH, OC) do { if (energy) LAUNCH(LJ, CO, SW, SH, OC, true); else LAUNCH(LJ, CO, SW, SH, OC, false); } while (0)
 #define PICK_OC(LJ, CO, SW, SH) do { if (onecut) PICK_EN(LJ, CO, SW, SH, true); else PICK_EN(LJ, CO, SW, SH, false); } while (0)
 #define PICK_SH(LJ, CO, SW) do { if (shift) PICK_OC(LJ, CO, SW, true); else PICK_OC(LJ, CO, SW, false); } while (0)
@@ -561,9 +792,16 @@ int pair_enumerate(mdk_ctx *c, int32_t *out_i, int32_t *out_j, int64_t cap, int6
         dim3 g(c->sm_count * c->pair_blocks_per_sm), b(PAIR_WARPS * 32);
         NlistView nl = nlist_view(c);
 #define EMIT_LAUNCH(CO, SW, SH)                                                                                    \
-        k_pair<true, CO, SW, SH, true, true, true><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, \
-                                                                           scratch, scratch + (size_t)c->n_pad * 3, \
-                                                                           c->counters.p + 3, em)
+        do {                                                                                                       \
+            if (c->pair_v5)                                                                                        \
+                k_pair5<true, CO, SW, SH, true, true, true><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, \
+                                                                                scratch, scratch + (size_t)c->n_pad * 3, \
+                                                                                c->counters.p + 3, em);                  \
+            else                                                                                                   \
+                k_pair<true, CO, SW, SH, true, true, true><<<g, b, 0, c->stream>>>(P, nl, c->xs.p, c->ljs.p, c->bb_center.p, \
+                                                                               scratch, scratch + (size_t)c->n_pad * 3, \
+                                                                               c->counters.p + 3, em);                   \
+        } while (0)
 #define EMIT_SH(CO, SW) do { if (shift) EMIT_LAUNCH(CO, SW, true); else EMIT_LAUNCH(CO, SW, false); } while (0)
         if (do_coul) { if (sw) EMIT_SH(true, true); else EMIT_SH(true, false); }
         else         { if (sw) EMIT_SH(false, true); else EMIT_SH(false, false); }

@@ -839,7 +839,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 5: c->pair_blocks_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value); break;
         case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;   // cuFFT also for small power-of-two meshes
         case 7: c->spread_smem = value != 0; break;        // shared-memory staged charge spreading (default on)
-        case 8: c->pair_v5 = value != 0; break;            // filter-then-compute pair kernel (default on)
+        case 8: c->pair_v5 = value != 0; break;            // filter-then-compute pair kernel (default off: measured slower)
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

@@ -93,7 +93,8 @@ struct mdk_ctx {
     cudaStream_t s_pme = nullptr, s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_pme = nullptr, ev_aux = nullptr;
     bool concurrent = true;
-    bool pair_v5 = true;                      // filter-then-compute pair kernel (option 8; 0 = the rotation-ring kernel)
+    bool pair_v5 = false;                     // filter-then-compute pair kernel (option 8).  Off: measured 415 vs 344 us at 92k, 69 vs 54 us
+                                              // at 23k — the per-lane bit counts are too uneven
     int pair_blocks_per_sm = 4;               // persistent k_pair blocks per SM (4 fill the register file; fewer leave room for the side-stream kernels)
     std::string err;
 

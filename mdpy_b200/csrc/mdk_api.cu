@@ -840,6 +840,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 6: c->pme_force_cufft = value != 0; c->pme_dirty = true; break;   // cuFFT also for small power-of-two meshes
         case 7: c->spread_smem = value != 0; break;        // shared-memory staged charge spreading (default on)
         case 8: c->pair_v5 = value != 0; break;            // filter-then-compute pair kernel (default off: measured slower)
+        case 9: c->unit_waves = value < 0.25 ? 0.25 : value; c->nlist_valid = false; break;   // work units per resident warp (list granularity)
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

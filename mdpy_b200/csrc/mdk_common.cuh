@@ -170,6 +170,7 @@ struct mdk_ctx {
     bool force_canonical = false;             // test hook: always the per-pair canonical minimum image
     bool shift_ok = false;                    // box large enough to hoist the minimum image out of the pair loop
     int seg_chunks = 8;
+    double unit_waves = 2.0;                  // work units per resident warp the list planner aims for (option 9)
     int64_t stat_units = 0, stat_chunks = 0, stat_masks = 0;
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;

@@ -598,8 +598,10 @@ static int nlist_plan(mdk_ctx *c) {
     // work-unit granularity: enough units to fill the machine a few times over
     double per_block = rho * (4.0 / 3.0) * M_PI * R * R * R * 0.5 * 2.2 / 32.0 + 1.0;  // chunks (estimate)
     double total_chunks = per_block * c->n_blocks;
-    double want_units = 8.0 * c->sm_count * 8;  // ~8 resident warps per SM, 8 waves
-    int seg = (int)(total_chunks / want_units);
+    // enough units to fill the machine's resident warps (4 blocks x 8 warps per SM) unit_waves times over: the tail of a
+    // launch is one unit long, so more, shorter units balance better (a decomposed rank lists only its share of the chunks)
+    double want_units = 32.0 * c->sm_count * c->unit_waves;
+    int seg = (int)(total_chunks / (c->dd ? c->nranks : 1) / want_units);
     if (seg < 2) seg = 2;
     if (seg > 16) seg = 16;
     c->seg_chunks = seg;

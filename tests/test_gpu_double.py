@@ -77,7 +77,8 @@ def test_double_precision_switch_and_erfc_direct_space_match_float64_oracle():
     lj.update()
     assert rel_rms(lj.forces, t['f_lj']) < 5e-9          # fixed-point resolution (1.8e-9 measured; SINGLE: 3e-6)
     assert abs(lj.potential_energy - t['e_lj']) < 1e-9 * t['e_lj_abs']
-    e = _native.context_of(ens).compute(pme.terms)
+    pme.update()
+    e = _native.context_of(ens).dev.last_energies()
     assert abs(e[_native.E_COUL_DIRECT] - t['e_coul']) < 1e-9 * t['e_coul_abs']
     assert e[_native.E_PME_EXCL] == pytest.approx(t['e_excl'], rel=1e-9)
     # SINGLE on the same system for scale: the float32 pair kernel sits at ~3e-6

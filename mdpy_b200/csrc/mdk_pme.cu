@@ -97,11 +97,10 @@ __global__ void k_spread(PmeParams p, const float4 *__restrict__ xs, long long *
 // independent of how the atoms are grouped into blocks (each contribution is rounded to 2^-26 on its own).
 // A block whose atoms span more mesh than fits (a block that wraps a cell row, a dilute system) falls back to
 // direct global atomics.
-constexpr int SPREAD_T = 256;
 constexpr int SPREAD_CAP = 15360;            // ints of dynamic shared memory (60 KB)
 constexpr float SPREAD_SCALE = 67108864.f;   // 2^26; global mesh = 2^40
 
-template <int P>
+template <int P, int SPREAD_T>
 __global__ void __launch_bounds__(SPREAD_T)
 k_spread_smem(PmeParams p, const float4 *__restrict__ xs, long long *__restrict__ grid) {
     extern __shared__ int s_mesh[];
@@ -529,10 +528,10 @@ int pme_prepare(mdk_ctx *c) {
     }
     {
         const int smem = SPREAD_CAP * (int)sizeof(int);
-        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#define SPREAD_ATTR(P) MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<P, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+                       MDK_CUDA(c, cudaFuncSetAttribute(k_spread_smem<P, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+        SPREAD_ATTR(4); SPREAD_ATTR(5); SPREAD_ATTR(6); SPREAD_ATTR(8);
+#undef SPREAD_ATTR
     }
     c->pme_dirty = false;
     return MDK_OK;
@@ -556,15 +555,22 @@ int pme_spread(mdk_ctx *c) {
     const int cnt = p.n - p.first;
     if (cnt <= 0) return MDK_OK;
     if (c->spread_smem) {
-        const int B = (cnt + SPREAD_T - 1) / SPREAD_T;
+        // 256 atoms per block merge more contributions per global atomic; small systems take 128 so that the launch
+        // still covers the machine (23k atoms: 92 blocks of 256 would leave a third of the SMs idle)
+        const bool small = cnt < 256 * c->sm_count * 2;
+        const int T = small ? 128 : 256;
+        const int B = (cnt + T - 1) / T;
         const size_t smem = SPREAD_CAP * sizeof(int);
+#define SPREAD(P) do { if (small) k_spread_smem<P, 128><<<B, 128, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); \
+                       else k_spread_smem<P, 256><<<B, 256, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); } while (0)
         switch (c->pme_order) {
-            case 4: k_spread_smem<4><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
-            case 5: k_spread_smem<5><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
-            case 6: k_spread_smem<6><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
-            case 8: k_spread_smem<8><<<B, SPREAD_T, smem, c->stream>>>(p, c->xs.p, c->grid_fix.p); break;
+            case 4: SPREAD(4); break;
+            case 5: SPREAD(5); break;
+            case 6: SPREAD(6); break;
+            case 8: SPREAD(8); break;
             default: return fail(c, MDK_ERR_BAD_ARG, "PME order %d not supported (4, 5, 6, 8)", c->pme_order);
         }
+#undef SPREAD
         c->n_launches += 1;
         MDK_CUDA(c, cudaGetLastError());
         return MDK_OK;

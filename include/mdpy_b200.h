@@ -182,6 +182,13 @@ MDK_API int mdk_step_langevin_host(mdk_ctx *ctx, const float *x_in, const float 
  * energy_first_prev_last[3] = potential energy before the first, before the last and after the last iteration. */
 MDK_API int mdk_minimize_sd(mdk_ctx *ctx, double alpha, double energy_tolerance, int max_iterations, unsigned terms,
                     int *iterations, double *energy_first_prev_last, double *energies);
+/* Trajectory frames for the dumpers (reference: mdpy/dumper/*.py read ensemble.state.positions once per dump period).
+ * stride > 0: every stride-th step of a following step call leaves the wrapped float32 positions [n,3] in a page-locked
+ * ring of max_frames frames, copied out by a separate copy stream while the next steps run.  mdk_get_frames waits for
+ * the copies, hands the frames over (at most max_frames into out; *n_frames = frames captured since the last hand-over)
+ * and rewinds the ring.  stride = 0 switches the capture off.  Single domain. */
+MDK_API int mdk_set_frame_capture(mdk_ctx *ctx, int stride, int max_frames);
+MDK_API int mdk_get_frames(mdk_ctx *ctx, float *out, int max_frames, int *n_frames);
 /* Page-locked host memory owned by the ctx (freed by mdk_destroy at the latest): State arrays that
  * live in it move to / from the device by DMA without a staging copy. */
 MDK_API int mdk_host_alloc(mdk_ctx *ctx, size_t bytes, void **out);

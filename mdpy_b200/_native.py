@@ -41,7 +41,7 @@ EXPORTS = [
     'mdk_download_forces', 'mdk_download_forces_f64', 'mdk_step_verlet', 'mdk_verlet_reset', 'mdk_step_langevin',
     'mdk_last_energies', 'mdk_get_pairs', 'mdk_get_timing', 'mdk_set_profiling', 'mdk_force_accumulator',
     'mdk_flush_l2', 'mdk_comm_unique_id', 'mdk_comm_init', 'mdk_set_option',
-    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64', 'mdk_dd_trace', 'mdk_dd_set_weights',
+    'mdk_dd_init', 'mdk_dd_compute_group', 'mdk_dd_step_langevin_group', 'mdk_dd_stats', 'mdk_minimize_sd', 'mdk_set_rigid_waters', 'mdk_set_precision', 'mdk_set_params_f64', 'mdk_dd_trace', 'mdk_dd_set_weights', 'mdk_set_frame_capture', 'mdk_get_frames',
     'mdk_step_langevin_host', 'mdk_host_alloc', 'mdk_host_free', 'mdk_get_pairs_production',
 ]
 
@@ -97,6 +97,8 @@ def load_library():
         'mdk_dd_stats': (i32, [vp, vp]),
         'mdk_dd_trace': (i32, [vp, i32, vp]),
         'mdk_dd_set_weights': (i32, [vp, vp]),
+        'mdk_set_frame_capture': (i32, [vp, i32, i32]),
+        'mdk_get_frames': (i32, [vp, vp, i32, C.POINTER(i32)]),
         'mdk_set_rigid_waters': (i32, [vp, i32, vp, f64, f64]),
         'mdk_set_precision': (i32, [vp, i32]),
         'mdk_set_params_f64': (i32, [vp, vp, vp]),
@@ -308,6 +310,17 @@ class Device:
 
     def step_langevin(self, dt, kT, gamma, seed, nsteps, terms):
         self._ck(self._lib.mdk_step_langevin(self._h, float(dt), float(kT), float(gamma), int(seed), int(nsteps), int(terms)))
+
+    def set_frame_capture(self, stride, max_frames):
+        """mdk_set_frame_capture: keep the wrapped float32 positions of every stride-th step (0 = off)."""
+        self._ck(self._lib.mdk_set_frame_capture(self._h, int(stride), int(max_frames)))
+
+    def get_frames(self, max_frames):
+        """mdk_get_frames -> float32 [k, n, 3]: the frames captured since the last call."""
+        out = np.empty((int(max_frames), self.n, 3), dtype=np.float32)
+        cnt = C.c_int(0)
+        self._ck(self._lib.mdk_get_frames(self._h, _ptr(out), int(max_frames), C.byref(cnt)))
+        return out[:min(cnt.value, int(max_frames))]
 
     def minimize_sd(self, alpha, energy_tolerance, max_iterations, terms):
         """mdk_minimize_sd -> (iterations, (E_first, E_before_last, E_last), energies[16])."""

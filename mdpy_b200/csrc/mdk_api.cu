@@ -245,6 +245,10 @@ void mdk_destroy(mdk_ctx *c) {
     c->grid_fix.release(); c->grid_r.release(); c->grid_c.release(); c->influence.release(); c->fft_tw.release();
     c->io_dev.release();
     if (c->io_host) cudaFreeHost(c->io_host);
+    if (c->frame_host) cudaFreeHost(c->frame_host);
+    c->frame_dev.release();
+    if (c->s_io) cudaStreamDestroy(c->s_io);
+    for (int k = 0; k < 2; ++k) { if (c->ev_frame_ready[k]) cudaEventDestroy(c->ev_frame_ready[k]); if (c->ev_frame_done[k]) cudaEventDestroy(c->ev_frame_done[k]); }
     if (c->pin_words) cudaFreeHost(c->pin_words);
     for (auto &b : c->pinned) cudaFreeHost(b.first);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -642,6 +646,46 @@ int mdk_minimize_sd(mdk_ctx *c, double alpha, double energy_tolerance, int max_i
     MDK_TRY(minimize_sd(c, alpha, energy_tolerance, max_iterations, terms, iterations, energy_first_prev_last, energy_first_prev_last + 1,
                         energy_first_prev_last + 2));
     if (energies) memcpy(energies, c->last_e, sizeof(c->last_e));
+    return MDK_OK;
+}
+
+int mdk_set_frame_capture(mdk_ctx *c, int stride, int max_frames) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (stride < 0 || max_frames < 0 || (stride > 0 && max_frames == 0)) return fail(c, MDK_ERR_BAD_ARG, "mdk_set_frame_capture(%d, %d)", stride, max_frames);
+    if (c->s_io) cudaStreamSynchronize(c->s_io);
+    c->frame_stride = 0; c->frame_count = 0; c->frame_total = 0;
+    if (stride == 0) return MDK_OK;
+    if (c->n <= 0) return fail(c, MDK_ERR_NOT_BOUND, "mdk_set_frame_capture before mdk_set_atoms");
+    const size_t m = (size_t)3 * c->n;
+    if (!c->s_io) {
+        MDK_CUDA(c, cudaStreamCreateWithFlags(&c->s_io, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            MDK_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame_ready[k], cudaEventDisableTiming));
+            MDK_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame_done[k], cudaEventDisableTiming));
+        }
+    }
+    MDK_CUDA(c, c->frame_dev.reserve(2 * m));
+    if (max_frames > c->frame_cap) {
+        if (c->frame_host) cudaFreeHost(c->frame_host);
+        c->frame_host = nullptr; c->frame_cap = 0;
+        MDK_CUDA(c, cudaHostAlloc(reinterpret_cast<void **>(&c->frame_host), (size_t)max_frames * m * sizeof(float), cudaHostAllocDefault));
+        c->frame_cap = max_frames;
+    }
+    c->frame_stride = stride;
+    ++c->graph_epoch;
+    return MDK_OK;
+}
+
+int mdk_get_frames(mdk_ctx *c, float *out, int max_frames, int *n_frames) {
+    NEED_CTX(c);
+    cudaSetDevice(c->device);
+    if (!n_frames || max_frames < 0 || (max_frames > 0 && !out)) return fail(c, MDK_ERR_BAD_ARG, "mdk_get_frames: bad arguments");
+    if (c->s_io) MDK_CUDA(c, cudaStreamSynchronize(c->s_io));
+    const int k = c->frame_count < max_frames ? c->frame_count : max_frames;
+    if (k > 0) memcpy(out, c->frame_host, (size_t)k * 3 * c->n * sizeof(float));
+    *n_frames = c->frame_count;
+    c->frame_count = 0;            // the ring is handed over: the next call fills it from the start
     return MDK_OK;
 }
 

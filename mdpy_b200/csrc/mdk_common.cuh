@@ -227,6 +227,15 @@ struct mdk_ctx {
     long long graph_epoch = 0, graph_epoch_built = -1;
     int graph_launches_per_step = 0;
 
+    // ---- trajectory frames (mdk_set_frame_capture): wrapped float32 positions every `stride` steps of a step call, copied
+    // to page-locked host memory by a copy stream while the steps go on ----
+    int frame_stride = 0, frame_cap = 0, frame_count = 0;
+    long long frame_total = 0;                // frames captured since the capture was switched on
+    mdk::DevBuf<float> frame_dev;             // [2][3 n] double-buffered staging
+    float *frame_host = nullptr;              // pinned [frame_cap][3 n]
+    cudaStream_t s_io = nullptr;
+    cudaEvent_t ev_frame_ready[2] = {nullptr, nullptr}, ev_frame_done[2] = {nullptr, nullptr};
+
     // ---- host transfer staging ----
     mdk::DevBuf<unsigned char> io_dev;
     void *io_host = nullptr;
@@ -322,6 +331,7 @@ void dd_destroy(mdk_ctx *c);
 int langevin_launch(mdk_ctx *c, int first, int end, int mode, double dt, double ca, double cb, double tg, uint64_t seed, uint64_t step);
 void prepare_pme_constants(mdk_ctx *c);
 int rigid_project(mdk_ctx *c);
+int frame_capture_enqueue(mdk_ctx *c, int step_in_call);   // no-op unless this step is a multiple of the capture stride
 
 // ---------------------------------------------------------------------------
 // device helpers

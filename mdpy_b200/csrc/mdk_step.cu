@@ -967,6 +967,36 @@ int integrate_verlet(mdk_ctx *c, double dt, int nsteps, unsigned terms, int quir
 }
 
 // ===========================================================================
+// Trajectory frames (the on-disk side of the loop; reference dumpers: mdpy/dumper/*.py call
+// ensemble.state.positions once per dump period from the host).  With a capture stride set, a step call copies the
+// wrapped float32 positions of every stride-th step into a page-locked ring on the host: a small kernel on the step
+// stream writes them to one of two staging buffers, a copy stream moves them out while the next steps run.
+__global__ void k_frame(int n, const double *__restrict__ x_cur, double Lx, double Ly, double Lz, float *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * n) return;
+    const int d = i % 3;
+    const double L = d == 0 ? Lx : (d == 1 ? Ly : Lz), x = x_cur[i];
+    out[i] = (float)(x - L * rint(x / L));
+}
+
+int frame_capture_enqueue(mdk_ctx *c, int step_in_call) {
+    if (c->frame_stride <= 0 || step_in_call % c->frame_stride != 0 || c->frame_count >= c->frame_cap) return MDK_OK;
+    const int slot = c->frame_count & 1;
+    const size_t m = (size_t)3 * c->n;
+    MDK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_frame_done[slot], 0));          // the copy that last used this staging buffer
+    k_frame<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->n, c->x_cur.p, c->box.Ld[0], c->box.Ld[1], c->box.Ld[2],
+                                                               c->frame_dev.p + slot * m);
+    ++c->n_launches;
+    MDK_CUDA(c, cudaEventRecord(c->ev_frame_ready[slot], c->stream));
+    MDK_CUDA(c, cudaStreamWaitEvent(c->s_io, c->ev_frame_ready[slot], 0));
+    MDK_CUDA(c, cudaMemcpyAsync(c->frame_host + (size_t)c->frame_count * m, c->frame_dev.p + slot * m, m * sizeof(float),
+                                cudaMemcpyDeviceToHost, c->s_io));
+    MDK_CUDA(c, cudaEventRecord(c->ev_frame_done[slot], c->s_io));
+    ++c->frame_count; ++c->frame_total;
+    return MDK_OK;
+}
+
+// ===========================================================================
 // Steepest descent (mdpy/minimizer/steepest_descent_minimizer.py:30-53): every atom moves a fixed
 // length alpha along ITS OWN unit force vector, x_i += alpha F_i / |F_i| (the reference normalises per atom,
 // np.linalg.norm(forces, axis=1)); the loop stops when the relative change of the potential energy between two
@@ -1194,6 +1224,7 @@ static int graph_run_langevin(mdk_ctx *c, double dt, double ca, double cb, doubl
     MDK_CUDA(c, cudaMemcpyAsync(c->step_dev.p, h_words, sizeof(h_words), cudaMemcpyHostToDevice, c->stream));
     for (int s = 0; s < nsteps; ++s) {
         const bool last = s + 1 == nsteps;
+        MDK_TRY(frame_capture_enqueue(c, s + 1));     // x_cur holds the positions after s + 1 steps of this call
         if (last && nsteps > 1) { k_set_word<<<1, 1, 0, c->stream>>>(c->step_dev.p + 1, 1ull); ++c->n_launches; }
         MDK_CUDA(c, cudaGraphLaunch(c->upkeep_exec, c->stream));
         MDK_CUDA(c, cudaGraphLaunch(c->step_exec[last ? 1 : 0], c->stream));
@@ -1264,6 +1295,7 @@ int integrate_langevin(mdk_ctx *c, double dt, double kT, double gamma, uint64_t 
         MDK_TRY(graph_run_langevin(c, dt, ca, cb, tg, seed, terms, nsteps, hosted));
     } else {
         for (int s = 0; s < nsteps; ++s) {
+            MDK_TRY(frame_capture_enqueue(c, s + 1));
             MDK_TRY(compute_terms(c, terms, false));  // f(x_n+1)
             const bool more = s + 1 < nsteps;
             LANGEVIN(more ? 3 : 1);

@@ -30,6 +30,8 @@ struct GridParams {
     int ncell[3];
     float inv_cw[3];
     float R, R2;
+    float Rn2;            // class radius^2 of the list order: j-atoms with an i-atom of the block within it come first ("near"),
+                          // the rest (skin shell only) last; < 0: one class
     float skin_half2;
     float wide_lim[3];    // a block whose bounding-box half extent exceeds this on an axis is "wide": canonical minimum image
     DDGeom dd;            // cell numbering: domain by domain
@@ -301,6 +303,11 @@ struct BlockEmitter {
 __device__ __forceinline__ int imod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
 constexpr int BUILD_WARPS = 4;
+// j-atoms that pass the list filter but have no i-atom of the block within the cutoff itself (they sit in the skin shell:
+// ~30 % of a list at rc 12 / skin 2) wait here and are emitted after the block's other atoms, so they end up in chunks of
+// their own.  In those chunks k_pair finds (almost) nothing inside the cutoff and every rotation step leaves after the
+// distance test — 16 instead of 80 warp instructions; mixed into the other chunks they would cost full steps.
+constexpr int FAR_CAP = 1024;
 
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
 k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const float4 *__restrict__ bbc,
@@ -308,9 +315,11 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
               const int *__restrict__ excl_s, int wb, const int *__restrict__ p14_s, int ws,
               BuildOut o) {
     __shared__ int stage_all[BUILD_WARPS][64];
+    __shared__ int far_all[BUILD_WARPS][FAR_CAP];
     __shared__ float4 s_xi[BUILD_WARPS][32];
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int *stage = stage_all[wid];
+    int *stage = stage_all[wid], *farb = far_all[wid];
+    const bool split = g.Rn2 > 0.f;
     int warp_global = blockIdx.x * BUILD_WARPS + wid, n_warps = gridDim.x * BUILD_WARPS;
     // domain decomposition: this rank lists the i-blocks of its own domain only.  Pairs inside the domain are
     // taken half shell by tile index as on one GPU; a pair of blocks that straddles two domains is taken by the
@@ -339,9 +348,14 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
         em.excl_s = excl_s; em.p14_s = p14_s; em.wb = wb; em.ws = ws; em.o = o;
         // i-atom positions of this block for the exact filter (ragged lanes repeat the first atom)
         __syncwarp();
-        {   // i-atom positions for the exact filter; lanes this rank does not own repeat an own atom of the block
+        {   // i-atom positions for the exact filter, relative to the block centre; lanes this rank does not own repeat an
+            // own atom of the block
             const unsigned vm = __ballot_sync(0xffffffffu, em.i_valid);
-            s_xi[wid][lane] = xs[em.i_valid ? my_slot : b * TILE + (vm ? __ffs(vm) - 1 : 0)];
+            float4 q = xs[em.i_valid ? my_slot : b * TILE + (vm ? __ffs(vm) - 1 : 0)];
+            q.x = min_image(q.x - c.x, g.L[0], g.invL[0]);
+            q.y = min_image(q.y - c.y, g.L[1], g.invL[1]);
+            q.z = min_image(q.z - c.z, g.L[2], g.invL[2]);
+            s_xi[wid][lane] = q;
         }
         __syncwarp();
         em.begin();
@@ -363,7 +377,8 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
             lo[a] = imod(l0, g.ncell[a]);
             len[a] = ln;
         }
-        int nstage = 0;
+        int nstage = 0, nfar = 0;
+        const float R2m = g.R2 * (1.f + 2e-5f);    // the hoisted differences round differently from the pair kernel's
         for (int iz = 0; iz < len[2]; ++iz) {
             int zz = lo[2] + iz; if (zz >= g.ncell[2]) zz -= g.ncell[2];
             for (int iy = 0; iy < len[1]; ++iy) {
@@ -389,7 +404,7 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                     for (int base = s; base < e; base += 32) {
                         if (base >= skip_lo && base + 32 <= skip_hi) continue;   // a whole stride of own atoms at or before this block
                         int j = base + lane;
-                        bool pass = false, unsure = false;
+                        bool pass = false, near = !split;
                         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                         bool cand = j < e;
                         if (multi && cand) {
@@ -397,42 +412,52 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                             if (j >= own_lo && j < own_hi) cand = bj > b;
                             else cand = ((b + bj) & 1) ? (bj < b) : (bj > b);
                         }
+                        float hx = 0.f, hy = 0.f, hz = 0.f;
                         if (cand) {
                             p = xs[j];
-                            float dx = fmaxf(fabsf(min_image(p.x - cc[0], g.L[0], g.invL[0])) - hh[0], 0.f);
-                            float dy = fmaxf(fabsf(min_image(p.y - cc[1], g.L[1], g.invL[1])) - hh[1], 0.f);
-                            float dz = fmaxf(fabsf(min_image(p.z - cc[2], g.L[2], g.invL[2])) - hh[2], 0.f);
-                            unsure = (dx * dx + dy * dy + dz * dz) <= g.R2;
-                            // quick accept: within R of one of four representative i-atoms
+                            hx = min_image(p.x - cc[0], g.L[0], g.invL[0]);
+                            hy = min_image(p.y - cc[1], g.L[1], g.invL[1]);
+                            hz = min_image(p.z - cc[2], g.L[2], g.invL[2]);
+                            const float dx = fmaxf(fabsf(hx) - hh[0], 0.f), dy = fmaxf(fabsf(hy) - hh[1], 0.f),
+                                        dz = fmaxf(fabsf(hz) - hh[2], 0.f);
+                            cand = dx * dx + dy * dy + dz * dz <= R2m;     // within R of the bounding box
+                        }
+                        if (!__any_sync(0xffffffffu, cand)) continue;
+                        // exact filter (the box test alone keeps ~25 % more atoms than needed): lane = candidate, smallest
+                        // distance to the 32 i-atoms, which sit in shared memory relative to the block centre
+                        float dmin = 3.0e38f;
+                        if (!em.wide) {
 #pragma unroll
-                            for (int t = 3; t < 32 && unsure && !pass; t += 8) {
+                            for (int t = 0; t < 32; ++t) {
                                 const float4 q = s_xi[wid][t];
-                                const float ex = min_image(p.x - q.x, g.L[0], g.invL[0]);
-                                const float ey = min_image(p.y - q.y, g.L[1], g.invL[1]);
-                                const float ez = min_image(p.z - q.z, g.L[2], g.invL[2]);
-                                if (dist2(ex, ey, ez) <= g.R2) pass = true;
+                                dmin = fminf(dmin, dist2(hx - q.x, hy - q.y, hz - q.z));
                             }
-                            unsure = unsure && !pass;
+                        } else {          // the block is too wide for one image per atom: minimum image per pair
+#pragma unroll 4
+                            for (int t = 0; t < 32; ++t) {
+                                const float4 q = s_xi[wid][t];
+                                dmin = fminf(dmin, dist2(min_image(hx - q.x, g.L[0], g.invL[0]), min_image(hy - q.y, g.L[1], g.invL[1]),
+                                                         min_image(hz - q.z, g.L[2], g.invL[2])));
+                            }
                         }
-                        // exact filter for the rest (the box test alone keeps ~25 % more atoms than needed):
-                        // the warp tests one candidate against all 32 i-atoms at a time
-                        unsigned todo = __ballot_sync(0xffffffffu, unsure);
-                        const float4 qi = s_xi[wid][lane];
-                        while (todo) {
-                            const int src = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const float px = __shfl_sync(0xffffffffu, p.x, src), py = __shfl_sync(0xffffffffu, p.y, src),
-                                        pz = __shfl_sync(0xffffffffu, p.z, src);
-                            const float ex = min_image(px - qi.x, g.L[0], g.invL[0]);
-                            const float ey = min_image(py - qi.y, g.L[1], g.invL[1]);
-                            const float ez = min_image(pz - qi.z, g.L[2], g.invL[2]);
-                            const bool hit = __any_sync(0xffffffffu, dist2(ex, ey, ez) <= g.R2);
-                            if (lane == src) pass = hit;
-                        }
-                        unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) stage[nstage + __popc(bal & ((1u << lane) - 1u))] = j;
+                        pass = cand && dmin <= R2m;
+                        if (split) near = dmin <= g.Rn2;
+                        const bool p_near = pass && near, p_far = pass && !near;
+                        unsigned bal = __ballot_sync(0xffffffffu, p_near);
+                        if (p_near) stage[nstage + __popc(bal & ((1u << lane) - 1u))] = j;
                         nstage += __popc(bal);
+                        if (split) {
+                            bal = __ballot_sync(0xffffffffu, p_far);
+                            if (p_far) farb[nfar + __popc(bal & ((1u << lane) - 1u))] = j;
+                            nfar += __popc(bal);
+                        }
                         __syncwarp();
+                        if (nfar > FAR_CAP - 32) {       // buffer full: a chunk of far atoms goes out early
+                            const int jj = farb[nfar - 32 + lane];
+                            nfar -= 32;
+                            __syncwarp();
+                            em.emit(jj, false);
+                        }
                         if (nstage >= 32) {
                             int jj = stage[lane];
                             int rest = stage[32 + lane];
@@ -446,7 +471,13 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                 }
             }
         }
-        if (nstage > 0) em.emit(lane < nstage ? stage[lane] : -1, false);
+        if (nstage > 0) {      // the last near atoms, topped up with far ones
+            const int take = min(32 - nstage, nfar);
+            const int jj = lane < nstage ? stage[lane] : (lane - nstage < take ? farb[nfar - take + lane - nstage] : -1);
+            nfar -= take;
+            em.emit(jj, false);
+        }
+        for (int base = 0; base < nfar; base += 32) em.emit(base + lane < nfar ? farb[base + lane] : -1, false);
         __syncwarp();
         em.close_unit();
     }
@@ -465,6 +496,7 @@ static GridParams make_grid_params(mdk_ctx *c) {
     float rc = fmaxf(c->have_lj ? c->rc_lj : 0.f, c->have_coul ? c->rc_coul : 0.f);
     g.R = rc + c->skin;
     g.R2 = g.R * g.R;
+    g.Rn2 = c->far_split ? rc * rc : -1.f;
     for (int a = 0; a < 3; ++a) g.wide_lim[a] = 0.5f * c->box.L[a] - g.R - 0.05f;
     g.skin_half2 = 0.25f * c->skin * c->skin;
     g.dd = c->dd_geom;

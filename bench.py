@@ -219,7 +219,7 @@ class Workload:
         self.dev = self.ctx.dev
         self.kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
         self.dt = cfg['dt']
-        self.skin = float(cfg.get('skin', 2.0))
+        self.skin = float(os.environ.get('MDK_SKIN', cfg.get('skin', 2.0)))   # experiments: MDK_SKIN=2.5
         if self.skin != 2.0:
             self.dev.set_nlist(self.skin)
         if args.no_graph:

@@ -226,7 +226,9 @@ MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64
  * 7 = shared-memory staged charge spreading (default 1; 0 = one global atomic per spline point), 8 = filter-then-compute
  * pair kernel (default 0 = the rotation-ring kernel; the variant measured slower), 9 = work units per
  * resident warp the list planner aims for (default 8), 10 = list order: the j-atoms of a block's list that have no i-atom
- * within the cutoff itself (skin shell) go last, into chunks of their own (default 1). */
+ * within the cutoff itself (skin shell) go last, into chunks of their own (default 1), 11 = work units a pair-kernel warp takes
+ * before it retires (default 0 = persistent blocks fed by an atomic cursor; > 0 = short-lived blocks, which lets the side
+ * streams' kernels in between). */
 MDK_API int mdk_set_option(mdk_ctx *ctx, int key, double value);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);

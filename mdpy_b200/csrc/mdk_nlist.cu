@@ -379,6 +379,7 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
         }
         int nstage = 0, nfar = 0;
         const float R2m = g.R2 * (1.f + 2e-5f);    // the hoisted differences round differently from the pair kernel's
+        const float cwy = 1.f / g.inv_cw[1], cwz = 1.f / g.inv_cw[2];
         for (int iz = 0; iz < len[2]; ++iz) {
             int zz = lo[2] + iz; if (zz >= g.ncell[2]) zz -= g.ncell[2];
             for (int iy = 0; iy < len[1]; ++iy) {
@@ -387,6 +388,18 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                 // the x range in pieces that neither wrap around the box nor cross a domain cut: inside a piece
                 // the cells are consecutive keys, i.e. one contiguous run of the tile order
                 int xg = lo[0], rem = len[0];
+                {   // the row's own x range: what is left of R after the row's y / z distance from the bounding box (a sphere
+                    // around the box instead of a cube: a third fewer candidates); rows out of reach are skipped
+                    const float yc = (yy + 0.5f) * cwy - 0.5f * g.L[1], zc = (zz + 0.5f) * cwz - 0.5f * g.L[2];
+                    const float ry = fmaxf(fabsf(min_image(yc - cc[1], g.L[1], g.invL[1])) - hh[1] - 0.5f * cwy - 1e-3f - 1e-5f * g.L[1], 0.f);
+                    const float rz = fmaxf(fabsf(min_image(zc - cc[2], g.L[2], g.invL[2])) - hh[2] - 0.5f * cwz - 1e-3f - 1e-5f * g.L[2], 0.f);
+                    const float rem2 = R2m - ry * ry - rz * rz;
+                    if (rem2 < 0.f) continue;
+                    const float ext = hh[0] + sqrtf(rem2) + 1e-3f + 1e-5f * g.L[0];
+                    const int l0 = (int)floorf((cc[0] - ext + 0.5f * g.L[0]) * g.inv_cw[0]);
+                    const int h0 = (int)floorf((cc[0] + ext + 0.5f * g.L[0]) * g.inv_cw[0]);
+                    if (h0 - l0 + 1 < g.ncell[0]) { xg = imod(l0, g.ncell[0]); rem = h0 - l0 + 1; }
+                }
 #pragma unroll 1
                 while (rem > 0) {
                     int dlo, dhi;

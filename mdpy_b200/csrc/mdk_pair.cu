@@ -27,6 +27,7 @@ struct PairParams {
     // expression (a handful per step), so the pair set is the canonical one bit for bit
     float lj_lo, lj_hi, c_lo, c_hi, max_lo, max_hi;
     int n;
+    int max_units;              // work units a warp takes before it retires (0: until the cursor runs out — persistent blocks)
 };
 
 // debug instantiation of k_pair: every slot that passes the kernel's own cutoff / exclusion decision is
@@ -449,7 +450,7 @@ k_pair5(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n_units = *nl.n_units;
     long long e_lj_tot = 0, e_c_tot = 0;
-    for (;;) {
+    for (int taken = 0; P.max_units == 0 || taken < P.max_units; ++taken) {
         int u = 0;
         if (lane == 0) u = atomicAdd(cursor, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
@@ -483,7 +484,7 @@ k_pair(PairParams P, NlistView nl, const float4 *__restrict__ xs, const float4 *
     const int n_units = *nl.n_units;
     long long e_lj_tot = 0, e_c_tot = 0;
 
-    for (;;) {
+    for (int taken = 0; P.max_units == 0 || taken < P.max_units; ++taken) {
         int u = 0;
         if (lane == 0) u = atomicAdd(cursor, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
@@ -677,6 +678,15 @@ int pair_compute(mdk_ctx *c, bool do_lj, bool do_coul) {
     long long max_blocks = (c->stat_units + PAIR_WARPS - 1) / PAIR_WARPS;
     if (max_blocks < 1) max_blocks = 1;
     if (grid > max_blocks && !c->in_capture) grid = (int)max_blocks;   // a captured launch must fit any later list
+    P.max_units = c->pair_units_per_warp;
+    if (P.max_units > 0) {
+        // short-lived blocks: every warp retires after max_units work units, so SM resources come free all the time and the
+        // blocks of the (higher-priority) side streams — PME chain, O(N) terms, NCCL transfers — get in between
+        const long long units = c->in_capture ? (long long)c->cap_units : c->stat_units;
+        const long long per_block = (long long)PAIR_WARPS * P.max_units;
+        grid = (int)((units + per_block - 1) / per_block);
+        if (grid < 1) grid = 1;
+    }
     dim3 g(grid), b(PAIR_WARPS * 32);
     int *cursor = c->counters.p + 3;
     // inner graph steps do not report energies; the energy-less instantiation is only used where it

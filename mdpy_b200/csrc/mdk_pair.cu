@@ -21,6 +21,8 @@ struct PairParams {
     float rc2_lj, ron2, inv_ab3, rc2_max;  // CHARMM switch: (rc^2 - ron^2)^-3
     float rc2_c, alpha, two_alpha_over_sqrtpi;
     float sw_c0, sw_12inv;      // rc^2 - 3 ron^2, 12 (rc^2 - ron^2)^-3
+    float sw_s0, sw_s1;         // S = da^2 (sw_s0 + sw_s1 r^2): the two above times (rc^2 - ron^2)^-3
+    float alpha04;              // 0.4 alpha
     float alpha2_log2e;         // alpha^2 log2(e): exp(-alpha^2 r^2) = ex2(-alpha2_log2e r^2)
     // SHIFT kernels: r^2 computed on hoisted images differs from the canonical r^2 by a few ulp of the box
     // length; slots whose r^2 falls inside [lo, hi] around a cutoff are re-decided on the canonical
@@ -61,6 +63,20 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // erfc(x) * exp(x^2) ~= t * P(t), t = 1 / (1 + 0.4 x): degree-8 least-squares fit on
 // x in [0, 4.2], max relative error 8e-9 in exact arithmetic, <4e-7 evaluated in fp32
 // (fit script: oracle/fit_erfc.py).
+// r04a = 0.4 alpha (one FFMA for the argument): x = alpha r
+__device__ __forceinline__ float erfcx_poly_r(float r, float r04a) {
+    float t = rcp_approx(__fmaf_rn(r04a, r, 1.0f));
+    float p = 1.2938003984e-02f;
+    p = __fmaf_rn(p, t, 8.5587749120e-03f);
+    p = __fmaf_rn(p, t, -2.5232078617e-01f);
+    p = __fmaf_rn(p, t, 5.1394868547e-01f);
+    p = __fmaf_rn(p, t, -2.5095656442e-01f);
+    p = __fmaf_rn(p, t, 3.5446957253e-01f);
+    p = __fmaf_rn(p, t, 1.5382895656e-01f);
+    p = __fmaf_rn(p, t, 2.3447514612e-01f);
+    p = __fmaf_rn(p, t, 2.2505821879e-01f);
+    return p * t;
+}
 __device__ __forceinline__ float erfcx_poly(float x) {
     float t = rcp_approx(__fmaf_rn(0.4f, x, 1.0f));
     float p = 1.2938003984e-02f;
@@ -75,7 +91,15 @@ __device__ __forceinline__ float erfcx_poly(float x) {
     return p * t;
 }
 
-constexpr int PAIR_WARPS = 8;
+#ifndef MDK_PAIR_WARPS
+#define MDK_PAIR_WARPS 8
+#endif
+#ifndef MDK_PAIR_UNROLL
+#define MDK_PAIR_UNROLL 8
+#endif
+#define MDK_PRAGMA_(x) _Pragma(#x)
+#define MDK_UNROLL(n) MDK_PRAGMA_(unroll n)
+constexpr int PAIR_WARPS = MDK_PAIR_WARPS;
 
 // One chunk = 32 j-atoms against the warp's 32 i-atoms, 32 rotation steps.  MASKED chunks carry
 // exclusion / 1-4 bits (a few per i-block); the rest skip the bit tests entirely.
@@ -97,7 +121,7 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
     // the chunk is staged twice back to back (64 entries), so slot (lane + k) & 31 is entry lane + k: one
     // base address per lane, the rotation step is an immediate offset of the LDS
     sx += lane; slj += lane;
-#pragma unroll 8
+    MDK_UNROLL(MDK_PAIR_UNROLL)
     for (int k = 0; k < 32; ++k) {
         const float4 xj = sx[k];
         float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
@@ -145,7 +169,7 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
                     if (SWITCH) {
                         if (r2 > P.ron2) {
                             const float da = P.rc2_lj - r2;
-                            const float S = da * da * fmaf(2.f, r2, P.sw_c0) * P.inv_ab3;
+                            const float S = da * da * fmaf(P.sw_s1, r2, P.sw_s0);
                             const float dS = P.sw_12inv * da * (P.ron2 - r2);   // (dS/dr)/r
                             gl = fmaf(gl, S, e * dS);
                             e *= S;
@@ -159,7 +183,7 @@ __device__ __forceinline__ void chunk_loop(const PairParams &P, const float4 *__
                 if (ONECUT || r2d <= P.rc2_c) {
                     // erfc(x) = P(t) exp(-x^2):  E = qq P ex / r,  dE/dr / r = -qq ex (P / r + 2 alpha / sqrt(pi)) / r^2
                     const float u = xi.w * xj.w * ex2_approx(-P.alpha2_log2e * r2);
-                    const float v = erfcx_poly(P.alpha * (r2 * rinv)) * rinv;
+                    const float v = erfcx_poly_r(r2 * rinv, P.alpha04) * rinv;
                     if (ENERGY) e_c = fmaf(u, v, e_c);
                     g = fmaf(-u, (v + P.two_alpha_over_sqrtpi) * r2inv, g);
                 }
@@ -524,6 +548,8 @@ static PairParams make_pair_params(mdk_ctx *c, bool do_lj, bool do_coul) {
     P.alpha2_log2e = (float)(c->alpha * c->alpha * 1.4426950408889634);
     P.sw_c0 = P.rc2_lj - 3.f * P.ron2;
     P.sw_12inv = 12.f * P.inv_ab3;
+    P.sw_s0 = P.sw_c0 * P.inv_ab3; P.sw_s1 = 2.f * P.inv_ab3;
+    P.alpha04 = 0.4f * P.alpha;
     P.n = c->n;
     // decision band of the SHIFT kernels.  Hoisted coordinates carry <= 1.5 ulp(L) of rounding per atom and axis,
     // the canonical difference 0.5 ulp(L): |d' - d| <= 2 L 2^-23 per axis; delta takes 4x that.

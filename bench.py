@@ -42,7 +42,10 @@ CONFIGS = {
     # name: (generator key, cutoff, switch, pme grid, dt fs)
     'water_23k': dict(gen='water_23k', cutoff=9.0, switch=None, grid=(64, 64, 64), dt=2.0),
     'protein_92k': dict(gen='protein_92k', cutoff=12.0, switch=10.0, grid=(108, 108, 80), dt=2.0),
-    'protein_1m': dict(gen='protein_1m', cutoff=12.0, switch=10.0, grid=(216, 216, 216), dt=2.0),
+    # skin_multi: list skin of decomposed runs.  A rebuild of a decomposed job costs every rank the global sort and a state
+    # all-gather, and the skin shell is cheap for the pair kernel (far-class list order), so fewer, larger lists win there
+    # (N = 8: 1.114 -> 1.068 ms/step); on one GPU 2.0 A stays best (3.83 vs 3.98 ms).  Physics is the same either way.
+    'protein_1m': dict(gen='protein_1m', cutoff=12.0, switch=10.0, grid=(216, 216, 216), dt=2.0, skin_multi=3.0),
     # BASELINE configs[4]: 10 000 002-atom water box, 1 A skin (rebuild stress), PME 480^3.  Generates in ~25 s
     # on the host; NOT run on a GPU in round 1 (the multi-GPU budget went into the 1M box).
     'water_10m': dict(gen='water_10m', cutoff=9.0, switch=None, grid=(480, 480, 480), dt=2.0, skin=1.0),
@@ -219,7 +222,8 @@ class Workload:
         self.dev = self.ctx.dev
         self.kT = float((Quantity(TEMPERATURE, kelvin) * KB).convert_to(default_energy_unit).value)
         self.dt = cfg['dt']
-        self.skin = float(os.environ.get('MDK_SKIN', cfg.get('skin', 2.0)))   # experiments: MDK_SKIN=2.5
+        multi = int(os.environ.get('WORLD_SIZE', '1')) > 1 and args.impl != 'reference'
+        self.skin = float(os.environ.get('MDK_SKIN', cfg.get('skin_multi' if multi and 'skin_multi' in cfg else 'skin', 2.0)))   # experiments: MDK_SKIN=2.5
         if self.skin != 2.0:
             self.dev.set_nlist(self.skin)
         if args.no_graph:

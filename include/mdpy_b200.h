@@ -228,7 +228,8 @@ MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64
  * resident warp the list planner aims for (default 8), 10 = list order: the j-atoms of a block's list that have no i-atom
  * within the cutoff itself (skin shell) go last, into chunks of their own (default 1), 11 = work units a pair-kernel warp takes
  * before it retires (default 0 = persistent blocks fed by an atomic cursor; > 0 = short-lived blocks, which lets the side
- * streams' kernels in between). */
+ * streams' kernels in between), 12 = staging threshold of the list builder's far class (default 992 atoms per block part;
+ * tests lower it to drive the early-flush path). */
 MDK_API int mdk_set_option(mdk_ctx *ctx, int key, double value);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);

@@ -887,6 +887,7 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 9: c->unit_waves = value < 0.25 ? 0.25 : value; c->nlist_valid = false; break;   // work units per resident warp (list granularity)
         case 10: c->far_split = value != 0; c->nlist_valid = false; break;   // skin-shell j-atoms last in every block's list
         case 11: c->pair_units_per_warp = value < 0 ? 0 : (int)value; break;   // k_pair: work units per warp before it retires (0 = persistent)
+        case 12: c->far_flush = value < 32 ? 32 : (value > 992 ? 992 : (int)value); c->nlist_valid = false; break;   // list builder: far-class staging threshold
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

@@ -171,6 +171,7 @@ struct mdk_ctx {
     bool shift_ok = false;                    // box large enough to hoist the minimum image out of the pair loop
     int seg_chunks = 8;
     int pair_units_per_warp = 0;              // 0: persistent k_pair blocks; > 0: warps retire after this many work units (option 11)
+    int far_flush = 992;                      // far-class staging threshold of the list builder (option 12; tests lower it)
     bool far_split = true;                    // list order: skin-shell j-atoms in chunks of their own (option 10)
     double unit_waves = 8.0;                  // work units per resident warp the list planner aims for (option 9): the tail of a pair launch
                                               // is one unit long; 92k box: 347 us at 2 (12 chunks per unit), 305 us at 8 (3 chunks)

@@ -32,6 +32,7 @@ struct GridParams {
     float R, R2;
     float Rn2;            // class radius^2 of the list order: j-atoms with an i-atom of the block within it come first ("near"),
                           // the rest (skin shell only) last; < 0: one class
+    int far_flush;        // far-class staging: a chunk goes out early when more than this many atoms wait (<= FAR_CAP - 32)
     float skin_half2;
     float wide_lim[3];    // a block whose bounding-box half extent exceeds this on an axis is "wide": canonical minimum image
     DDGeom dd;            // cell numbering: domain by domain
@@ -465,7 +466,7 @@ k_build_lists(GridParams g, int n_parts, const float4 *__restrict__ xs, const fl
                             nfar += __popc(bal);
                         }
                         __syncwarp();
-                        if (nfar > FAR_CAP - 32) {       // buffer full: a chunk of far atoms goes out early
+                        if (nfar > g.far_flush) {       // buffer full: a chunk of far atoms goes out early
                             const int jj = farb[nfar - 32 + lane];
                             nfar -= 32;
                             __syncwarp();
@@ -510,6 +511,7 @@ static GridParams make_grid_params(mdk_ctx *c) {
     g.R = rc + c->skin;
     g.R2 = g.R * g.R;
     g.Rn2 = c->far_split ? rc * rc : -1.f;
+    g.far_flush = c->far_flush;
     for (int a = 0; a < 3; ++a) g.wide_lim[a] = 0.5f * c->box.L[a] - g.R - 0.05f;
     g.skin_half2 = 0.25f * c->skin * c->skin;
     g.dd = c->dd_geom;

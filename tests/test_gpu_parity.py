@@ -13,7 +13,7 @@ import pytest
 
 import mdpy_b200 as md
 from conftest import GOLDEN, load_golden, rel_rms
-from mdpy_b200 import synthetic
+from mdpy_b200 import _native, synthetic
 from mdpy_b200.constraint import (CharmmAngleConstraint, CharmmBondConstraint, CharmmDihedralConstraint,
                                   CharmmImproperConstraint, CharmmNonbondedConstraint, CharmmVDWConstraint,
                                   ElectrostaticConstraint, ElectrostaticPMEConstraint)
@@ -233,6 +233,28 @@ def test_pair_set_is_bit_exact():
         want = ora.pair_set_f32(ens.state.positions, np.float32(g['box']), float(g['rc']), g['bonded'])
         assert got.shape == want.shape, name
         assert np.array_equal(got, want), name
+
+
+@pytest.mark.parametrize('opts', [dict(far_split=0), dict(far_flush=32), dict(pair_units_per_warp=2), dict(far_flush=64, unit_waves=1)])
+def test_pair_set_and_forces_do_not_depend_on_list_options(opts):
+    """The list order (skin-shell atoms last, early flushes of their staging buffer), the work-unit granularity and the
+    block lifetime of the pair kernel are execution options: same pair set bit for bit, same forces to float32 summation order."""
+    g = load_golden('mix_small_f64')
+    def build(options):
+        ens = ensemble_from_golden(g)
+        lj = CharmmNonbondedConstraint(g['lj_table'], cutoff_radius=float(g['rc']))
+        ens.add_constraints(lj)
+        dev = _native.context_of(ens).dev
+        dev.set_nlist(4.0)            # a thick skin: a third of every list is far class
+        for k, v in options.items():
+            dev.set_option(k, v)
+        ens.update()
+        return lj.neighbor_pairs(), lj.forces.copy(), lj.potential_energy
+    p0, f0, e0 = build({})
+    p1, f1, e1 = build(opts)
+    want = ora.pair_set_f32(g['positions'].astype(np.float32), np.float32(g['box']), float(g['rc']), g['bonded'])
+    assert np.array_equal(p0, want) and np.array_equal(p1, want)
+    assert rel_rms(f1, f0) < 1e-6 and e1 == pytest.approx(e0, rel=1e-7)
 
 
 def test_q1_case_matches_bruteforce_truth_not_the_reference_defect():

@@ -254,7 +254,8 @@ def test_pair_set_and_forces_do_not_depend_on_list_options(opts):
     p1, f1, e1 = build(opts)
     want = ora.pair_set_f32(g['positions'].astype(np.float32), np.float32(g['box']), float(g['rc']), g['bonded'])
     assert np.array_equal(p0, want) and np.array_equal(p1, want)
-    assert rel_rms(f1, f0) < 1e-6 and e1 == pytest.approx(e0, rel=1e-7)
+    # (the LJ total of this box is a small difference of large pair terms: 2e-7 of it is float32 summation order)
+    assert rel_rms(f1, f0) < 1e-6 and e1 == pytest.approx(e0, rel=1e-5)
 
 
 def test_q1_case_matches_bruteforce_truth_not_the_reference_defect():

@@ -403,7 +403,7 @@ class Device:
     def set_option(self, key, value):
         """Execution options of mdk_set_option (include/mdpy_b200.h): 'graph', 'concurrent',
         'canonical_min_image', 'graph_energy', 'graph_nccl', 'pair_blocks_per_sm', 'pme_cufft', 'spread_smem'."""
-        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6, 'spread_smem': 7, 'pair_v5': 8, 'unit_waves': 9, 'far_split': 10, 'pair_units_per_warp': 11, 'far_flush': 12}[key]
+        k = {'graph': 0, 'concurrent': 1, 'canonical_min_image': 2, 'graph_energy': 3, 'graph_nccl': 4, 'pair_blocks_per_sm': 5, 'pme_cufft': 6, 'spread_smem': 7, 'pair_v5': 8, 'unit_waves': 9, 'far_split': 10, 'pair_units_per_warp': 11, 'far_flush': 12, 'dd_late_spread': 13, 'dd_early_recv': 14}[key]
         self._ck(self._lib.mdk_set_option(self._h, k, float(value)))
 
     def flush_l2(self):

@@ -888,6 +888,8 @@ int mdk_set_option(mdk_ctx *c, int key, double value) {
         case 10: c->far_split = value != 0; c->nlist_valid = false; break;   // skin-shell j-atoms last in every block's list
         case 11: c->pair_units_per_warp = value < 0 ? 0 : (int)value; break;   // k_pair: work units per warp before it retires (0 = persistent)
         case 12: c->far_flush = value < 32 ? 32 : (value > 992 ? 992 : (int)value); c->nlist_valid = false; break;   // list builder: far-class staging threshold
+        case 13: c->dd_late_spread = value != 0; break;   // decomposed step: the round-2a order (spread after the halo exchange)
+        case 14: c->dd_early_recv = value != 0; break;    // decomposed step: post the receive of the potential box before the pair kernel
         default: return fail(c, MDK_ERR_BAD_ARG, "mdk_set_option: unknown key %d", key);
     }
     ++c->graph_epoch;

@@ -71,8 +71,8 @@ int comm_exchange(mdk_ctx *c, const void *sbuf, void *rbuf, const Xfer *x, int n
     PhaseTimer pt(c, PH_COMM);
     int rc = g_nccl.group_start();
     for (int k = 0; k < nx && rc == 0; ++k) {
-        if (x[k].sbytes) rc = g_nccl.send(static_cast<const char *>(sbuf) + x[k].soff, x[k].sbytes, NCCL_INT8, x[k].peer, c->nccl_comm, c->stream);
-        if (rc == 0 && x[k].rbytes) rc = g_nccl.recv(static_cast<char *>(rbuf) + x[k].roff, x[k].rbytes, NCCL_INT8, x[k].peer, c->nccl_comm, c->stream);
+        if (x[k].sbytes) rc = g_nccl.send(x[k].sptr ? static_cast<const char *>(x[k].sptr) : static_cast<const char *>(sbuf) + x[k].soff, x[k].sbytes, NCCL_INT8, x[k].peer, c->nccl_comm, c->stream);
+        if (rc == 0 && x[k].rbytes) rc = g_nccl.recv(x[k].rptr ? static_cast<char *>(x[k].rptr) : static_cast<char *>(rbuf) + x[k].roff, x[k].rbytes, NCCL_INT8, x[k].peer, c->nccl_comm, c->stream);
     }
     int rc2 = g_nccl.group_end();
     if (rc == 0) rc = rc2;

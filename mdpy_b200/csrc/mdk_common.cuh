@@ -171,6 +171,8 @@ struct mdk_ctx {
     bool shift_ok = false;                    // box large enough to hoist the minimum image out of the pair loop
     int seg_chunks = 8;
     int pair_units_per_warp = 0;              // 0: persistent k_pair blocks; > 0: warps retire after this many work units (option 11)
+    bool dd_early_recv = false;               // decomposed step: potential boxes return on the side stream, receives posted before k_pair (option 14)
+    bool dd_late_spread = false;              // decomposed step: spread after the halo exchange, sub-meshes in an exchange of their own (option 13)
     int far_flush = 992;                      // far-class staging threshold of the list builder (option 12; tests lower it)
     bool far_split = true;                    // list order: skin-shell j-atoms in chunks of their own (option 10)
     double unit_waves = 8.0;                  // work units per resident warp the list planner aims for (option 9): the tail of a pair launch
@@ -323,7 +325,8 @@ int forces_enqueue(mdk_ctx *c, unsigned terms, bool clean_on_entry);
 void graph_destroy(mdk_ctx *c);
 int graph_finish(mdk_ctx *c);                        // counters / sticky errors of a queued graph run, after a sync
 int check_lost_flag(mdk_ctx *c);                     // flags[0] in the last read-back block -> MDK_ERR_PARTICLE_LOST
-struct Xfer { int peer; size_t soff, sbytes, roff, rbytes; };
+// sptr / rptr, when set, replace buffer base + offset (one grouped exchange over several buffers)
+struct Xfer { int peer; size_t soff, sbytes, roff, rbytes; const void *sptr = nullptr; void *rptr = nullptr; };
 int comm_exchange(mdk_ctx *c, const void *sbuf, void *rbuf, const Xfer *x, int nx);   // grouped ncclSend / ncclRecv
 int comm_allgather_i32(mdk_ctx *c, const int *mine, int *all, int count);
 int comm_allreduce_energies(mdk_ctx *c);

@@ -254,7 +254,8 @@ static int group_exchange(Group &g) {
             if (!px || px->sbytes != x.rbytes)
                 return fail(c, MDK_ERR_NCCL, "local exchange: rank %d expects %zu bytes from rank %d, which sends %zu", c->rank, x.rbytes,
                             x.peer, px ? px->sbytes : (size_t)0);
-            MDK_CUDA(c, cudaMemcpyAsync(c->dd->rbuf + x.roff, p->dd->sbuf + px->soff, x.rbytes, cudaMemcpyDeviceToDevice, c->stream));
+            MDK_CUDA(c, cudaMemcpyAsync(x.rptr ? x.rptr : c->dd->rbuf + x.roff, px->sptr ? px->sptr : p->dd->sbuf + px->soff, x.rbytes,
+                                        cudaMemcpyDeviceToDevice, c->stream));
         }
         ++c->dd->stat_exchanges;
     }
@@ -316,7 +317,9 @@ static void dd_mesh_boxes(mdk_ctx *c) {
         b.pts = 1;
         for (int a = 0; a < 3; ++a) {
             const double w = c->cellw[a], L = c->box.Ld[a];
-            const double x0 = cell_lo[a] * w - 0.5 * c->skin - 0.05 * w, x1 = cell_hi[a] * w + 0.5 * c->skin + 0.05 * w;
+            // (0.75 skin: the step that raises the rebuild flag spreads BEFORE the rebuild, with atoms up to skin/2 + one step's move from
+            // where the lists were built)
+            const double x0 = cell_lo[a] * w - 0.75 * c->skin - 0.05 * w, x1 = cell_hi[a] * w + 0.75 * c->skin + 0.05 * w;
             const int m = c->pme_n[a];
             int lo = (int)floor(x0 / L * m) - c->pme_order, hi = (int)floor(x1 / L * m) + 2;   // mesh index of x = -L/2 is 0
             int n = hi - lo + 1;
@@ -445,7 +448,8 @@ static int dd_rebuild(Group &g) {
 
 // ---------------------------------------------------------------------------------------------------------
 // one force evaluation of the whole job
-static int dd_halo_positions(Group &g, bool *rebuild) {
+// with_mesh: the sub-meshes (already spread and packed by dd_spread_pack) ride in the same grouped exchange
+static int dd_halo_positions(Group &g, bool *rebuild, bool with_mesh) {
     const int P = g[0]->nranks;
     for (mdk_ctx *c : g) {
         each_set_device(c);
@@ -462,6 +466,14 @@ static int dd_halo_positions(Group &g, bool *rebuild) {
                 d->xf.push_back(Xfer{r, d->send_off[r] * sizeof(float4), d->send_cnt[r] * sizeof(float4), d->need_off[r] * sizeof(float4),
                                      d->need_cnt[r] * sizeof(float4)});
             d->xf.push_back(Xfer{r, (size_t)(d->n_send + r) * sizeof(float4), sizeof(float4), (size_t)(d->n_need + r) * sizeof(float4), sizeof(float4)});
+        }
+        if (with_mesh) {
+            if (c->rank != d->pme_rank) {
+                d->xf.push_back(Xfer{d->pme_rank, 0, d->box[c->rank].pts * sizeof(float), 0, 0, d->m_send.p, nullptr});
+            } else {
+                for (int r = 0; r < P; ++r)
+                    if (r != c->rank) d->xf.push_back(Xfer{r, 0, 0, 0, d->box[r].pts * sizeof(float), nullptr, d->m_recv.p + d->box_off[r]});
+            }
         }
     }
     MDK_TRY(group_exchange(g));
@@ -489,19 +501,54 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
         return fail(g[0], MDK_ERR_BAD_ARG, "the all-pairs reference Coulomb sum (MDK_TERM_COUL_BARE) is not domain decomposed");
     bool rebuild = false;
     for (mdk_ctx *c : g) rebuild = rebuild || !c->nlist_valid || !c->xs_current;
+    const bool pme = terms & MDK_TERM_PME_RECIP;
+    const unsigned bonded_bits = terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER);
+    bool fresh = true;
+    for (mdk_ctx *c : g) fresh = fresh && c->dd->fresh;
+    // own charges onto the own mesh copy, the touched box packed for the mesh rank (needs the own atoms' positions only)
+    auto spread_pack = [&](bool add_xfers) -> int {
+        for (mdk_ctx *c : g) {
+            each_set_device(c);
+            MDK_TRY(pme_prepare(c));
+            DDState *d = c->dd;
+            if (d->box.empty()) dd_mesh_boxes(c);
+            MDK_TRY(pme_spread(c));
+            const bool mesh_rank = c->rank == d->pme_rank;
+            const size_t total_pts = d->box_off[P];
+            MDK_CUDA(c, d->m_send.reserve(mesh_rank ? total_pts : d->box[c->rank].pts));
+            MDK_CUDA(c, d->m_recv.reserve(mesh_rank ? total_pts : d->box[c->rank].pts));
+            if (add_xfers) {
+                d->sbuf = reinterpret_cast<const char *>(d->m_send.p);
+                d->rbuf = reinterpret_cast<char *>(d->m_recv.p);
+                d->xf.clear();
+            }
+            if (!mesh_rank) {
+                const SubBox &b = d->box[c->rank];
+                k_dd_mesh_pack<<<(unsigned)((b.pts + 255) / 256), 256, 0, c->stream>>>(box_arg(c, b), b.pts, c->grid_fix.p, d->m_send.p);
+                ++c->n_launches;
+                if (add_xfers) d->xf.push_back(Xfer{d->pme_rank, 0, b.pts * sizeof(float), 0, 0});
+            } else if (add_xfers) {
+                for (int r = 0; r < P; ++r)
+                    if (r != c->rank) d->xf.push_back(Xfer{r, 0, 0, d->box_off[r] * sizeof(float), d->box[r].pts * sizeof(float)});
+            }
+        }
+        return MDK_OK;
+    };
+    // the normal step: spread first, so that the sub-meshes travel with the halo positions in ONE grouped exchange (one
+    // rendezvous of the ranks less per step).  A rebuild that this very exchange announces comes after it: the spread then used
+    // the previous ownership, which is still a partition of all atoms, and the boxes carry the margin for it (dd_mesh_boxes).
+    const bool early = pme && P > 1 && !rebuild && !fresh && !g[0]->dd_late_spread;
+    // NCCL backend only: the potential boxes return on the side stream, their receives posted before the pair kernel
+    const bool early_recv = pme && P > 1 && !g[0]->dd->local && g[0]->dd_early_recv;
     trace_mark(g);
-    if (!rebuild) {
-        bool fresh = true;
-        for (mdk_ctx *c : g) fresh = fresh && c->dd->fresh;
-        if (!fresh) MDK_TRY(dd_halo_positions(g, &rebuild));
-    }
+    if (early) MDK_TRY(spread_pack(false));
+    trace_add(g, TP_AUX_SPREAD);
+    if (!rebuild && !fresh) MDK_TRY(dd_halo_positions(g, &rebuild, early));
     trace_add(g, TP_HALO_X);
     if (rebuild) MDK_TRY(dd_rebuild(g));
     trace_mark(g);
     if (rebuild || clear)
         for (mdk_ctx *c : g) { each_set_device(c); MDK_CUDA(c, cudaMemsetAsync(c->f_acc.p, 0, (size_t)c->n_pad * 3 * sizeof(long long), c->stream)); }
-    const bool pme = terms & MDK_TERM_PME_RECIP;
-    const unsigned bonded_bits = terms & (MDK_TERM_BOND | MDK_TERM_ANGLE | MDK_TERM_DIHEDRAL | MDK_TERM_IMPROPER);
     for (mdk_ctx *c : g) {
         each_set_device(c);
         c->dd->fresh = false;
@@ -517,31 +564,10 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
             c->stream = main_stream;
             MDK_TRY(rc);
         }
-        if (pme) {
-            MDK_TRY(pme_prepare(c));
-            DDState *d = c->dd;
-            if (d->box.empty()) dd_mesh_boxes(c);
-            MDK_TRY(pme_spread(c));
-            const bool mesh_rank = c->rank == d->pme_rank;
-            const size_t total_pts = d->box_off[P];
-            MDK_CUDA(c, d->m_send.reserve(mesh_rank ? total_pts : d->box[c->rank].pts));
-            MDK_CUDA(c, d->m_recv.reserve(mesh_rank ? total_pts : d->box[c->rank].pts));
-            d->sbuf = reinterpret_cast<const char *>(d->m_send.p);
-            d->rbuf = reinterpret_cast<char *>(d->m_recv.p);
-            d->xf.clear();
-            if (!mesh_rank) {
-                const SubBox &b = d->box[c->rank];
-                k_dd_mesh_pack<<<(unsigned)((b.pts + 255) / 256), 256, 0, c->stream>>>(box_arg(c, b), b.pts, c->grid_fix.p, d->m_send.p);
-                ++c->n_launches;
-                d->xf.push_back(Xfer{d->pme_rank, 0, b.pts * sizeof(float), 0, 0});
-            } else {
-                for (int r = 0; r < P; ++r)
-                    if (r != c->rank) d->xf.push_back(Xfer{r, 0, 0, d->box_off[r] * sizeof(float), d->box[r].pts * sizeof(float)});
-            }
-        }
     }
+    if (pme && !early) MDK_TRY(spread_pack(true));
     trace_add(g, TP_AUX_SPREAD);
-    if (pme && P > 1) MDK_TRY(group_exchange(g));
+    if (pme && P > 1 && !early) MDK_TRY(group_exchange(g));
     trace_add(g, TP_MESH_IN);
     for (mdk_ctx *c : g) {
         each_set_device(c);
@@ -566,12 +592,42 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
                     k_dd_mesh_extract<<<(unsigned)((b.pts + 255) / 256), 256, 0, c->stream>>>(box_arg(c, b), b.pts, c->grid_r.p, d->m_send.p + d->box_off[r]);
                 }
             c->n_launches += 1 + 2 * (P - 1);
+            if (rc == MDK_OK && early_recv) {     // the potential boxes leave from the side stream as soon as the mesh chain is through
+                d->xf.clear();
+                for (int r = 0; r < P; ++r)
+                    if (r != c->rank) d->xf.push_back(Xfer{r, d->box_off[r] * sizeof(float), d->box[r].pts * sizeof(float), 0, 0});
+                rc = comm_exchange(c, d->m_send.p, d->m_recv.p, d->xf.data(), (int)d->xf.size());
+                ++d->stat_exchanges;
+            }
+            cudaEventRecord(c->ev_pme, c->s_pme);
+            c->stream = main_stream;
+            MDK_TRY(rc);
+        } else if (early_recv) {
+            // the receive of this rank's potential box is posted on the side stream BEFORE the pair kernel is launched: the
+            // NCCL kernel holds its few CTAs while the persistent pair kernel fills the rest of the machine, and the box is
+            // there when the pair kernel ends (posted after it, the transfer would start only then)
+            const SubBox &b = d->box[c->rank];
+            MDK_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+            MDK_CUDA(c, cudaStreamWaitEvent(c->s_pme, c->ev_fork, 0));
+            c->stream = c->s_pme;
+            d->xf.clear();
+            d->xf.push_back(Xfer{d->pme_rank, 0, 0, 0, b.pts * sizeof(float)});
+            int rc = comm_exchange(c, d->m_send.p, d->m_recv.p, d->xf.data(), (int)d->xf.size());
+            ++d->stat_exchanges;
+            if (rc == MDK_OK) {
+                k_dd_mesh_put<<<(unsigned)((b.pts + 255) / 256), 256, 0, c->stream>>>(box_arg(c, b), b.pts, d->m_recv.p, c->grid_r.p);
+                ++c->n_launches;
+            }
             cudaEventRecord(c->ev_pme, c->s_pme);
             c->stream = main_stream;
             MDK_TRY(rc);
         }
         MDK_TRY(pair_compute(c, terms & MDK_TERM_LJ, terms & MDK_TERM_COUL_DIRECT));
-        if (pme) {
+        if (pme && early_recv) {
+            MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_pme, 0));
+        } else if (pme) {
+            d->sbuf = reinterpret_cast<const char *>(d->m_send.p);
+            d->rbuf = reinterpret_cast<char *>(d->m_recv.p);
             d->xf.clear();
             if (c->rank == d->pme_rank) {
                 MDK_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_pme, 0));
@@ -583,13 +639,13 @@ static int dd_forces(Group &g, unsigned terms, bool clear) {
         }
     }
     trace_add(g, TP_PAIR);
-    if (pme && P > 1) MDK_TRY(group_exchange(g));
+    if (pme && P > 1 && !early_recv) MDK_TRY(group_exchange(g));
     trace_add(g, TP_MESH_OUT);
     for (mdk_ctx *c : g) {
         each_set_device(c);
         DDState *d = c->dd;
         if (pme) {
-            if (c->rank != d->pme_rank) {
+            if (c->rank != d->pme_rank && !early_recv) {
                 const SubBox &b = d->box[c->rank];
                 k_dd_mesh_put<<<(unsigned)((b.pts + 255) / 256), 256, 0, c->stream>>>(box_arg(c, b), b.pts, d->m_recv.p, c->grid_r.p);
                 ++c->n_launches;

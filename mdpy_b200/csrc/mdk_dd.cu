@@ -10,9 +10,12 @@
 // Memory is replicated (every rank holds arrays for all N atoms: 1.2 GB at a million atoms, of 180 GB), but between
 // list rebuilds a rank's copy is CURRENT only for its own atoms and for its halo — the atoms of other domains that
 // its work units / terms reference.  Per step:
+//   0. PME spread       every rank spreads its own charges (own positions are current after the update) and packs the
+//                        sub-mesh it touched for the mesh rank
 //   1. halo positions   owner -> user   pack (index list) -> grouped ncclSend / ncclRecv of float4 -> unpack into xs;
 //                        a header word per message carries the sender's skin/2 flag, so after this exchange every
-//                        rank knows whether ANY atom in the job has moved too far (no separate collective)
+//                        rank knows whether ANY atom in the job has moved too far (no separate collective); the
+//                        sub-meshes of step 0 travel in the same group (one rendezvous of the ranks per step less)
 //   2. forces           pair kernel over own units, PME, bonded terms — all accumulate in int64 fixed point
 //   3. halo forces      user -> owner   pack -> grouped ncclSend / ncclRecv of int64 x 3 -> atomic add at the owner
 //   4. update           G-JF Langevin of the own atoms only

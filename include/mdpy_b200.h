@@ -230,7 +230,9 @@ MDK_API int mdk_force_accumulator(mdk_ctx *ctx, void **dev_ptr, int64_t *n_int64
  * before it retires (default 0 = persistent blocks fed by an atomic cursor; > 0 = short-lived blocks, which lets the side
  * streams' kernels in between), 12 = staging threshold of the list builder's far class (default 992 atoms per block part;
  * tests lower it to drive the early-flush path), 13 = decomposed step: spread after the halo exchange and send the sub-meshes in
- * an exchange of their own (default 0: spread first, sub-meshes and halo positions in one grouped exchange). */
+ * an exchange of their own (default 0: spread first, sub-meshes and halo positions in one grouped exchange), 14 = decomposed
+ * step, NCCL backend: the potential boxes return on the PME side stream and every rank posts its receive before it launches the
+ * pair kernel (default 0: measured no gain at 8 GPUs, 4 % slower at 2). */
 MDK_API int mdk_set_option(mdk_ctx *ctx, int key, double value);
 /* Benchmark hygiene: overwrite a 256 MB scratch buffer on the ctx stream (evicts the 126 MB L2). */
 MDK_API int mdk_flush_l2(mdk_ctx *ctx);
